@@ -1,0 +1,257 @@
+/*
+ * tpg_b200.h — C ABI of the B200-native pairwise-individual similarity path
+ * (KING-robust kinship, IBS, allele sharing, GRM) of tidypopgen.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no R / Rcpp /
+ * torch types.  Every entry point names the reference interface it replaces
+ * (paths relative to the tidypopgen source tree).
+ *
+ * Reference today                                   Replacement
+ * ------------------------------------------------  -----------------------------
+ * .Call(_tidypopgen_increment_king_numerator) once  ONE tpg_pairwise() per job
+ *   per loci block   src/RcppExports.cpp:256-275    (stat = TPG_STAT_KING)
+ *   kernel           src/snp_king.cpp:21-74
+ *   driver + finish  R/snp_king.R:32-103
+ * .Call(_tidypopgen_increment_ibs_counts)           tpg_pairwise(TPG_STAT_IBS_*)
+ *   src/RcppExports.cpp:276-292, src/snp_ibs.cpp:22-74, R/snp_ibs.R:42-104
+ * .Call(_tidypopgen_increment_as_counts)            tpg_pairwise(TPG_STAT_AS)
+ *   src/RcppExports.cpp:293-306, src/snp_as.cpp:22-67, R/snp_allele_sharing.R:33-82
+ * pairwise_grm post-processing R/pairwise_grm.R:42-50   tpg_pairwise(TPG_STAT_GRM),
+ *                                                       tpg_grm_from_as()
+ * CutBySize -> bigparallelr::split_len              tpg_split_len(), tpg_as_pad_count()
+ *   R/local_reimplementations.R:13-15
+ * bigstatsr::block_size(n)                          tpg_block_size()
+ *
+ * Index conventions are R's: ind_row / ind_col are 1-based, any order, any subset
+ * (R/snp_king.R:12-15); outputs are n x n column-major doubles where row/col k
+ * corresponds to ind_row[k].
+ *
+ * There is no CPU fallback: every compute entry point needs a B200 (sm_100a) and
+ * returns TPG_ERR_CUDA otherwise.
+ */
+#ifndef TPG_B200_H
+#define TPG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPG_ABI_VERSION 1
+
+/* ---- error codes (0 = success).  The message goes to the caller's err buffer;
+ * the R glue turns a non-zero code into Rcpp::stop(msg), mirroring myassert()
+ * -> Rcpp::exception -> END_RCPP in the reference (src/snp_king.cpp:11,63). */
+enum {
+  TPG_OK = 0,
+  TPG_ERR_ARG = 1,   /* bad argument / index out of range / short .bk          */
+  TPG_ERR_IO = 2,    /* cannot open / read the backing file                    */
+  TPG_ERR_CUDA = 3,  /* CUDA error, no device, or not an sm_100 device         */
+  TPG_ERR_NOMEM = 4, /* host or device allocation failed                       */
+  TPG_ERR_KERNEL = 5 /* device-side watchdog tripped (pipeline stall)          */
+};
+
+/* ---- statistics.  One job computes one of these. */
+enum {
+  TPG_STAT_KING = 0,           /* snp_king: out0 = KING-robust kinship           */
+  TPG_STAT_IBS_RAW = 1,        /* snp_ibs(type="raw_counts"): out0 = ibs, out1 = valid_n */
+  TPG_STAT_IBS_PROPORTION = 2, /* snp_ibs(type="proportion"):  out0 = ibs/valid_n */
+  TPG_STAT_IBS_ADJUSTED = 3,   /* snp_ibs(type="adjusted_counts"): out0 = prop*m  */
+  TPG_STAT_AS = 4,             /* snp_allele_sharing: out0 = allele sharing       */
+  TPG_STAT_GRM = 5             /* pairwise_grm: out0 = 2*(AS-mb)/(1-mb)           */
+};
+
+/* ---- where the FBM.code256 bytes live. */
+enum {
+  TPG_SRC_FILE = 0,  /* bk_path: the .bk backing file (R: X$backingfile)       */
+  TPG_SRC_HOST = 1,  /* bk_data: host pointer (e.g. the mmap bigstatsr holds)  */
+  TPG_SRC_DEVICE = 2 /* bk_data: device pointer, bytes already resident in HBM */
+};
+
+/* ---- how a multi-GPU job is partitioned ("Multi-GPU"). */
+enum {
+  TPG_SHARD_NONE = 0,
+  TPG_SHARD_LOCI = 1, /* this call sees loci shard_rank of shard_world (contiguous slices of ind_col) */
+  TPG_SHARD_TILES = 2 /* this call computes output blocks owned by shard_rank (all loci) */
+};
+
+/*
+ * One pairwise job.  Mirrors the arguments of snp_king / snp_ibs /
+ * snp_allele_sharing (R/snp_king.R:32-37, R/snp_ibs.R:42-48,
+ * R/snp_allele_sharing.R:33-38): X -> (src_kind, bk_*, nrow_total, ncol_total),
+ * ind.row -> ind_row, ind.col -> ind_col, block.size -> block_size,
+ * type -> stat.
+ */
+typedef struct tpg_job {
+  int32_t abi_version;   /* TPG_ABI_VERSION */
+  int32_t stat;          /* TPG_STAT_*      */
+  int32_t src_kind;      /* TPG_SRC_*       */
+  int32_t device;        /* CUDA device ordinal */
+  const char* bk_path;   /* TPG_SRC_FILE */
+  const uint8_t* bk_data; /* TPG_SRC_HOST / TPG_SRC_DEVICE: column-major nrow_total x ncol_total, 1 byte/genotype */
+  int64_t nrow_total;    /* nrow(X): individuals stored in the .bk */
+  int64_t ncol_total;    /* ncol(X): loci stored in the .bk        */
+  const int32_t* ind_row; /* 1-based; NULL = all rows in order     */
+  int64_t n;             /* length(ind.row)                        */
+  const int32_t* ind_col; /* 1-based; NULL = all columns in order  */
+  int64_t m;             /* length(ind.col)                        */
+  int64_t block_size;    /* R block.size; only affects allele sharing / GRM through the
+                            reference's padding quirk (src/snp_as.cpp:56-62); <=0 = bigstatsr default */
+  int32_t pad_quirk;     /* 1 = reproduce that quirk (reference-exact, default), 0 = mathematically clean */
+  int32_t shard_mode;    /* TPG_SHARD_* */
+  int32_t shard_rank;
+  int32_t shard_world;
+  int64_t gpu_chunk_loci; /* loci per GPU chunk (0 = auto).  Decoupled from block_size. */
+  int32_t flags;         /* TPG_FLAG_* */
+  int32_t reserved;
+} tpg_job;
+
+#define TPG_FLAG_PLANES_K_MAJOR 1 /* transpose in decode, K-major UMMA operands (default: MN-major) */
+#define TPG_FLAG_NO_OVERLAP 2     /* serialise copy / decode / gram (debugging)                      */
+
+/* Per-stage figures for the caller (R glue prints them when verbose). */
+typedef struct tpg_stats {
+  double ms_total;   /* wall time of the call                                       */
+  double ms_read;    /* host: disk/mmap -> pinned staging (summed over chunks)      */
+  double ms_h2d;     /* device: H2D copies  (CUDA events, summed)                   */
+  double ms_decode;  /* device: decode_planes kernels (CUDA events, summed)         */
+  double ms_gram;    /* device: gram_i8 kernels (CUDA events, summed)               */
+  double ms_finish;  /* device: finish kernels                                      */
+  double ms_d2h;     /* device: D2H of results                                      */
+  int64_t bytes_h2d;
+  int64_t bytes_d2h;
+  int64_t n_chunks;
+  int64_t n_launches; /* kernels launched by this library in the call               */
+  int64_t mma_macs;   /* int8 MACs issued to the tensor pipe (incl. padding)        */
+  int64_t n_short;    /* allele-sharing padding-quirk constant that was applied     */
+} tpg_stats;
+
+/*
+ * Results.  All matrices are caller-allocated, n x n, column-major (an R REALSXP,
+ * or the mmapped .bk of a bigstatsr::FBM(n, n) for raw_counts — R/snp_ibs.R:84-85).
+ * out0 is required; the others may be NULL.
+ *
+ *   stat            out0              out1       aux0 (optional)     aux1 (optional)
+ *   KING            kinship           -          KING numerator K    N_Aa_i (non-symmetric)
+ *   IBS_RAW         ibs counts        valid_n    -                   -
+ *   IBS_PROPORTION  ibs/valid_n       -          ibs counts          valid_n
+ *   IBS_ADJUSTED    ibs/valid_n * m   -          ibs counts          valid_n
+ *   AS              allele sharing    -          dos_tcross (num)    na_tcross (denom)
+ *   GRM             GRM               -          allele sharing      -
+ */
+typedef struct tpg_result {
+  double* out0;
+  double* out1;
+  double* aux0;
+  double* aux1;
+  int32_t out_on_device; /* 1 = the four pointers are device pointers (no D2H) */
+  int32_t reserved;
+  tpg_stats stats;
+} tpg_result;
+
+/* ------------------------------------------------------------------ host-only helpers */
+
+const char* tpg_version(void);
+
+/* Number of CUDA devices visible (0 on a CPU-only host; never fails). */
+int tpg_device_count(void);
+
+/* bigstatsr::block_size(n) with the default options(bigstatsr.block.sizeGB = 1):
+ * max(1, floor(2^30 / (8 n))).  Used as the default block.size by every
+ * wrapper (R/pairwise_king.R:36, R/snp_ibs.R:47, R/snp_allele_sharing.R:37). */
+int64_t tpg_block_size(int64_t n);
+
+/* CutBySize(m, block.size) = bigparallelr::split_len(m, nb_split = ceiling(m / block.size))
+ * (R/local_reimplementations.R:13-15).  Fills lower/upper/size (1-based, inclusive)
+ * for up to cap intervals; returns the number of intervals, or -1 on bad arguments. */
+int64_t tpg_split_len(int64_t m, int64_t block_size, int64_t* lower, int64_t* upper,
+                      int64_t* size, int64_t cap);
+
+/* Number of loci blocks shorter than the longest one = the constant the reference
+ * adds to every allele-sharing numerator (src/snp_as.cpp:56-64 with the scratch
+ * sized by R/snp_allele_sharing.R:55-56). */
+int64_t tpg_as_pad_count(int64_t m, int64_t block_size);
+
+/* ------------------------------------------------------------------ one call per job */
+
+/* Runs a whole job on job->device and writes the result matrices.
+ * Returns TPG_OK or an error code with a message in err (never partial results
+ * reported as success). */
+int tpg_pairwise(const tpg_job* job, tpg_result* res, char* err, size_t errlen);
+
+/* pairwise_grm(x, allele_sharing_mat = <precomputed>) — R/pairwise_grm.R:42-50.
+ * as_in / grm_out: n x n column-major host doubles (may alias). */
+int tpg_grm_from_as(int device, const double* as_in, int64_t n, double* grm_out, double* mb_out,
+                    char* err, size_t errlen);
+
+/* ------------------------------------------------------------------ staged interface
+ * Used by the sharding layer (one process per GPU): accumulate integer counts for a
+ * shard, combine them outside (NCCL all-reduce on the device buffer), then finish. */
+
+typedef struct tpg_ctx tpg_ctx;
+
+tpg_ctx* tpg_ctx_create(int device, char* err, size_t errlen);
+void tpg_ctx_destroy(tpg_ctx* ctx);
+
+/* Layout of the int32 count buffer for n individuals: TPG_NUM_COUNT_MATS matrices,
+ * each column-major with leading dimension ld = n_pad (X(i,j) at X[i + j*ld]);
+ * the symmetric ones (DD, NN, HH) only hold entries with i <= j (plus whatever else
+ * falls in the same 128x256 tile). */
+#define TPG_NUM_COUNT_MATS 4
+enum { TPG_MAT_DD = 0, TPG_MAT_NN = 1, TPG_MAT_HH = 2, TPG_MAT_HN = 3 };
+int64_t tpg_counts_ld(int64_t n);       /* n rounded up to the tile multiple       */
+int64_t tpg_counts_elems(int64_t n);    /* TPG_NUM_COUNT_MATS * ld * ld            */
+
+/* Adds the counts of job's loci (honouring shard_mode) into d_counts (device,
+ * tpg_counts_elems(n) int32, zeroed by the caller before the first call). */
+int tpg_accumulate(tpg_ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_stats* stats,
+                   char* err, size_t errlen);
+
+/* Turns counts into the job's statistic.  m = total loci over ALL shards,
+ * n_short = tpg_as_pad_count(m, block_size) (0 when pad_quirk is off). */
+int tpg_finish(tpg_ctx* ctx, const tpg_job* job, const int32_t* d_counts, tpg_result* res,
+               char* err, size_t errlen);
+
+/* ------------------------------------------------------------------ kernel-level entry
+ * points (device pointers; used by the parity tests and the profiler harness). */
+
+/* decode_planes: raw FBM bytes -> int8 indicator planes d (= hom-alt minus hom-ref,
+ * -1/0/+1), NM (non-missing, 0/1), H1 (het, 0/1).  Replaces the decode loops
+ * src/snp_king.cpp:45-58, src/snp_ibs.cpp:45-56, src/snp_as.cpp:44-53 and the
+ * SubBMAcc gather (src/snp_king.cpp:35).
+ *   d_raw      : device, column-major bytes, column stride raw_stride
+ *   d_row_idx  : device, 0-based rows (NULL = rows row0 .. row0+n-1)
+ *   d_col_idx  : device, 0-based raw columns per chunk locus (NULL = col0 .. col0+lc-1)
+ *   d_planes   : device, 3 planes, plane p at d_planes + p*plane_stride
+ *   layout     : MN-major (default): plane[l*ld + i], ld = n_pad, lc_pad rows
+ *                K-major (k_major=1): plane[i*ld + l], ld = lc_pad, n_pad rows
+ * Padding rows/loci are written as zeros. */
+int tpg_decode_planes(tpg_ctx* ctx, const uint8_t* d_raw, int64_t raw_bytes, int64_t raw_stride,
+                      const int32_t* d_row_idx, int64_t row0, int64_t n, int64_t n_pad,
+                      const int32_t* d_col_idx, int64_t col0, int64_t lc, int64_t lc_pad,
+                      int8_t* d_planes, int64_t plane_stride, int32_t k_major,
+                      char* err, size_t errlen);
+
+/* gram_i8: int8 tcgen05 Gram products of the planes into the int32 count buffer
+ * (atomic adds, so calls accumulate).  Replaces the dsyrk/dgemm products
+ * src/snp_king.cpp:70-72, src/snp_ibs.cpp:67-72, src/snp_as.cpp:64-65.
+ * prod_mask: bit TPG_MAT_* set = compute that product. */
+int tpg_gram(tpg_ctx* ctx, const int8_t* d_planes, int64_t plane_stride, int64_t n_pad,
+             int64_t lc_pad, int32_t k_major, int32_t prod_mask, int32_t shard_rank,
+             int32_t shard_world, int32_t* d_counts, float* ms_out, char* err, size_t errlen);
+
+/* Deterministic synthetic genotypes (counter-based hash RNG; oracle/synth.c is the
+ * CPU twin, byte-identical): fills column-major nrow x ncol bytes on the device. */
+int tpg_synth_fill(tpg_ctx* ctx, uint8_t* d_raw, int64_t nrow, int64_t ncol, int64_t col_offset,
+                   uint64_t seed, double missing_rate, int32_t mode, char* err, size_t errlen);
+
+/* Host twin of tpg_synth_fill (byte-identical; include/tpg_synth.h holds the hash). */
+void tpg_synth_fill_host(uint8_t* raw, int64_t nrow, int64_t ncol, int64_t col_offset,
+                         uint64_t seed, double missing_rate, int32_t mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPG_B200_H */

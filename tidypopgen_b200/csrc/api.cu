@@ -1,0 +1,748 @@
+// C-ABI of libtpg_b200.so (include/tpg_b200.h): job validation, the .bk chunk streamer
+// (disk/mmap -> pinned staging -> HBM, double buffered against decode + gram), the staged
+// accumulate/finish interface used by the sharding layer, and kernel-level entry points.
+//
+// Replaces the per-block R loop + .Call of the reference (R/snp_king.R:63-77,
+// R/snp_ibs.R:69-83, R/snp_allele_sharing.R:58-70) by ONE call per job; the GPU chunk
+// size is decoupled from R's block.size (which only survives as the allele-sharing
+// padding constant, see tpg_as_pad_count).
+#include <algorithm>
+#include <cerrno>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <fcntl.h>
+#include <mutex>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include "internal.h"
+#include "../../include/tpg_synth.h"
+
+namespace tpg {
+
+int Err::fail(int code, const char* fmt, ...) const {
+  if (buf && len) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, len, fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+static double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------ host helpers
+
+int64_t block_size_default(int64_t n) {
+  if (n <= 0) return 1;
+  const double b = std::floor(1073741824.0 / (8.0 * double(n)));
+  return b < 1.0 ? 1 : int64_t(b);
+}
+
+// bigparallelr::split_len(total_len = m, nb_split = ceiling(m / block.size)):
+//   nb clamped to [1, m]; int = m / nb (double); upper = round(1:nb * int) with R's
+//   half-to-even rounding; lower = c(1, upper[-nb] + 1); size = c(upper[1], diff(upper)).
+int64_t split_len(int64_t m, int64_t block_size, int64_t* lower, int64_t* upper, int64_t* size,
+                  int64_t cap) {
+  if (m <= 0 || block_size <= 0) return -1;
+  int64_t nb = int64_t(std::ceil(double(m) / double(block_size)));
+  if (nb > m) nb = m;
+  if (nb <= 0) nb = 1;
+  const double step = double(m) / double(nb);
+  int64_t prev = 0;
+  for (int64_t k = 1; k <= nb; ++k) {
+    const int64_t up = int64_t(std::nearbyint(double(k) * step));  // FE_TONEAREST = half-even
+    if (k - 1 < cap) {
+      if (lower) lower[k - 1] = prev + 1;
+      if (upper) upper[k - 1] = up;
+      if (size) size[k - 1] = up - prev;
+    }
+    prev = up;
+  }
+  return nb;
+}
+
+int64_t as_pad_count(int64_t m, int64_t block_size) {
+  if (m <= 0 || block_size <= 0) return 0;
+  int64_t nb = int64_t(std::ceil(double(m) / double(block_size)));
+  if (nb > m) nb = m;
+  if (nb <= 0) nb = 1;
+  const double step = double(m) / double(nb);
+  int64_t prev = 0, mx = 0;
+  for (int64_t k = 1; k <= nb; ++k) {
+    const int64_t up = int64_t(std::nearbyint(double(k) * step));
+    mx = std::max(mx, up - prev);
+    prev = up;
+  }
+  prev = 0;
+  int64_t n_short = 0;
+  for (int64_t k = 1; k <= nb; ++k) {
+    const int64_t up = int64_t(std::nearbyint(double(k) * step));
+    if (up - prev < mx) ++n_short;
+    prev = up;
+  }
+  return n_short;
+}
+
+static int64_t round_up(int64_t x, int64_t q) { return (x + q - 1) / q * q; }
+
+// ------------------------------------------------------------------ context
+
+static int ctx_init(Ctx* c, int device, const Err& E) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return E.fail(TPG_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return E.fail(TPG_ERR_ARG, "device %d out of range [0,%d)", device, ndev);
+  TPG_CUDA_OK(cudaSetDevice(device), E);
+  cudaDeviceProp prop;
+  TPG_CUDA_OK(cudaGetDeviceProperties(&prop, device), E);
+  if (prop.major != 10)
+    return E.fail(TPG_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                  device, prop.major, prop.minor);
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  TPG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking), E);
+  TPG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking), E);
+  TPG_CUDA_OK(cudaMalloc(&c->d_err_flag, sizeof(int)), E);
+  TPG_CUDA_OK(cudaMemset(c->d_err_flag, 0, sizeof(int)), E);
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+    return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  c->encode_tiled = fn;
+  return TPG_OK;
+}
+
+int check_err_flag(Ctx* ctx, const Err& E) {
+  int flag = 0;
+  cudaError_t e = cudaMemcpy(&flag, ctx->d_err_flag, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return E.fail(TPG_ERR_CUDA, "device error: %s", cudaGetErrorString(e));
+  if (flag) return E.fail(TPG_ERR_KERNEL, "gram_i8 pipeline watchdog tripped (role %d)", flag);
+  return TPG_OK;
+}
+
+// ------------------------------------------------------------------ job plumbing
+
+struct Plan {
+  // rows
+  bool rows_contig = true;
+  int64_t row0 = 0;
+  std::vector<int32_t> rows0;  // 0-based (gather mode)
+  // loci of this shard, 0-based raw columns, in job order
+  bool cols_contig = true;
+  int64_t col0 = 0;
+  std::vector<int32_t> cols0;
+  int64_t n = 0, n_pad = 0, m_shard = 0;
+  int prod_mask = 0;
+  int nplanes = 3;
+};
+
+static int prod_mask_for(int stat) {
+  switch (stat) {
+    case TPG_STAT_KING: return (1 << TPG_MAT_DD) | (1 << TPG_MAT_NN) | (1 << TPG_MAT_HN);
+    case TPG_STAT_IBS_RAW:
+    case TPG_STAT_IBS_PROPORTION:
+    case TPG_STAT_IBS_ADJUSTED: return (1 << TPG_MAT_DD) | (1 << TPG_MAT_NN) | (1 << TPG_MAT_HH);
+    case TPG_STAT_AS:
+    case TPG_STAT_GRM: return (1 << TPG_MAT_DD) | (1 << TPG_MAT_NN);
+    default: return 0;
+  }
+}
+
+static int make_plan(const tpg_job* job, Plan* pl, const Err& E) {
+  if (!job) return E.fail(TPG_ERR_ARG, "job is NULL");
+  if (job->abi_version != TPG_ABI_VERSION)
+    return E.fail(TPG_ERR_ARG, "ABI version mismatch: job %d, library %d", job->abi_version, TPG_ABI_VERSION);
+  if (job->nrow_total <= 0 || job->ncol_total <= 0)
+    return E.fail(TPG_ERR_ARG, "X has no rows or columns (%lld x %lld)", (long long)job->nrow_total,
+                  (long long)job->ncol_total);
+  pl->prod_mask = prod_mask_for(job->stat);
+  if (!pl->prod_mask) return E.fail(TPG_ERR_ARG, "unknown stat %d", job->stat);
+  pl->nplanes = (pl->prod_mask & ((1 << TPG_MAT_HH) | (1 << TPG_MAT_HN))) ? 3 : 2;
+  const int64_t n = job->ind_row ? job->n : job->nrow_total;
+  const int64_t m = job->ind_col ? job->m : job->ncol_total;
+  if (n <= 0 || m <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row or ind.col (n=%lld, m=%lld)", (long long)n, (long long)m);
+  if (n > (int64_t(1) << 24)) return E.fail(TPG_ERR_ARG, "n=%lld exceeds the supported 2^24 individuals", (long long)n);
+  pl->n = n;
+  pl->n_pad = round_up(n, kRowPad);
+  // rows: R semantics, 1-based, no negatives (R/snp_king.R:12-15); bounds as SubBMAcc checks them
+  if (job->ind_row) {
+    bool contig = true;
+    for (int64_t k = 0; k < n; ++k) {
+      const int64_t r = job->ind_row[k];
+      if (r < 1 || r > job->nrow_total)
+        return E.fail(TPG_ERR_ARG, "ind.row[%lld] = %lld is out of bounds [1, %lld]", (long long)(k + 1),
+                      (long long)r, (long long)job->nrow_total);
+      if (r != int64_t(job->ind_row[0]) + k) contig = false;
+    }
+    pl->rows_contig = contig;
+    if (contig) {
+      pl->row0 = job->ind_row[0] - 1;
+    } else {
+      pl->rows0.resize(n);
+      for (int64_t k = 0; k < n; ++k) pl->rows0[k] = job->ind_row[k] - 1;
+    }
+  } else {
+    pl->rows_contig = true;
+    pl->row0 = 0;
+  }
+  // loci of this shard
+  int64_t c_lo = 0, c_hi = m;
+  if (job->shard_mode == TPG_SHARD_LOCI && job->shard_world > 1) {
+    if (job->shard_rank < 0 || job->shard_rank >= job->shard_world)
+      return E.fail(TPG_ERR_ARG, "shard_rank %d out of range", job->shard_rank);
+    c_lo = m * job->shard_rank / job->shard_world;
+    c_hi = m * (job->shard_rank + 1) / job->shard_world;
+  } else if (job->shard_mode == TPG_SHARD_TILES && job->shard_world > 1) {
+    if (job->shard_rank < 0 || job->shard_rank >= job->shard_world)
+      return E.fail(TPG_ERR_ARG, "shard_rank %d out of range", job->shard_rank);
+  }
+  pl->m_shard = c_hi - c_lo;
+  if (job->ind_col) {
+    bool contig = true;
+    for (int64_t k = 0; k < m; ++k) {
+      const int64_t c = job->ind_col[k];
+      if (c < 1 || c > job->ncol_total)
+        return E.fail(TPG_ERR_ARG, "ind.col[%lld] = %lld is out of bounds [1, %lld]", (long long)(k + 1),
+                      (long long)c, (long long)job->ncol_total);
+    }
+    for (int64_t k = c_lo; k < c_hi; ++k)
+      if (job->ind_col[k] != int64_t(job->ind_col[c_lo]) + (k - c_lo)) { contig = false; break; }
+    pl->cols_contig = contig;
+    if (pl->m_shard > 0) {
+      if (contig) {
+        pl->col0 = job->ind_col[c_lo] - 1;
+      } else {
+        pl->cols0.resize(pl->m_shard);
+        for (int64_t k = c_lo; k < c_hi; ++k) pl->cols0[k - c_lo] = job->ind_col[k] - 1;
+      }
+    }
+  } else {
+    pl->cols_contig = true;
+    pl->col0 = c_lo;
+  }
+  return TPG_OK;
+}
+
+struct Mapped {
+  const uint8_t* base = nullptr;
+  size_t bytes = 0;
+  int fd = -1;
+  bool owned = false;
+  ~Mapped() {
+    if (owned && base) munmap(const_cast<uint8_t*>(base), bytes);
+    if (fd >= 0) close(fd);
+  }
+};
+
+static int open_source(const tpg_job* job, Mapped* mp, const Err& E) {
+  const int64_t need = job->nrow_total * job->ncol_total;
+  if (job->src_kind == TPG_SRC_FILE) {
+    if (!job->bk_path) return E.fail(TPG_ERR_ARG, "bk_path is NULL");
+    mp->fd = open(job->bk_path, O_RDONLY);
+    if (mp->fd < 0) return E.fail(TPG_ERR_IO, "cannot open backing file '%s': %s", job->bk_path, strerror(errno));
+    struct stat sb;
+    if (fstat(mp->fd, &sb) != 0) return E.fail(TPG_ERR_IO, "fstat('%s') failed: %s", job->bk_path, strerror(errno));
+    if (int64_t(sb.st_size) < need)
+      return E.fail(TPG_ERR_ARG, "backing file '%s' has %lld bytes, %lld x %lld needs %lld", job->bk_path,
+                    (long long)sb.st_size, (long long)job->nrow_total, (long long)job->ncol_total, (long long)need);
+    void* p = mmap(nullptr, size_t(need), PROT_READ, MAP_PRIVATE, mp->fd, 0);
+    if (p == MAP_FAILED) return E.fail(TPG_ERR_IO, "mmap('%s') failed: %s", job->bk_path, strerror(errno));
+    madvise(p, size_t(need), MADV_SEQUENTIAL);
+    mp->base = static_cast<const uint8_t*>(p);
+    mp->bytes = size_t(need);
+    mp->owned = true;
+    return TPG_OK;
+  }
+  if (job->src_kind == TPG_SRC_HOST || job->src_kind == TPG_SRC_DEVICE) {
+    if (!job->bk_data) return E.fail(TPG_ERR_ARG, "bk_data is NULL");
+    mp->base = job->bk_data;
+    mp->bytes = size_t(need);
+    return TPG_OK;
+  }
+  return E.fail(TPG_ERR_ARG, "unknown src_kind %d", job->src_kind);
+}
+
+// RAII bundle of the per-job device / pinned buffers.
+struct Buffers {
+  uint8_t* d_raw[2] = {nullptr, nullptr};
+  int8_t* d_planes[2] = {nullptr, nullptr};
+  uint8_t* h_pin[2] = {nullptr, nullptr};
+  int32_t* d_rows = nullptr;
+  int32_t* d_cols = nullptr;
+  std::vector<cudaEvent_t> events;
+  ~Buffers() {
+    for (int b = 0; b < 2; ++b) {
+      if (d_raw[b]) cudaFree(d_raw[b]);
+      if (d_planes[b]) cudaFree(d_planes[b]);
+      if (h_pin[b]) cudaFreeHost(h_pin[b]);
+    }
+    if (d_rows) cudaFree(d_rows);
+    if (d_cols) cudaFree(d_cols);
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+  }
+  cudaEvent_t ev(bool timing) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming);
+    events.push_back(e);
+    return e;
+  }
+};
+
+static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_stats* st,
+                           const Err& E) {
+  const double t_begin = now_ms();
+  Plan pl;
+  int rc = make_plan(job, &pl, E);
+  if (rc) return rc;
+  TPG_CUDA_OK(cudaSetDevice(ctx->device), E);
+  if (pl.m_shard <= 0) return TPG_OK;  // more ranks than loci: nothing to add
+  Mapped src;
+  rc = open_source(job, &src, E);
+  if (rc) return rc;
+
+  const bool on_device = job->src_kind == TPG_SRC_DEVICE;
+  const bool k_major = (job->flags & TPG_FLAG_PLANES_K_MAJOR) != 0;
+  const bool no_overlap = (job->flags & TPG_FLAG_NO_OVERLAP) != 0;
+  const int64_t nrow = job->nrow_total;
+
+  // Rows actually needed from each raw column: [rlo, rhi).  Staging copies only that span.
+  int64_t rlo = pl.row0, rhi = pl.row0 + pl.n;
+  if (!pl.rows_contig) {
+    rlo = nrow; rhi = 0;
+    for (int32_t r : pl.rows0) { rlo = std::min<int64_t>(rlo, r); rhi = std::max<int64_t>(rhi, r + 1); }
+  }
+  const int64_t span = on_device ? nrow : rhi - rlo;  // bytes per staged column
+
+  // ---- chunk size (loci per GPU chunk), decoupled from R's block.size
+  size_t free_b = 0, total_b = 0;
+  TPG_CUDA_OK(cudaMemGetInfo(&free_b, &total_b), E);
+  int64_t lc = job->gpu_chunk_loci;
+  const int64_t per_locus = (on_device ? 0 : 2 * span) + 2 * int64_t(pl.nplanes) * pl.n_pad;
+  const int64_t mem_cap = std::max<int64_t>(kLociPad, int64_t(double(free_b) * 0.45 / double(per_locus)));
+  if (lc <= 0) {
+    if (on_device) lc = int64_t(1) << 20;
+    else lc = std::max<int64_t>(8192, (int64_t(256) << 20) / std::max<int64_t>(span, 1));
+  }
+  lc = std::min(lc, mem_cap);
+  lc = std::min(lc, round_up(pl.m_shard, kLociPad));
+  lc = std::max<int64_t>(kLociPad, lc / kLociPad * kLociPad);
+  const int64_t n_chunks = (pl.m_shard + lc - 1) / lc;
+  const int64_t plane_stride = pl.n_pad * lc;
+
+  Buffers B;
+  for (int b = 0; b < 2 && b < n_chunks; ++b) {
+    if (cudaMalloc(&B.d_planes[b], size_t(plane_stride) * pl.nplanes) != cudaSuccess)
+      return E.fail(TPG_ERR_NOMEM, "cannot allocate %lld bytes of plane storage", (long long)plane_stride * pl.nplanes);
+    if (!on_device) {
+      if (cudaMalloc(&B.d_raw[b], size_t(span * lc) + 16) != cudaSuccess)
+        return E.fail(TPG_ERR_NOMEM, "cannot allocate %lld bytes of raw chunk storage", (long long)(span * lc));
+      if (cudaMallocHost(&B.h_pin[b], size_t(span * lc)) != cudaSuccess)
+        return E.fail(TPG_ERR_NOMEM, "cannot allocate %lld bytes of pinned staging", (long long)(span * lc));
+    }
+  }
+  if (!pl.rows_contig) {
+    // staged columns start at raw row rlo
+    std::vector<int32_t> rel(pl.rows0);
+    if (!on_device) for (auto& r : rel) r -= int32_t(rlo);
+    TPG_CUDA_OK(cudaMalloc(&B.d_rows, sizeof(int32_t) * pl.n), E);
+    TPG_CUDA_OK(cudaMemcpy(B.d_rows, rel.data(), sizeof(int32_t) * pl.n, cudaMemcpyHostToDevice), E);
+  }
+  if (on_device && !pl.cols_contig) {
+    TPG_CUDA_OK(cudaMalloc(&B.d_cols, sizeof(int32_t) * pl.m_shard), E);
+    TPG_CUDA_OK(cudaMemcpy(B.d_cols, pl.cols0.data(), sizeof(int32_t) * pl.m_shard, cudaMemcpyHostToDevice), E);
+  }
+
+  cudaEvent_t ev_h2d_done[2] = {B.ev(false), B.ev(false)};
+  cudaEvent_t ev_dec_done[2] = {B.ev(false), B.ev(false)};
+  struct Tm { cudaEvent_t c0, c1, d0, d1, g1; };
+  std::vector<Tm> tm(n_chunks);
+  int64_t macs = 0;
+  double ms_read = 0;
+
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int b = int(c & 1);
+    const int64_t k0 = c * lc, k1 = std::min(pl.m_shard, k0 + lc);
+    const int64_t lcc = k1 - k0;
+    const int64_t lc_pad = round_up(lcc, kLociPad);
+    tm[c] = {B.ev(true), B.ev(true), B.ev(true), B.ev(true), B.ev(true)};
+
+    DecodeArgs da;
+    da.n = pl.n;
+    da.n_pad = pl.n_pad;
+    da.lc = lcc;
+    da.lc_pad = lc_pad;
+    da.planes = B.d_planes[b];
+    // planes of a short last chunk keep the full-chunk plane stride (one allocation)
+    da.plane_stride = plane_stride;
+    da.nplanes = pl.nplanes;
+    da.k_major = k_major;
+    da.row_idx = B.d_rows;
+    if (on_device) {
+      da.raw = src.base;
+      da.raw_bytes = int64_t(src.bytes);
+      da.raw_stride = nrow;
+      da.row0 = pl.row0;
+      da.col_idx = pl.cols_contig ? nullptr : B.d_cols + k0;
+      da.col0 = pl.col0 + k0;
+      TPG_CUDA_OK(cudaEventRecord(tm[c].c0, ctx->s_copy), E);
+      TPG_CUDA_OK(cudaEventRecord(tm[c].c1, ctx->s_copy), E);
+    } else {
+      // ---- stage the chunk's columns into pinned memory (compact, rows [rlo, rhi) only)
+      if (c >= 2) TPG_CUDA_OK(cudaEventSynchronize(ev_h2d_done[b]), E);
+      const double t0 = now_ms();
+      uint8_t* hp = B.h_pin[b];
+      if (pl.cols_contig && span == nrow) {
+        memcpy(hp, src.base + (pl.col0 + k0) * nrow, size_t(lcc * nrow));
+      } else {
+        for (int64_t k = k0; k < k1; ++k) {
+          const int64_t col = pl.cols_contig ? pl.col0 + k : pl.cols0[k];
+          memcpy(hp + (k - k0) * span, src.base + col * nrow + rlo, size_t(span));
+        }
+      }
+      ms_read += now_ms() - t0;
+      // ---- H2D on the copy stream, after the decode that last read this raw buffer
+      if (c >= 2) TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_copy, ev_dec_done[b], 0), E);
+      TPG_CUDA_OK(cudaEventRecord(tm[c].c0, ctx->s_copy), E);
+      TPG_CUDA_OK(cudaMemcpyAsync(B.d_raw[b], hp, size_t(lcc * span), cudaMemcpyHostToDevice, ctx->s_copy), E);
+      TPG_CUDA_OK(cudaEventRecord(tm[c].c1, ctx->s_copy), E);
+      TPG_CUDA_OK(cudaEventRecord(ev_h2d_done[b], ctx->s_copy), E);
+      TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ev_h2d_done[b], 0), E);
+      st->bytes_h2d += lcc * span;
+      da.raw = B.d_raw[b];
+      da.raw_bytes = lcc * span;
+      da.raw_stride = span;
+      da.row0 = pl.rows_contig ? pl.row0 - rlo : 0;
+      da.col_idx = nullptr;
+      da.col0 = 0;
+    }
+    TPG_CUDA_OK(cudaEventRecord(tm[c].d0, ctx->s_compute), E);
+    rc = launch_decode(ctx, da, ctx->s_compute, E);
+    if (rc) return rc;
+    TPG_CUDA_OK(cudaEventRecord(tm[c].d1, ctx->s_compute), E);
+    TPG_CUDA_OK(cudaEventRecord(ev_dec_done[b], ctx->s_compute), E);
+
+    GramArgs ga;
+    ga.planes = B.d_planes[b];
+    ga.plane_stride = plane_stride;
+    ga.n = pl.n;
+    ga.n_pad = pl.n_pad;
+    ga.lc_pad = lc_pad;
+    ga.k_major = k_major;
+    ga.prod_mask = pl.prod_mask;
+    ga.shard_rank = job->shard_mode == TPG_SHARD_TILES ? job->shard_rank : 0;
+    ga.shard_world = job->shard_mode == TPG_SHARD_TILES ? job->shard_world : 1;
+    ga.counts = d_counts;
+    ga.ld = pl.n_pad;
+    int64_t mm = 0;
+    rc = launch_gram(ctx, ga, ctx->s_compute, &mm, E);
+    if (rc) return rc;
+    macs += mm;
+    TPG_CUDA_OK(cudaEventRecord(tm[c].g1, ctx->s_compute), E);
+    if (no_overlap) TPG_CUDA_OK(cudaStreamSynchronize(ctx->s_compute), E);
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->s_compute);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_copy);
+  if (e != cudaSuccess) {
+    Err quiet{nullptr, 0};
+    if (check_err_flag(ctx, quiet) == TPG_ERR_KERNEL) return check_err_flag(ctx, E);
+    return E.fail(TPG_ERR_CUDA, "accumulate failed on device: %s", cudaGetErrorString(e));
+  }
+  rc = check_err_flag(ctx, E);
+  if (rc) return rc;
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, tm[c].c0, tm[c].c1); st->ms_h2d += ms;
+    cudaEventElapsedTime(&ms, tm[c].d0, tm[c].d1); st->ms_decode += ms;
+    cudaEventElapsedTime(&ms, tm[c].d1, tm[c].g1); st->ms_gram += ms;
+  }
+  st->ms_read += ms_read;
+  st->n_chunks += n_chunks;
+  st->mma_macs += macs;
+  st->ms_total += now_ms() - t_begin;
+  return TPG_OK;
+}
+
+static int finish_impl(Ctx* ctx, const tpg_job* job, const int32_t* d_counts, tpg_result* res,
+                       const Err& E) {
+  if (!res || !res->out0) return E.fail(TPG_ERR_ARG, "result / out0 is NULL");
+  const double t_begin = now_ms();
+  TPG_CUDA_OK(cudaSetDevice(ctx->device), E);
+  const int64_t n = job->ind_row ? job->n : job->nrow_total;
+  const int64_t m = job->ind_col ? job->m : job->ncol_total;
+  const int64_t n_pad = round_up(n, kRowPad);
+  int64_t n_short = 0;
+  if ((job->stat == TPG_STAT_AS || job->stat == TPG_STAT_GRM) && job->pad_quirk) {
+    const int64_t bs = job->block_size > 0 ? job->block_size : block_size_default(job->nrow_total);
+    n_short = as_pad_count(m, bs);
+  }
+  res->stats.n_short = n_short;
+  FinishArgs fa;
+  fa.stat = job->stat;
+  fa.counts = d_counts;
+  fa.ld = n_pad;
+  fa.n = n;
+  fa.m = m;
+  fa.n_short = n_short;
+  fa.shard_rank = job->shard_mode == TPG_SHARD_TILES ? job->shard_rank : 0;
+  fa.shard_world = job->shard_mode == TPG_SHARD_TILES ? job->shard_world : 1;
+  double* host[4] = {res->out0, res->out1, res->aux0, res->aux1};
+  double* dev[4] = {nullptr, nullptr, nullptr, nullptr};
+  const size_t bytes = sizeof(double) * size_t(n) * size_t(n);
+  struct Guard { double** d; bool own; ~Guard() { if (own) for (int o = 0; o < 4; ++o) if (d[o]) cudaFree(d[o]); } } guard{dev, !res->out_on_device};
+  for (int o = 0; o < 4; ++o) {
+    if (!host[o]) continue;
+    if (res->out_on_device) { dev[o] = host[o]; continue; }
+    if (cudaMalloc(&dev[o], bytes) != cudaSuccess) return E.fail(TPG_ERR_NOMEM, "cannot allocate %zu bytes for the result", bytes);
+    if (fa.shard_world > 1)  // blocks of other ranks: leave the caller's values untouched
+      TPG_CUDA_OK(cudaMemcpyAsync(dev[o], host[o], bytes, cudaMemcpyHostToDevice, ctx->s_compute), E);
+  }
+  fa.out0 = dev[0]; fa.out1 = dev[1]; fa.aux0 = dev[2]; fa.aux1 = dev[3];
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  cudaEventRecord(e0, ctx->s_compute);
+  int rc = launch_finish(ctx, fa, ctx->s_compute, E);
+  cudaEventRecord(e1, ctx->s_compute);
+  if (rc == TPG_OK && !res->out_on_device) {
+    for (int o = 0; o < 4 && rc == TPG_OK; ++o) {
+      if (!host[o]) continue;
+      cudaError_t e = cudaMemcpyAsync(host[o], dev[o], bytes, cudaMemcpyDeviceToHost, ctx->s_compute);
+      if (e != cudaSuccess) rc = E.fail(TPG_ERR_CUDA, "D2H of result failed: %s", cudaGetErrorString(e));
+      res->stats.bytes_d2h += int64_t(bytes);
+    }
+  }
+  cudaEventRecord(e2, ctx->s_compute);
+  cudaError_t e = cudaStreamSynchronize(ctx->s_compute);
+  if (rc == TPG_OK && e != cudaSuccess) rc = E.fail(TPG_ERR_CUDA, "finish failed on device: %s", cudaGetErrorString(e));
+  if (rc == TPG_OK) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1); res->stats.ms_finish += ms;
+    cudaEventElapsedTime(&ms, e1, e2); res->stats.ms_d2h += ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  res->stats.ms_total += now_ms() - t_begin;
+  res->stats.n_launches = ctx->launches;
+  return rc;
+}
+
+// One cached context per device for the one-call-per-job entry point (R is single threaded;
+// the mutex only protects the table).
+static std::mutex g_mu;
+static Ctx* g_ctx[64] = {nullptr};
+
+static Ctx* cached_ctx(int device, const Err& E, int* rc) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (device < 0 || device >= 64) { *rc = E.fail(TPG_ERR_ARG, "device %d out of range", device); return nullptr; }
+  if (g_ctx[device]) return g_ctx[device];
+  Ctx* c = new Ctx();
+  *rc = ctx_init(c, device, E);
+  if (*rc) { delete c; return nullptr; }
+  g_ctx[device] = c;
+  return c;
+}
+
+}  // namespace tpg
+
+using namespace tpg;
+
+extern "C" {
+
+const char* tpg_version(void) { return "tidypopgen_b200 0.1.0 (sm_100a, abi 1)"; }
+
+int tpg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int64_t tpg_block_size(int64_t n) { return block_size_default(n); }
+
+int64_t tpg_split_len(int64_t m, int64_t block_size, int64_t* lower, int64_t* upper, int64_t* size,
+                      int64_t cap) {
+  return split_len(m, block_size, lower, upper, size, cap);
+}
+
+int64_t tpg_as_pad_count(int64_t m, int64_t block_size) { return as_pad_count(m, block_size); }
+
+int64_t tpg_counts_ld(int64_t n) { return round_up(n, kRowPad); }
+int64_t tpg_counts_elems(int64_t n) {
+  const int64_t ld = round_up(n, kRowPad);
+  return int64_t(TPG_NUM_COUNT_MATS) * ld * ld;
+}
+
+tpg_ctx* tpg_ctx_create(int device, char* err, size_t errlen) {
+  Err E{err, errlen};
+  Ctx* c = new Ctx();
+  if (ctx_init(c, device, E) != TPG_OK) { delete c; return nullptr; }
+  return reinterpret_cast<tpg_ctx*>(c);
+}
+
+void tpg_ctx_destroy(tpg_ctx* h) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->s_compute) cudaStreamDestroy(c->s_compute);
+  if (c->s_copy) cudaStreamDestroy(c->s_copy);
+  if (c->d_err_flag) cudaFree(c->d_err_flag);
+  if (c->d_items) cudaFree(c->d_items);
+  delete c;
+}
+
+int tpg_accumulate(tpg_ctx* h, const tpg_job* job, int32_t* d_counts, tpg_stats* stats, char* err,
+                   size_t errlen) {
+  Err E{err, errlen};
+  if (!h) return E.fail(TPG_ERR_ARG, "ctx is NULL");
+  if (!d_counts) return E.fail(TPG_ERR_ARG, "d_counts is NULL");
+  tpg_stats local;
+  memset(&local, 0, sizeof local);
+  tpg_stats* st = stats ? stats : &local;
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  const int64_t l0 = c->launches;
+  int rc = accumulate_impl(c, job, d_counts, st, E);
+  st->n_launches += c->launches - l0;
+  return rc;
+}
+
+int tpg_finish(tpg_ctx* h, const tpg_job* job, const int32_t* d_counts, tpg_result* res, char* err,
+               size_t errlen) {
+  Err E{err, errlen};
+  if (!h) return E.fail(TPG_ERR_ARG, "ctx is NULL");
+  if (!job) return E.fail(TPG_ERR_ARG, "job is NULL");
+  if (!d_counts) return E.fail(TPG_ERR_ARG, "d_counts is NULL");
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  const int64_t l0 = c->launches;
+  int rc = finish_impl(c, job, d_counts, res, E);
+  if (res) res->stats.n_launches = c->launches - l0;
+  return rc;
+}
+
+int tpg_pairwise(const tpg_job* job, tpg_result* res, char* err, size_t errlen) {
+  Err E{err, errlen};
+  if (!job || !res) return E.fail(TPG_ERR_ARG, "job / result is NULL");
+  if (job->shard_mode == TPG_SHARD_LOCI && job->shard_world > 1)
+    return E.fail(TPG_ERR_ARG, "loci-sharded jobs need the staged interface (tpg_accumulate, "
+                               "all-reduce of the counts, tpg_finish)");
+  int rc = TPG_OK;
+  Ctx* c = cached_ctx(job->device, E, &rc);
+  if (!c) return rc;
+  const int64_t l0 = c->launches;
+  memset(&res->stats, 0, sizeof res->stats);
+  const int64_t n = job->ind_row ? job->n : job->nrow_total;
+  if (n <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row");
+  TPG_CUDA_OK(cudaSetDevice(c->device), E);
+  int32_t* d_counts = nullptr;
+  const size_t cbytes = sizeof(int32_t) * size_t(tpg_counts_elems(n));
+  if (cudaMalloc(&d_counts, cbytes) != cudaSuccess)
+    return E.fail(TPG_ERR_NOMEM, "cannot allocate %zu bytes for the count matrices", cbytes);
+  cudaError_t e = cudaMemsetAsync(d_counts, 0, cbytes, c->s_compute);
+  if (e != cudaSuccess) { cudaFree(d_counts); return E.fail(TPG_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e)); }
+  rc = accumulate_impl(c, job, d_counts, &res->stats, E);
+  if (rc == TPG_OK) {
+    rc = finish_impl(c, job, d_counts, res, E);
+  }
+  cudaFree(d_counts);
+  res->stats.n_launches = c->launches - l0;
+  return rc;
+}
+
+int tpg_grm_from_as(int device, const double* as_in, int64_t n, double* grm_out, double* mb_out,
+                    char* err, size_t errlen) {
+  Err E{err, errlen};
+  if (!as_in || !grm_out || n <= 0) return E.fail(TPG_ERR_ARG, "bad arguments");
+  int rc = TPG_OK;
+  Ctx* c = cached_ctx(device, E, &rc);
+  if (!c) return rc;
+  TPG_CUDA_OK(cudaSetDevice(c->device), E);
+  double* d = nullptr;
+  const size_t bytes = sizeof(double) * size_t(n) * size_t(n);
+  if (cudaMalloc(&d, bytes) != cudaSuccess) return E.fail(TPG_ERR_NOMEM, "cannot allocate %zu bytes", bytes);
+  cudaError_t e = cudaMemcpyAsync(d, as_in, bytes, cudaMemcpyHostToDevice, c->s_compute);
+  if (e == cudaSuccess) rc = launch_grm(c, d, n, d, mb_out, c->s_compute, E);
+  else rc = E.fail(TPG_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(e));
+  if (rc == TPG_OK) {
+    e = cudaMemcpy(grm_out, d, bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = E.fail(TPG_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d);
+  return rc;
+}
+
+int tpg_decode_planes(tpg_ctx* h, const uint8_t* d_raw, int64_t raw_bytes, int64_t raw_stride,
+                      const int32_t* d_row_idx, int64_t row0, int64_t n, int64_t n_pad,
+                      const int32_t* d_col_idx, int64_t col0, int64_t lc, int64_t lc_pad,
+                      int8_t* d_planes, int64_t plane_stride, int32_t k_major, char* err,
+                      size_t errlen) {
+  Err E{err, errlen};
+  if (!h) return E.fail(TPG_ERR_ARG, "ctx is NULL");
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  TPG_CUDA_OK(cudaSetDevice(c->device), E);
+  DecodeArgs a;
+  a.raw = d_raw; a.raw_bytes = raw_bytes; a.raw_stride = raw_stride;
+  a.row_idx = d_row_idx; a.row0 = row0; a.n = n; a.n_pad = n_pad;
+  a.col_idx = d_col_idx; a.col0 = col0; a.lc = lc; a.lc_pad = lc_pad;
+  a.planes = d_planes; a.plane_stride = plane_stride; a.nplanes = 3; a.k_major = k_major != 0;
+  int rc = launch_decode(c, a, c->s_compute, E);
+  if (rc) return rc;
+  TPG_CUDA_OK(cudaStreamSynchronize(c->s_compute), E);
+  return TPG_OK;
+}
+
+int tpg_gram(tpg_ctx* h, const int8_t* d_planes, int64_t plane_stride, int64_t n_pad,
+             int64_t lc_pad, int32_t k_major, int32_t prod_mask, int32_t shard_rank,
+             int32_t shard_world, int32_t* d_counts, float* ms_out, char* err, size_t errlen) {
+  Err E{err, errlen};
+  if (!h) return E.fail(TPG_ERR_ARG, "ctx is NULL");
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  TPG_CUDA_OK(cudaSetDevice(c->device), E);
+  GramArgs a;
+  a.planes = d_planes; a.plane_stride = plane_stride; a.n = n_pad; a.n_pad = n_pad;
+  a.lc_pad = lc_pad; a.k_major = k_major != 0; a.prod_mask = prod_mask;
+  a.shard_rank = shard_rank; a.shard_world = shard_world; a.counts = d_counts; a.ld = n_pad;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, c->s_compute);
+  int rc = launch_gram(c, a, c->s_compute, nullptr, E);
+  cudaEventRecord(e1, c->s_compute);
+  cudaError_t e = cudaStreamSynchronize(c->s_compute);
+  if (rc == TPG_OK && e != cudaSuccess) {
+    Err quiet{nullptr, 0};
+    rc = check_err_flag(c, quiet) == TPG_ERR_KERNEL ? check_err_flag(c, E)
+                                                     : E.fail(TPG_ERR_CUDA, "gram failed: %s", cudaGetErrorString(e));
+  }
+  if (rc == TPG_OK) rc = check_err_flag(c, E);
+  if (rc == TPG_OK && ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return rc;
+}
+
+int tpg_synth_fill(tpg_ctx* h, uint8_t* d_raw, int64_t nrow, int64_t ncol, int64_t col_offset,
+                   uint64_t seed, double missing_rate, int32_t mode, char* err, size_t errlen) {
+  Err E{err, errlen};
+  if (!h) return E.fail(TPG_ERR_ARG, "ctx is NULL");
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  TPG_CUDA_OK(cudaSetDevice(c->device), E);
+  int rc = launch_synth(c, d_raw, nrow, ncol, col_offset, seed, missing_rate, mode, c->s_compute, E);
+  if (rc) return rc;
+  TPG_CUDA_OK(cudaStreamSynchronize(c->s_compute), E);
+  return TPG_OK;
+}
+
+/* Host twin of tpg_synth_fill (fixtures for the CPU-side checks and the CPU baseline). */
+void tpg_synth_fill_host(uint8_t* raw, int64_t nrow, int64_t ncol, int64_t col_offset, uint64_t seed,
+                         double missing_rate, int32_t mode) {
+  const uint32_t thr = uint32_t(missing_rate * 4294967296.0);
+  for (int64_t l = 0; l < ncol; ++l)
+    for (int64_t i = 0; i < nrow; ++i)
+      raw[l * nrow + i] = tpg_synth_byte(seed, uint64_t(l + col_offset), uint64_t(i), thr, mode);
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+// decode_planes: raw FBM.code256 bytes -> int8 indicator planes, HBM-bandwidth bound.
+//
+// Replaces the serial decode loops of the reference (and the SubBMAcc row/column gather
+// in front of them):
+//   src/snp_king.cpp:45-58   value==0/1/2 -> genotype0/1/2, genotype_valid
+//   src/snp_ibs.cpp:45-56    same three indicators
+//   src/snp_as.cpp:44-53     value<3 -> dos = value-1, na = 1; else 0, 0
+// All three read the RAW byte (SubBMAcc<unsigned char>, never code256), so the rule is
+// "byte <= 2 is a dosage, anything else is missing" — imputed codes 4/5/6 included.
+//
+// Planes written (int8): d = [byte==2] - [byte==0]  (-1/0/+1; the reference's dos-1)
+//                        NM = [byte<=2]             (0/1;  genotype_valid / na_mat)
+//                        H1 = [byte==1]             (0/1;  genotype1)
+// Algorithmic traffic: 1 byte read + 3 bytes written per genotype (2 written for AS/GRM).
+//
+// Default layout is MN-major: plane[l * n_pad + i] — the same orientation as the .bk
+// (individuals contiguous), so the kernel is a pure stream: each lane owns 4 consecutive
+// individuals (one 32-bit word), a warp reads/writes 128 contiguous bytes per locus, and
+// tcgen05 consumes the planes as MN-major operands.  Column starts in a .bk are not
+// aligned (nrow is arbitrary), so loads are aligned 32-bit words re-assembled with a
+// funnel shift across neighbouring lanes.  The K-major variant transposes 4x4 byte blocks
+// in registers (PRMT) and writes plane[i * lc_pad + l].
+#include "internal.h"
+
+namespace tpg {
+
+struct DecodeParams {
+  const uint8_t* raw;
+  const uint8_t* raw_end;
+  int64_t raw_stride;
+  const int32_t* row_idx;
+  int64_t row0;
+  const int32_t* col_idx;
+  int64_t col0;
+  int n, n_pad, lc, lc_pad;
+  int8_t* planes;
+  int64_t plane_stride;
+  int nplanes;
+};
+
+// 4 packed genotype bytes -> 4 packed plane bytes each (SWAR, no per-byte branches).
+__device__ __forceinline__ void decode4(uint32_t g, uint32_t& d, uint32_t& nm, uint32_t& h1) {
+  const uint32_t t = (g & 0x7F7F7F7Fu) + 0x7D7D7D7Du;  // bit 7 set iff (byte & 127) >= 3
+  nm = (((t | g) >> 7) & 0x01010101u) ^ 0x01010101u;   // 1 iff byte <= 2
+  h1 = g & nm;                                         // valid bytes are 0,1,2: bit 0 <=> het
+  const uint32_t h2 = (g >> 1) & nm;                   // bit 1 <=> hom-alt
+  const uint32_t h0 = nm ^ h1 ^ h2;                    // the remaining valid ones
+  d = h2 | (h0 * 255u);                                // +1 -> 0x01, -1 -> 0xFF
+}
+
+// Aligned 32-bit load that never touches bytes outside [raw, raw_end).
+__device__ __forceinline__ uint32_t guarded_ld32(const uint8_t* p, const uint8_t* lo,
+                                                 const uint8_t* hi) {
+  if (p >= lo && p + 4 <= hi) return __ldg(reinterpret_cast<const uint32_t*>(p));
+  uint32_t w = 0x03030303u;
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+    if (p + b >= lo && p + b < hi) w = (w & ~(0xFFu << (8 * b))) | (uint32_t(__ldg(p + b)) << (8 * b));
+  return w;
+}
+
+// Returns the word holding the genotypes of individuals i0..i0+3 (this lane's four) of one
+// raw column.  Contiguous rows: one aligned load per lane + shuffle + funnel shift.
+// Gathered rows: four byte loads.  Individuals >= n read as 0x03 (missing).
+struct RowSel {
+  bool gather;
+  int32_t r[4];    // gathered raw rows (gather mode)
+  int64_t off;     // row0 + i0 (contiguous mode)
+  uint32_t keep;   // byte mask of individuals < n
+  bool ld;         // this lane's aligned word is needed (by itself or by lane-1's funnel shift)
+};
+
+__device__ __forceinline__ uint32_t load4(const DecodeParams& p, const RowSel& rs, int64_t col,
+                                          int lane) {
+  const uint8_t* cbase = p.raw + col * p.raw_stride;
+  uint32_t w;
+  if (rs.gather) {
+    w = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (rs.keep & (0xFFu << (8 * b))) w |= uint32_t(__ldg(cbase + rs.r[b])) << (8 * b);
+  } else {
+    const uint8_t* a = cbase + rs.off;
+    const uint32_t sh = uint32_t(reinterpret_cast<uintptr_t>(a) & 3u);
+    const uint8_t* al = a - sh;
+    // Lanes far beyond the last individual skip the load (their bytes are masked anyway).
+    uint32_t w0 = rs.ld ? guarded_ld32(al, p.raw, p.raw_end) : 0u;
+    uint32_t w1 = __shfl_down_sync(0xFFFFFFFFu, w0, 1);
+    if (lane == 31 && sh && rs.keep) w1 = guarded_ld32(al + 4, p.raw, p.raw_end);
+    w = __funnelshift_r(w0, w1, sh * 8);
+  }
+  return (w & rs.keep) | (0x03030303u & ~rs.keep);
+}
+
+__device__ __forceinline__ RowSel make_rowsel(const DecodeParams& p, int i0) {
+  RowSel rs;
+  rs.gather = p.row_idx != nullptr;
+  const int nv = min(max(p.n - i0, 0), 4);
+  rs.keep = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
+  rs.off = p.row0 + i0;
+  rs.ld = i0 < p.n + 4;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) rs.r[b] = (rs.gather && b < nv) ? p.row_idx[i0 + b] : 0;
+  return rs;
+}
+
+// ------------------------------------------------------------------ MN-major (streaming)
+constexpr int kDecThreads = 256;
+constexpr int kDecLociPerBlock = 16;  // two batches of 8 independent loads per lane
+
+__global__ void __launch_bounds__(kDecThreads)
+decode_planes_mn_kernel(const DecodeParams p) {
+  const int lane = threadIdx.x & 31;
+  // 1-D grid, individual blocks fastest: CTAs resident together sweep whole raw columns.
+  const int nib = (p.n_pad + kDecThreads * 4 - 1) / (kDecThreads * 4);
+  const int ib = blockIdx.x % nib, lb = blockIdx.x / nib;
+  const int i0 = (ib * kDecThreads + threadIdx.x) * 4;
+  if (i0 >= p.n_pad) return;  // n_pad is a multiple of 128: whole warps leave together
+  const RowSel rs = make_rowsel(p, i0);
+  const int l0 = lb * kDecLociPerBlock;
+#pragma unroll
+  for (int half = 0; half < kDecLociPerBlock / 8; ++half) {
+    uint32_t g[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int l = l0 + half * 8 + u;
+      if (l < p.lc) {
+        const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
+        g[u] = load4(p, rs, col, lane);
+      } else {
+        g[u] = 0x03030303u;  // padding loci decode to zeros
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int l = l0 + half * 8 + u;
+      if (l >= p.lc_pad) break;
+      uint32_t d, nm, h1;
+      decode4(g[u], d, nm, h1);
+      int8_t* o = p.planes + int64_t(l) * p.n_pad + i0;
+      *reinterpret_cast<uint32_t*>(o) = d;
+      *reinterpret_cast<uint32_t*>(o + p.plane_stride) = nm;
+      if (p.nplanes > 2) *reinterpret_cast<uint32_t*>(o + 2 * p.plane_stride) = h1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K-major (transposing)
+// Block = 128 individuals x 128 loci; warp w owns loci [16w, 16w+16), lane owns 4 individuals.
+__global__ void __launch_bounds__(256)
+decode_planes_k_kernel(const DecodeParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nib = p.n_pad / 128;
+  const int i0 = int(blockIdx.x % nib) * 128 + lane * 4;
+  const int l0 = int(blockIdx.x / nib) * 128 + warp * 16;
+  if (l0 >= p.lc_pad) return;
+  const RowSel rs = make_rowsel(p, i0);
+  uint32_t g[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int l = l0 + k;
+    if (l < p.lc) {
+      const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
+      g[k] = load4(p, rs, col, lane);
+    } else {
+      g[k] = 0x03030303u;
+    }
+  }
+  // 4x4 byte transposes: t[r][q] = loci 4q..4q+3 of individual i0+r.
+  uint32_t t[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t a0 = __byte_perm(g[4 * q], g[4 * q + 1], 0x5140);
+    const uint32_t a1 = __byte_perm(g[4 * q + 2], g[4 * q + 3], 0x5140);
+    const uint32_t b0 = __byte_perm(g[4 * q], g[4 * q + 1], 0x7362);
+    const uint32_t b1 = __byte_perm(g[4 * q + 2], g[4 * q + 3], 0x7362);
+    t[0][q] = __byte_perm(a0, a1, 0x5410);
+    t[1][q] = __byte_perm(a0, a1, 0x7632);
+    t[2][q] = __byte_perm(b0, b1, 0x5410);
+    t[3][q] = __byte_perm(b0, b1, 0x7632);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    uint4 vd, vn, vh;
+    decode4(t[r][0], vd.x, vn.x, vh.x);
+    decode4(t[r][1], vd.y, vn.y, vh.y);
+    decode4(t[r][2], vd.z, vn.z, vh.z);
+    decode4(t[r][3], vd.w, vn.w, vh.w);
+    int8_t* o = p.planes + int64_t(i0 + r) * p.lc_pad + l0;
+    *reinterpret_cast<uint4*>(o) = vd;
+    *reinterpret_cast<uint4*>(o + p.plane_stride) = vn;
+    if (p.nplanes > 2) *reinterpret_cast<uint4*>(o + 2 * p.plane_stride) = vh;
+  }
+}
+
+int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E) {
+  if (a.n_pad % 128 || a.lc_pad % 16 || a.n > a.n_pad || a.lc > a.lc_pad || a.n <= 0 || a.lc <= 0)
+    return E.fail(TPG_ERR_ARG, "decode: bad geometry n=%lld n_pad=%lld lc=%lld lc_pad=%lld",
+                  (long long)a.n, (long long)a.n_pad, (long long)a.lc, (long long)a.lc_pad);
+  if (a.n_pad > INT32_MAX || a.lc_pad > INT32_MAX)
+    return E.fail(TPG_ERR_ARG, "decode: chunk dimensions exceed int32");
+  DecodeParams p;
+  p.raw = a.raw;
+  p.raw_end = a.raw + a.raw_bytes;
+  p.raw_stride = a.raw_stride;
+  p.row_idx = a.row_idx;
+  p.row0 = a.row0;
+  p.col_idx = a.col_idx;
+  p.col0 = a.col0;
+  p.n = int(a.n);
+  p.n_pad = int(a.n_pad);
+  p.lc = int(a.lc);
+  p.lc_pad = int(a.lc_pad);
+  p.planes = a.planes;
+  p.plane_stride = a.plane_stride;
+  p.nplanes = a.nplanes;
+  if (a.k_major) {
+    if (a.lc_pad % 128) return E.fail(TPG_ERR_ARG, "decode(K-major): lc_pad must be a multiple of 128");
+    const int64_t blocks = (a.n_pad / 128) * (a.lc_pad / 128);
+    if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "decode: chunk too large for one launch");
+    decode_planes_k_kernel<<<unsigned(blocks), 256, 0, st>>>(p);
+  } else {
+    const int64_t blocks = ((a.n_pad + kDecThreads * 4 - 1) / (kDecThreads * 4)) *
+                           ((a.lc_pad + kDecLociPerBlock - 1) / kDecLociPerBlock);
+    if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "decode: chunk too large for one launch");
+    decode_planes_mn_kernel<<<unsigned(blocks), kDecThreads, 0, st>>>(p);
+  }
+  TPG_CUDA_OK(cudaGetLastError(), E);
+  ctx->launches++;
+  return TPG_OK;
+}
+
+}  // namespace tpg

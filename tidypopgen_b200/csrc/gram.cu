@@ -1,0 +1,343 @@
+// gram_i8: exact int8 x int8 -> s32 Gram products of the indicator planes on the 5th-gen
+// tensor cores (tcgen05.mma kind::i8, accumulators in TMEM, operands staged by TMA).
+//
+// Replaces the FP64 dsyrk/dgemm products of the reference:
+//   KING  src/snp_king.cpp:70-72   K += g1 g1' - 2 (g0 g2' + g2 g0');  N_Aa_i += g1 valid'
+//   IBS   src/snp_ibs.cpp:67-72    K += 2(g2g2'+g1g1'+g0g0') + g1(g0+g2)' + (g0+g2)g1';  K2 += 2 nm nm'
+//   AS    src/snp_as.cpp:64-65     K += dos dos';  K2 += na na'
+// With d = g2 - g0 (-1/0/+1), NM = g0+g1+g2, H1 = g1 all of these are linear
+// combinations of four integer products ("Algebra"):
+//   DD = d d'   NN = NM NM'   HH = H1 H1'   (symmetric: upper-triangle tiles only)
+//   HN = H1 NM'                              (full)
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0   TMA producer       (one lane)    global planes -> 4-stage smem ring
+//   warp 1   MMA issuer         (one lane)    4 x tcgen05.mma (M128 N256 K32) per stage
+//   warps 2-5 epilogue          TMEM -> registers -> red.global.add.s32 (coalesced, exact)
+// TMEM holds two 128x256 s32 accumulators, so the epilogue of one work item overlaps the
+// MMAs of the next.  A work item is (product, tile, k-block range); the host orders the
+// list so that CTAs running at the same time share operand panels in L2.
+#include <algorithm>
+#include <cstring>
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace tpg {
+
+constexpr int kStages = 4;
+constexpr int kABytes = kTileM * kTileK;            // 16 KiB
+constexpr int kBBytes = kTileN * kTileK;            // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytes;      // 48 KiB
+constexpr int kGramThreads = 192;
+constexpr int kTmemCols = 512;                      // 2 accumulators x 256 columns
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// product -> (A plane, B plane); planes: 0 = d, 1 = NM, 2 = H1
+__device__ __forceinline__ void prod_planes(int prod, int& pa, int& pb) {
+  pa = (prod == TPG_MAT_DD) ? 0 : (prod == TPG_MAT_NN) ? 1 : 2;
+  pb = (prod == TPG_MAT_DD) ? 0 : (prod == TPG_MAT_HH) ? 2 : 1;
+}
+
+struct GramParams {
+  const WorkItem* items;
+  int n_items;
+  int32_t* counts;
+  int64_t mat_stride;  // elements between count matrices
+  int64_t ld;
+  int n;               // valid individuals
+  int* err_flag;
+};
+
+template <bool kMajorK>
+__global__ void __launch_bounds__(kGramThreads, 1)
+gram_i8_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_nm,
+               const __grid_constant__ CUtensorMap tm_h1, const GramParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned tiles.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full_bar = bars;                    // [kStages] TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;         // [kStages] MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * kStages;     // [2] MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_d);
+    tma_prefetch_desc(&tm_nm);
+    tma_prefetch_desc(&tm_h1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        const WorkItem w = p.items[it];
+        const int prod = w.prod_ti & 15, ti = w.prod_ti >> 4, tj = w.tj;
+        int pa, pb;
+        prod_planes(prod, pa, pb);
+        const CUtensorMap* ma = pa == 0 ? &tm_d : pa == 1 ? &tm_nm : &tm_h1;
+        const CUtensorMap* mb = pb == 0 ? &tm_d : pb == 1 ? &tm_nm : &tm_h1;
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          if (kMajorK) {  // planes[row][locus]: coords (locus, row)
+            tma_load_2d(sa, ma, &full_bar[stage], kb * kTileK, ti * kTileM);
+            tma_load_2d(sb, mb, &full_bar[stage], kb * kTileK, tj * kTileN);
+            tma_load_2d(sb + kABytes, mb, &full_bar[stage], kb * kTileK, tj * kTileN + 128);
+          } else {        // planes[locus][row]: coords (row, locus)
+            tma_load_2d(sa, ma, &full_bar[stage], ti * kTileM, kb * kTileK);
+            tma_load_2d(sb, mb, &full_bar[stage], tj * kTileN, kb * kTileK);
+            tma_load_2d(sb + kABytes, mb, &full_bar[stage], tj * kTileN + 128, kb * kTileK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_i8(kTileM, kTileN, !kMajorK);
+      // K-major  SW128: 8-row groups 1024 B apart (SBO); one MMA consumes 32 B of K.
+      // MN-major SW128: 8-locus groups 1024 B apart (SBO), 128-row blocks 16 KiB apart (LBO);
+      //                 one MMA consumes 32 loci = 4096 B.
+      constexpr uint32_t lbo = kMajorK ? 16u : uint32_t(kABytes);
+      constexpr uint32_t sbo = 1024u;
+      constexpr uint32_t kstep = kMajorK ? (32u >> 4) : (4096u >> 4);  // descriptor units of 16 B
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        const WorkItem w = p.items[it];
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(acc * kTileN);
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint64_t da = make_smem_desc_sw128(sa, lbo, sbo);
+          const uint64_t db = make_smem_desc_sw128(sa + kABytes, lbo, sbo);
+#pragma unroll
+          for (int k = 0; k < kTileK / 32; ++k) {
+            umma_i8(tmem_d, da + uint64_t(k * kstep), db + uint64_t(k * kstep), idesc,
+                    (kb > w.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+      const WorkItem w = p.items[it];
+      const int prod = w.prod_ti & 15, ti = w.prod_ti >> 4, tj = w.tj;
+      const bool sym = prod != TPG_MAT_HN;
+      mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
+      tc_fence_after();
+      const int i = ti * kTileM + q * 32 + lane;  // A row  = count-matrix row
+      const int j0 = tj * kTileN;                 // B rows = count-matrix columns
+      int32_t* cbase = p.counts + int64_t(prod) * p.mat_stride + i;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kTileN);
+#pragma unroll 1
+      for (int c = 0; c < kTileN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + uint32_t(c), v);
+        tmem_ld_wait();
+        if (c + 32 == kTileN) {  // accumulator drained: hand it back before the last adds
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        if (j0 + c < p.n && i < p.n) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = j0 + c + jj;
+            // X(i,j) at X[i + j*ld]: the 32 lanes of a warp hit 32 consecutive ints.
+            if (j < p.n && (!sym || i <= j)) atomicAdd(cbase + int64_t(j) * p.ld, int32_t(v[jj]));
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_plane_map(Ctx* ctx, CUtensorMap* out, const int8_t* base, uint64_t inner,
+                          uint64_t outer, const Err& E) {
+  if (!ctx->encode_tiled) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled entry point missing");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner};  // bytes, dim 1
+  cuuint32_t box[2] = {128, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(base), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", int(r));
+  return TPG_OK;
+}
+
+// Chooses how many k-splits a tile gets so that the persistent CTAs finish together.
+static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms) {
+  if (n_tile_items >= int64_t(8) * sms) return 1;
+  int best = 1;
+  double best_cost = 1e300;
+  const int max_ks = int(std::min<int64_t>(kblocks, 512));
+  for (int ks = 1; ks <= max_ks; ++ks) {
+    const int64_t per = (kblocks + ks - 1) / ks;      // k-blocks per item
+    if (ks > 1 && per < 8) break;                     // keep the epilogue amortised
+    const int64_t waves = (n_tile_items * ks + sms - 1) / sms;
+    const double cost = double(waves) * (double(per) + 2.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = ks; }
+  }
+  return best;
+}
+
+int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out, const Err& E) {
+  if (a.n_pad % kRowPad || a.lc_pad % kLociPad || a.lc_pad <= 0)
+    return E.fail(TPG_ERR_ARG, "gram: n_pad (%lld) / lc_pad (%lld) not tile multiples",
+                  (long long)a.n_pad, (long long)a.lc_pad);
+  const int64_t tiles_m = a.n_pad / kTileM, tiles_n = a.n_pad / kTileN;
+  const int64_t kblocks = a.lc_pad / kTileK;
+
+  // ---- tile list in L2-friendly order: 1024x1024 regions, then tiles, then products
+  struct T { int prod, ti, tj; };
+  std::vector<T> tiles;
+  const int64_t RI = 8, RJ = 4;
+  for (int64_t rj = 0; rj < tiles_n; rj += RJ)
+    for (int64_t ri = 0; ri < tiles_m; ri += RI)
+      for (int64_t tj = rj; tj < std::min(rj + RJ, tiles_n); ++tj)
+        for (int64_t ti = ri; ti < std::min(ri + RI, tiles_m); ++ti) {
+          const bool upper = kTileN * tj + (kTileN - 1) >= kTileM * ti;
+          // 256x256 ownership block of the tile (rows ti/2, cols tj); lower blocks mirror
+          const int64_t bi = ti / 2, bj = tj;
+          for (int prod = 0; prod < TPG_NUM_COUNT_MATS; ++prod) {
+            if (!(a.prod_mask & (1 << prod))) continue;
+            if (prod != TPG_MAT_HN && !upper) continue;
+            const int64_t lo = std::min(bi, bj), hi = std::max(bi, bj);
+            if (!block_owned(lo, hi, tiles_n, a.shard_rank, a.shard_world)) continue;
+            tiles.push_back({prod, int(ti), int(tj)});
+          }
+        }
+  if (tiles.empty()) { if (macs_out) *macs_out = 0; return TPG_OK; }
+
+  const int sms = ctx->num_sms;
+  const int ks = choose_ksplit(int64_t(tiles.size()), kblocks, sms);
+  if (macs_out) *macs_out = int64_t(tiles.size()) * kTileM * kTileN * a.lc_pad;
+
+  // The work list only depends on the geometry; chunks of equal size reuse the upload.
+  char key[160];
+  snprintf(key, sizeof key, "%lld/%lld/%d/%d/%d/%d", (long long)a.n_pad, (long long)a.lc_pad,
+           a.prod_mask, a.shard_rank, a.shard_world, ks);
+  if (ctx->items_key != key) {
+    std::vector<WorkItem>& items = ctx->h_items;
+    items.clear();
+    items.reserve(tiles.size() * ks);
+    for (int s = 0; s < ks; ++s) {
+      const int32_t kb0 = int32_t(kblocks * s / ks), kb1 = int32_t(kblocks * (s + 1) / ks);
+      if (kb1 <= kb0) continue;
+      for (const T& t : tiles) items.push_back({int32_t(t.prod | (t.ti << 4)), t.tj, kb0, kb1});
+    }
+    if (items.size() > ctx->d_items_cap) {
+      TPG_CUDA_OK(cudaStreamSynchronize(st), E);
+      if (ctx->d_items) cudaFree(ctx->d_items);
+      ctx->d_items = nullptr;
+      ctx->d_items_cap = 0;
+      const size_t cap = items.size() + items.size() / 4 + 1024;
+      TPG_CUDA_OK(cudaMalloc(&ctx->d_items, cap * sizeof(WorkItem)), E);
+      ctx->d_items_cap = cap;
+    }
+    // Stream-ordered after any kernel still reading the previous list.
+    TPG_CUDA_OK(cudaMemcpyAsync(ctx->d_items, items.data(), items.size() * sizeof(WorkItem),
+                                cudaMemcpyHostToDevice, st), E);
+    ctx->items_key = key;
+  }
+  const size_t n_items = ctx->h_items.size();
+
+  CUtensorMap maps[3];
+  for (int pl = 0; pl < 3; ++pl) {
+    const int8_t* base = a.planes + int64_t(pl) * a.plane_stride;
+    const uint64_t inner = a.k_major ? uint64_t(a.lc_pad) : uint64_t(a.n_pad);
+    const uint64_t outer = a.k_major ? uint64_t(a.n_pad) : uint64_t(a.lc_pad);
+    // AS / GRM jobs carry two planes only: alias the missing H1 map to plane 0 (never used).
+    const bool present = pl < 2 || (a.prod_mask & ((1 << TPG_MAT_HH) | (1 << TPG_MAT_HN)));
+    int rc = make_plane_map(ctx, &maps[pl], present ? base : a.planes, inner, outer, E);
+    if (rc) return rc;
+  }
+
+  GramParams p;
+  p.items = ctx->d_items;
+  p.n_items = int(n_items);
+  p.counts = a.counts;
+  p.mat_stride = a.ld * a.ld;
+  p.ld = a.ld;
+  p.n = int(a.n);
+  p.err_flag = ctx->d_err_flag;
+
+  const int grid = int(std::min<size_t>(n_items, size_t(sms)));
+  if (a.k_major) {
+    TPG_CUDA_OK(cudaFuncSetAttribute(gram_i8_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), E);
+    gram_i8_kernel<true><<<grid, kGramThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
+  } else {
+    TPG_CUDA_OK(cudaFuncSetAttribute(gram_i8_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), E);
+    gram_i8_kernel<false><<<grid, kGramThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
+  }
+  TPG_CUDA_OK(cudaGetLastError(), E);
+  ctx->launches++;
+  return TPG_OK;
+}
+
+}  // namespace tpg

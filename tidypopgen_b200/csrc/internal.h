@@ -1,0 +1,129 @@
+// Internal declarations shared by the translation units of libtpg_b200.so.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "../../include/tpg_b200.h"
+
+namespace tpg {
+
+// ---- tile geometry of the Gram kernel ("gram_i8")
+constexpr int kTileM = 128;   // A rows per tile  (TMEM lanes)
+constexpr int kTileN = 256;   // B rows per tile  (TMEM columns)
+constexpr int kTileK = 128;   // loci per pipeline stage (= one 128B swizzle span)
+constexpr int kRowPad = 256;  // individuals are padded to this multiple
+constexpr int kLociPad = 128; // loci per chunk are padded to this multiple
+
+struct __align__(16) WorkItem {
+  int32_t prod_ti;  // prod in bits [0,4), ti in bits [4,32)
+  int32_t tj;
+  int32_t kb0;      // first k-block (units of kTileK loci)
+  int32_t kb1;      // one past the last k-block
+};
+
+// Per-device state: streams, events, reusable buffers, the driver entry point for
+// tensor-map encoding.
+struct Ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t s_compute = nullptr;
+  cudaStream_t s_copy = nullptr;
+  int* d_err_flag = nullptr;       // device-side watchdog flag
+  WorkItem* d_items = nullptr;     // work list of the last gram launch
+  size_t d_items_cap = 0;
+  std::vector<WorkItem> h_items;   // host copy (kept alive for the async upload)
+  std::string items_key;           // geometry the uploaded list was built for
+  void* encode_tiled = nullptr;    // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
+  int64_t launches = 0;
+};
+
+struct Err {
+  char* buf;
+  size_t len;
+  int fail(int code, const char* fmt, ...) const;
+};
+
+#define TPG_CUDA_OK(call, E)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return (E).fail(TPG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                      __FILE__, __LINE__);                                                \
+  } while (0)
+
+// ---- kernels' host launchers (each returns TPG_OK or an error code)
+struct DecodeArgs {
+  const uint8_t* raw;
+  int64_t raw_bytes;   // bytes addressable from raw (for guarded word loads)
+  int64_t raw_stride;  // bytes between consecutive raw columns
+  const int32_t* row_idx;  // device, 0-based, or nullptr
+  int64_t row0;
+  int64_t n, n_pad;
+  const int32_t* col_idx;  // device, 0-based, or nullptr
+  int64_t col0;
+  int64_t lc, lc_pad;
+  int8_t* planes;
+  int64_t plane_stride;
+  int nplanes;  // 2 (d, NM) or 3 (d, NM, H1)
+  bool k_major;
+};
+int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E);
+
+struct GramArgs {
+  const int8_t* planes;
+  int64_t plane_stride;
+  int64_t n;       // valid individuals (entries beyond are skipped in the epilogue)
+  int64_t n_pad;
+  int64_t lc_pad;  // loci in this chunk (padded)
+  bool k_major;
+  int prod_mask;
+  int shard_rank, shard_world;  // tile sharding (world <= 1: everything)
+  int32_t* counts;
+  int64_t ld;
+};
+int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out, const Err& E);
+
+// Tile sharding: output blocks of 256x256 (bi <= bj, nblocks per side) are dealt round-robin
+// over the row-major order of the upper triangle; identical on every rank, host and device.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline bool block_owned(int64_t bi, int64_t bj, int64_t nblocks, int rank, int world) {
+  if (world <= 1) return true;
+  const int64_t idx = bi * nblocks - bi * (bi - 1) / 2 + (bj - bi);
+  return int(idx % world) == rank;
+}
+
+struct FinishArgs {
+  int stat;
+  const int32_t* counts;
+  int64_t ld;
+  int64_t n;
+  int64_t m;        // total loci (adjusted_counts multiplies by it)
+  int64_t n_short;  // allele-sharing pad-quirk constant
+  int shard_rank, shard_world;  // TILES mode: only owned blocks are written
+  double* out0;     // device, n x n column-major
+  double* out1;
+  double* aux0;
+  double* aux1;
+};
+int launch_finish(Ctx* ctx, const FinishArgs& a, cudaStream_t st, const Err& E);
+// GRM from an allele-sharing matrix already on the device (in place allowed).
+int launch_grm(Ctx* ctx, const double* d_as, int64_t n, double* d_grm, double* mb_host,
+               cudaStream_t st, const Err& E);
+
+int launch_synth(Ctx* ctx, uint8_t* d_raw, int64_t nrow, int64_t ncol, int64_t col_offset,
+                 uint64_t seed, double missing_rate, int mode, cudaStream_t st, const Err& E);
+
+int check_err_flag(Ctx* ctx, const Err& E);
+
+// ---- host helpers (split.cpp)
+int64_t block_size_default(int64_t n);
+int64_t split_len(int64_t m, int64_t block_size, int64_t* lower, int64_t* upper, int64_t* size,
+                  int64_t cap);
+int64_t as_pad_count(int64_t m, int64_t block_size);
+
+}  // namespace tpg
