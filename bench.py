@@ -1,0 +1,318 @@
+"""bench.py — pairwise_king pair-SNP ops/s (n^2 * m / s) on BASELINE.json configs[1]
+(HGDP-shape synthetic: 929 individuals x 650,000 SNPs, 2% missing), on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A step = one whole pairwise_king job: decode_planes + gram_i8 (tcgen05 int8) + finish_king.
+`value` is measured with the .bk bytes resident in HBM; `e2e` goes through the public API
+with HOST (pinned) buffers, H2D and D2H inside the timed region.  N > 1 is loci-sharded
+(weak scaling: every rank owns its own 650,000 loci, global m = N * 650,000): staged C-ABI
+accumulate, ONE NCCL all-reduce of the int32 count matrices, finish.  Prints one JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_IND, M_LOCI, MISSING, SEED = 929, 650_000, 0.02, 20260002
+WORKLOAD = "HGDP-shape synthetic 929 x 650000, 2% missing, pairwise_king (BASELINE.json configs[1])"
+METRIC = "pairwise_king pair-SNP ops/sec (n^2*m)"
+UNIT = "pair-SNP/s"
+KING_INT8_OPS_PER_PAIRSNP = 4.0   # 2.0 MAC: DD (upper) + NN (upper) + HN (full) — DESIGN.md "Algebra"
+DECODE_BYTES_PER_GENOTYPE = 4.0   # 1 read + 3 plane bytes written
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            j = json.load(f)
+        p.update(hbm_gbs=float(j["hbm_gbs"]), bf16_tflops=float(j["bf16_tflops"]),
+                 bf16_tflops_sustained=float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
+                 source="MEASURED_PEAKS.json")
+    except Exception:  # noqa: BLE001
+        pass
+    return p
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                for ln in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in ln.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({nm for r in self.rows if len(r) >= 8 for nm, v in zip(names, r[4:8]) if v == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def traffic_from_profile():
+    """dram bytes per gram_i8 launch from the committed ncu capture, if one exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+# ---------------------------------------------------------------------------- reference arm
+
+def synth_numpy(n, m, seed):
+    """Same law as include/tpg_synth.h (p ~ U(0.05, 0.5), Binomial(2, p), iid missing -> 3),
+    drawn with numpy so the reference arm touches none of this repo's native code."""
+    rng = np.random.default_rng(seed)
+    p = rng.uniform(0.05, 0.5, size=(m, 1))
+    g = (rng.random((m, n)) < p).astype(np.uint8) + (rng.random((m, n)) < p).astype(np.uint8)
+    g[rng.random((m, n)) < MISSING] = 3
+    return g
+
+
+def run_reference(args, rank):
+    """The reference's CPU path (restated: oracle/blas_baseline.py) on the host cores."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import blas_baseline as B
+    from oracle import oracle as O
+
+    bs = O.block_size(N_IND)                   # pairwise_king passes block_size(nrow(x)): 144,475
+    iv = O.split_len(M_LOCI, bs)               # 5 blocks of 130,000 loci
+    sample = int(iv[0, 2])
+    raw = synth_numpy(N_IND, sample, SEED)
+    t0 = time.perf_counter()
+    B.king_blocks(raw, N_IND, sample, bs, max_blocks=1)
+    first = time.perf_counter() - t0
+    if first > 8.0:                            # keep the whole run within minutes on a small host
+        sample = max(4096, int(sample * 4.0 / first))
+        raw = raw[:sample]
+    for _ in range(max(0, args.warmup - 1)):
+        B.king_blocks(raw, N_IND, sample, bs, max_blocks=1)
+    times = []
+    for _ in range(args.steps):
+        K, N, done, sec = B.king_blocks(raw, N_IND, sample, bs, max_blocks=1)
+        t1 = time.perf_counter()
+        B.king_finish(K, N)
+        times.append(sec + (time.perf_counter() - t1) * (sample / M_LOCI))
+    sec = float(np.mean(times))
+    value = N_IND * N_IND * sample / sec
+    cores = torch.get_num_threads()
+    desc = (f"1 loci block of {sample} of 650000 loci (R block.size {bs}), serial-equivalent numpy decode + "
+            f"FP64 dgemm via MKL on {cores} threads; rate is per pair-SNP so it extrapolates linearly in m")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ---------------------------------------------------------------------------- B200 arm
+
+def run_b200(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+
+    import tidypopgen_b200 as tpg
+    from tidypopgen_b200 import _lib as L
+    from tidypopgen_b200 import dist as tdist
+
+    torch.cuda.set_device(local)
+    eng = tdist.CudaEngine(local)
+    lib = L.lib()
+    n, m = N_IND, M_LOCI
+    m_global = m * world
+
+    # ---- synthetic .bk image of this rank's loci, resident in HBM
+    dev_raw = torch.empty(n * m + 64, dtype=torch.uint8, device=f"cuda:{local}")
+    eb = L.errbuf()
+    L.check(lib.tpg_synth_fill(eng.ctx.handle, dev_raw.data_ptr(), n, m, rank * m, SEED, MISSING, 0, eb, len(eb)), eb)
+    X = tpg.FBMCode256.__new__(tpg.FBMCode256)
+    X.backingfile, X.nrow, X.ncol, X.code256 = "<synthetic>", n, m, None
+    bs = tpg.block_size(n)
+    job, keep = tpg.snp.make_job(X, None, None, L.STAT_KING, bs, device=local,
+                                 src=(L.SRC_DEVICE, dev_raw.data_ptr(), dev_raw))
+    counts = eng.new_counts(n)
+    out_dev = torch.zeros((n, n), dtype=torch.float64, device=f"cuda:{local}")
+    res = L.Result(out0=out_dev.data_ptr(), out1=None, aux0=None, aux1=None, out_on_device=1)
+    agg = {"ms_decode": 0.0, "ms_gram": 0.0, "ms_finish": 0.0, "launches": 0, "chunks": 0, "macs": 0}
+
+    def step(record: bool):
+        with torch.cuda.stream(eng.stream):
+            counts.zero_()
+        st = L.Stats()
+        L.check(lib.tpg_accumulate(eng.ctx.handle, C.byref(job), counts.data_ptr(), C.byref(st), eb, len(eb)), eb)
+        if world > 1:
+            dist.all_reduce(counts)
+            torch.cuda.current_stream().synchronize()
+        L.check(lib.tpg_finish(eng.ctx.handle, C.byref(job), counts.data_ptr(), C.byref(res), eb, len(eb)), eb)
+        if record:
+            agg["ms_decode"] += st.ms_decode
+            agg["ms_gram"] += st.ms_gram
+            agg["ms_finish"] += res.stats.ms_finish
+            agg["launches"] += st.n_launches + res.stats.n_launches + 1  # + the counts memset
+            agg["chunks"] += st.n_chunks
+            agg["macs"] += st.mma_macs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(eng.stream)
+    for _ in range(args.steps):
+        step(True)
+    e1.record(eng.stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / args.steps
+    value = n * n * m_global / (ms_step * 1e-3)
+
+    # ---- e2e: host (pinned) .bk bytes -> public API -> host result, copies inside the timed region
+    host_raw = torch.empty(n * m, dtype=torch.uint8).pin_memory()
+    host_raw.copy_(dev_raw[: n * m])
+    src_h = (L.SRC_HOST, host_raw.data_ptr(), host_raw)
+
+    def e2e_step():
+        return tdist.pairwise_sharded(eng, X, None, None, L.STAT_KING, bs, mode="loci", rank=rank, world=world,
+                                      src=src_h)
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        king_host, _ = e2e_step()
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    sampler.stop_flag = True
+    sampler.join(2)
+    e2e_value = n * n * m_global / (float(e2e_ms.item()) * 1e-3)
+    same = bool(np.array_equal(king_host, out_dev.t().cpu().numpy(), equal_nan=True))
+
+    if rank != 0:
+        return
+    pk = peaks()
+    steps = args.steps
+    gram_ms = agg["ms_gram"] / max(1, agg["chunks"])          # per launch
+    dec_ms = agg["ms_decode"] / max(1, agg["chunks"])
+    loci_per_launch = m * steps / max(1, agg["chunks"])
+    gram_ops = KING_INT8_OPS_PER_PAIRSNP * n * n * loci_per_launch
+    int8_peak = 2.0 * pk["bf16_tflops"]
+    tr = traffic_from_profile()
+    roof = {"kernel": "gram_i8_kernel", "bound": "tensor", "achieved": gram_ops / (gram_ms * 1e-3) / 1e12,
+            "peak": int8_peak, "unit": "TFLOP/s", "frac": gram_ops / (gram_ms * 1e-3) / 1e12 / int8_peak,
+            "traffic": tr.get("gram_i8_dram_bytes_per_launch"),
+            "note": ("int8 tensor ops (2 per MAC); algorithmic = 4 op per pair-SNP (DD+NN upper, HN full); "
+                     f"peak = 2 x measured bf16 burst from {pk['source']} (nominal int8 dense 4500); "
+                     f"issued incl. tile padding = {2 * agg['macs'] / steps / (agg['ms_gram'] / steps * 1e-3) / 1e12:.0f} TOP/s; "
+                     f"avg launch {gram_ms:.3f} ms over {agg['chunks'] // steps} launch(es)/step")}
+    dec_bytes = DECODE_BYTES_PER_GENOTYPE * n * loci_per_launch
+    roof_dec = {"kernel": "decode_planes_mn_kernel", "bound": "hbm", "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9,
+                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                "traffic": tr.get("decode_planes_dram_bytes_per_launch"),
+                "note": f"1 B read + 3 B written per genotype; avg launch {dec_ms:.3f} ms; peak from {pk['source']}"}
+
+    # ---- CPU baseline on this host: the reference path restated (oracle/blas_baseline.py)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import blas_baseline as B
+        from oracle import oracle as O
+        iv = O.split_len(m, bs)
+        sample = int(iv[0, 2])
+        raw_np = host_raw[: n * sample].numpy().reshape(sample, n)
+        B.king_blocks(raw_np[:8192], n, 8192, bs, max_blocks=1)  # BLAS thread warm-up
+        _, _, done, sec = B.king_blocks(raw_np, n, sample, bs, max_blocks=1)
+        cpu = {"value": n * n * done / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"first loci block ({done} of {m} loci, R block.size {bs}); numpy decode + FP64 dgemm (MKL) "
+                         f"in {sec:.2f} s; per-pair-SNP rate extrapolates linearly in m"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n": n, "m_per_gpu": m, "m_global": m_global,
+                   "sharding": "none" if world == 1 else f"loci x{world}, one NCCL all-reduce of int32 counts",
+                   "l2": "inputs larger than L2 (604 MB raw + 2 GB planes per step vs 126 MB), no flush needed",
+                   "int8_ops_per_pair_snp": KING_INT8_OPS_PER_PAIRSNP},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * m, "d2h_bytes_per_step": 8 * n * n,
+                "ms_per_step": float(e2e_ms.item()), "steps": e2e_steps, "matches_device_run": same},
+        "gpu_launches": agg["launches"],
+        "roofline": roof, "roofline_decode": roof_dec,
+        "stage_ms_per_step": {"decode": agg["ms_decode"] / steps, "gram": agg["ms_gram"] / steps,
+                              "finish": agg["ms_finish"] / steps},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        from tidypopgen_b200 import dist as tdist
+        tdist.init_process_group("nccl")
+    elif args.gpus > 1:
+        sys.exit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    run_b200(args, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -194,6 +194,13 @@ typedef struct tpg_ctx tpg_ctx;
 
 tpg_ctx* tpg_ctx_create(int device, char* err, size_t errlen);
 void tpg_ctx_destroy(tpg_ctx* ctx);
+/* A context keeps its staging / plane / result buffers between jobs (grow-only);
+ * tpg_ctx_trim frees them.  tpg_release does the same for the context tpg_pairwise
+ * caches per device. */
+void tpg_ctx_trim(tpg_ctx* ctx);
+void tpg_release(int device);
+/* The cudaStream_t all kernels of this context are launched on (for event timing). */
+void* tpg_ctx_stream(tpg_ctx* ctx);
 
 /* Layout of the int32 count buffer for n individuals: TPG_NUM_COUNT_MATS matrices,
  * each column-major with leading dimension ld = n_pad (X(i,j) at X[i + j*ld]);

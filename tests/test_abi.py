@@ -1,0 +1,108 @@
+"""The C-ABI library loads on a CPU-only host, exports every symbol include/tpg_b200.h
+declares, agrees with the header on every enum, and its host-only helpers agree with the
+oracle.  No compute calls (no GPU here)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tidypopgen_b200 import _lib as L
+
+HEADER = (Path(__file__).resolve().parent.parent / "include" / "tpg_b200.h").read_text()
+
+
+def declared_functions():
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    return sorted(set(re.findall(r"\b(tpg_[a-z0-9_]+)\s*\(", body)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.lib()
+    names = declared_functions()
+    assert "tpg_pairwise" in names and "tpg_accumulate" in names and len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/tpg_b200.h but not exported"
+    assert set(names) == set(L.SIGNATURES), "ctypes signatures out of sync with the header"
+
+
+def test_enums_match_header():
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    vals = {k: int(v) for k, v in re.findall(r"\b(TPG_[A-Z0-9_]+)\s*=\s*(\d+)", body)}
+    vals.update({k: int(v) for k, v in re.findall(r"#define\s+(TPG_[A-Z0-9_]+)\s+(\d+)", body)})
+    for k, v in vals.items():
+        py = k[4:]
+        assert hasattr(L, py), f"{k} missing from _lib.py"
+        assert getattr(L, py) == v, k
+
+
+def test_struct_layout_matches_c():
+    # offsets the C compiler would produce for the declared field order (LP64)
+    assert C.sizeof(L.Job) == 120 and L.Job.bk_path.offset == 16 and L.Job.flags.offset == 112
+    assert C.sizeof(L.Stats) == 104
+    assert C.sizeof(L.Result) == 40 + 104 and L.Result.stats.offset == 40
+
+
+def test_version_and_device_count_without_gpu():
+    lib = L.lib()
+    assert b"sm_100a" in lib.tpg_version()
+    assert lib.tpg_device_count() >= 0
+
+
+@pytest.mark.parametrize("n", [1, 7, 12, 929, 2504, 10000, 50000, 10**6, 2 * 10**8])
+def test_block_size_matches_oracle(n):
+    assert L.lib().tpg_block_size(n) == O.block_size(n)
+
+
+def test_split_len_matches_oracle():
+    lib = L.lib()
+    rng = np.random.default_rng(11)
+    cases = [(961, 300), (6, 3), (6, 2), (5, 100), (650000, 144475), (1000000, 53601), (500000, 2684),
+             (1000000, 13421), (7, 7), (7, 1), (10, 3), (25, 10)]
+    cases += [(int(rng.integers(1, 200000)), int(rng.integers(1, 5000))) for _ in range(200)]
+    for m, bs in cases:
+        ref = O.split_len(m, bs)
+        nb = lib.tpg_split_len(m, bs, None, None, None, 0)
+        assert nb == len(ref)
+        lo, up, sz = (np.zeros(nb, np.int64) for _ in range(3))
+        lib.tpg_split_len(m, bs, lo.ctypes.data, up.ctypes.data, sz.ctypes.data, nb)
+        assert np.array_equal(np.stack([lo, up, sz], 1), ref), (m, bs)
+        assert sz.sum() == m and up[-1] == m and sz.max() - sz.min() <= 1
+        assert lib.tpg_as_pad_count(m, bs) == O.n_short(m, bs)
+    assert lib.tpg_split_len(0, 5, None, None, None, 0) == -1
+
+
+def test_counts_layout():
+    lib = L.lib()
+    assert lib.tpg_counts_ld(929) == 1024 and lib.tpg_counts_ld(1024) == 1024 and lib.tpg_counts_ld(1) == 256
+    assert lib.tpg_counts_elems(929) == 4 * 1024 * 1024
+
+
+def test_synth_host_is_deterministic_and_in_law():
+    lib = L.lib()
+    a = np.zeros(50 * 4000, np.uint8)
+    b = np.zeros(50 * 4000, np.uint8)
+    lib.tpg_synth_fill_host(a.ctypes.data, 50, 4000, 0, 42, 0.02, 0)
+    lib.tpg_synth_fill_host(b.ctypes.data, 50, 2000, 2000, 42, 0.02, 0)
+    assert np.array_equal(a[50 * 2000:], b[:50 * 2000]), "shards must be independently generable"
+    assert set(np.unique(a)) <= {0, 1, 2, 3}
+    assert 0.01 < (a == 3).mean() < 0.03
+    dos = a[a < 3].mean() / 2  # mean allele frequency ~ E U(0.05, 0.5) = 0.275
+    assert 0.25 < dos < 0.30
+    c = np.zeros(50 * 4000, np.uint8)
+    lib.tpg_synth_fill_host(c.ctypes.data, 50, 4000, 0, 42, 0.02, 1)
+    assert set(np.unique(c)) <= {0, 1, 2, 4, 5, 6} and np.array_equal(c < 3, a < 3)
+
+
+def test_compute_fails_loudly_without_gpu():
+    if L.lib().tpg_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(L.TpgError) as ei:
+        L.Context(0)
+    assert ei.value.code == L.ERR_CUDA and "no CPU path" in ei.value.msg
+    import tidypopgen_b200 as tpg
+    X = tpg.FBMCode256.from_matrix(np.array([[0.0, 1, 2], [2, 1, 0]]))
+    with pytest.raises(L.TpgError):
+        tpg.snp_king(X)

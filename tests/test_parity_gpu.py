@@ -1,0 +1,361 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle and
+the reference's golden vectors.  Integer counts and the FP64 statistics must be bit-exact
+(NaN payloads aside); GRM within 1e-10 absolute (north_star) — in practice ~1e-15."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import tidypopgen_b200 as tpg
+from conftest import EXAMPLE_7x6, TOY_3x6, TOY_3x6_NA, same
+from oracle import oracle as O
+from tidypopgen_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+GRM_ATOL = 1e-10
+
+
+def fbm_of(raw, n, m):
+    return tpg.FBMCode256.from_bytes(raw, n, m)
+
+
+# ------------------------------------------------------------------ the reference's own tests
+
+def test_snp_king_toy_and_blocks():
+    # tests/testthat/test_snp_king.R:50-64
+    gt = tpg.gen_tibble(TOY_3x6, indiv_id=["a", "b", "c"])
+    king = tpg.snp_king(gt.fbm)
+    ref = O.snp_king(np.fromfile(gt.fbm.backingfile, np.uint8), 3, 6)["king"]
+    assert same(king, ref)
+    assert same(tpg.snp_king(gt.fbm, block_size=3), king)
+    pk = tpg.pairwise_king(gt, as_matrix=True)
+    assert same(np.asarray(pk), king) and pk.names == ["a", "b", "c"] and "pairwise_matrix" in pk.r_class
+    t = tpg.pairwise_king(gt)
+    assert t.item1 == ["a", "a", "b"] and same(t.value, king[[0, 0, 1], [1, 2, 2]])
+
+
+def test_snp_king_families_with_missing(families):
+    # test_snp_king.R:66-81
+    f = families
+    X = tpg.FBMCode256(f["path"], f["n"], f["m"])
+    ref = O.snp_king(f["raw"], f["n"], f["m"])
+    king, K, N = tpg.snp_king_counts(X)
+    assert np.array_equal(K, ref["K"]) and np.array_equal(N, ref["N_Aa_i"])
+    assert same(king, ref["king"])
+    assert same(tpg.snp_king(X, block_size=300), king)
+    assert K[0, 1] == -32 and N[0, 1] == 326 and N[1, 0] == 309
+
+
+def test_snp_king_vs_king_binary(families):
+    # test_snp_king.R:84-131
+    f = families
+    king = tpg.snp_king(tpg.FBMCode256(f["path"], f["n"], f["m"]))
+    for i, j, v in f["kin0"]:
+        assert abs(king[i - 1, j - 1] - v) < 6e-5 and king[i - 1, j - 1] == king[j - 1, i - 1]
+    assert np.array_equal(np.diag(king), np.full(12, 0.5))
+
+
+def test_snp_ibs_toy_blocks_and_subsets():
+    # test_snp_ibs.R:28-65
+    gt = tpg.gen_tibble(TOY_3x6, indiv_id=["a", "b", "c"])
+    r = tpg.snp_ibs(gt.fbm, type="raw_counts")
+    assert r["ibs"][:][0, 1] == 9
+    r2 = tpg.snp_ibs(gt.fbm, block_size=3, type="raw_counts")
+    assert np.array_equal(r2["ibs"][:], r["ibs"][:])
+    pg = tpg.pairwise_ibs(gt, type="raw_counts")
+    assert np.array_equal(pg["ibs"][:], r["ibs"][:]) and pg["ibs"].attrs["indiv_names"] == ["a", "b", "c"]
+    prop = tpg.pairwise_ibs(gt)
+    by_hand = r["ibs"][:] / r["valid_n"][:]
+    assert same(prop.value, by_hand[[0, 0, 1], [1, 2, 2]])
+    sub = gt[[0, 2]].select_loci([1, 2, 4, 5])
+    assert tpg.pairwise_ibs(sub, type="raw_counts")["ibs"][:][0, 1] == 6
+
+
+def test_snp_ibs_vs_plink(families):
+    # test_snp_ibs.R:69-104
+    f = families
+    X = tpg.FBMCode256(f["path"], f["n"], f["m"])
+    ibs = tpg.snp_ibs(X)
+    assert np.array_equal(np.round(ibs, 6), f["mibs"])
+    assert same(tpg.snp_ibs(X, type="adjusted_counts"), O.snp_ibs(f["raw"], 12, 961, type="adjusted_counts")["out"])
+
+
+def test_allele_sharing_toy():
+    # test_pairwise_allele_sharing.R:29-46
+    gt = tpg.gen_tibble(TOY_3x6_NA, indiv_id=["a", "b", "c"])
+    raw = np.fromfile(gt.fbm.backingfile, np.uint8)
+    a = tpg.snp_allele_sharing(gt.fbm)
+    assert same(a, O.snp_allele_sharing(raw, 3, 6)["as"])
+    assert same(tpg.snp_allele_sharing(gt.fbm, block_size=3), a)
+    assert same(np.asarray(tpg.pairwise_allele_sharing(gt, as_matrix=True)), a)
+
+
+def test_pairwise_grm_example(example_gt):
+    # test_pairwise_grm.R:33-40
+    e = example_gt
+    gt = tpg.gen_tibble(tpg.FBMCode256(e["path"], 7, 6), indiv_id=list("abcdefg"))
+    ref, mb = O.grm_from_as(O.snp_allele_sharing(e["raw"], 7, 6)["as"])
+    g = tpg.pairwise_grm(gt)
+    assert np.allclose(np.asarray(g), ref, rtol=0, atol=GRM_ATOL)
+    assert abs(g[0, 0] - 0.396947) < 1e-6 and abs(g[1, 1] - 1.519084) < 1e-6
+    as_m = tpg.pairwise_allele_sharing(gt, as_matrix=True)
+    g2 = tpg.pairwise_grm(gt, allele_sharing_mat=as_m)
+    assert np.allclose(np.asarray(g2), ref, rtol=0, atol=GRM_ATOL)
+
+
+def test_example_gt_nan_pattern(example_gt):
+    # test_autoplot_pairwise.R:17-24 pins 0/0 -> NaN in KING on the example
+    e = example_gt
+    X = tpg.FBMCode256(e["path"], 7, 6)
+    king, K, N = tpg.snp_king_counts(X)
+    ref = O.snp_king(e["raw"], 7, 6)
+    assert same(king, ref["king"]) and np.isnan(king[1, 2]) and np.isnan(king[5, 6]) and king[1, 4] == -1.25
+    assert K[0].tolist() == [4, 1, 1, 2, 2, 0, 2] and N[0].tolist() == [4, 3, 3, 4, 4, 3, 4]
+    r = tpg.snp_ibs(X, type="raw_counts")
+    assert r["ibs"][:][0].tolist() == [12, 8, 7, 10, 9, 6, 7]
+    assert r["valid_n"][:][0].tolist() == [12, 10, 10, 12, 12, 10, 10]
+
+
+# ------------------------------------------------------------------ randomized parity vs the oracle
+
+def random_bk(rng, n, m, p_missing=0.05, codes=(0, 1, 2, 3)):
+    p = np.array([0.45, 0.3, 0.25]) * (1 - p_missing)
+    extra = len(codes) - 3
+    probs = np.concatenate([p, np.full(extra, p_missing / extra)])
+    return rng.choice(np.array(codes, np.uint8), size=(m, n), p=probs).reshape(-1)
+
+
+CASES = [
+    # n, m, block_size, gpu_chunk_loci, rows, cols
+    (1, 5, None, 0, "all", "all"),
+    (2, 1, None, 0, "all", "all"),
+    (33, 257, 50, 128, "all", "all"),
+    (129, 1000, 333, 256, "all", "all"),
+    (257, 700, None, 0, "all", "all"),          # second row tile, ragged
+    (300, 2000, 777, 512, "shuffle", "shuffle"),
+    (130, 900, 100, 0, "subset", "subset"),
+    (64, 1500, 1, 384, "dup", "every3"),        # duplicated rows, block.size = 1
+    (513, 300, None, 0, "window", "window"),
+]
+
+
+def pick(kind, total, rng):
+    if kind == "all":
+        return None
+    idx = np.arange(1, total + 1)
+    if kind == "shuffle":
+        return rng.permutation(idx).astype(np.int32)
+    if kind == "subset":
+        return np.sort(rng.choice(idx, size=max(1, total * 7 // 10), replace=False)).astype(np.int32)[::-1].copy()
+    if kind == "dup":
+        return rng.choice(idx, size=total, replace=True).astype(np.int32)
+    if kind == "every3":
+        tail = rng.permutation(idx)[: max(1, total // 20)]
+        return np.concatenate([idx[::3], tail]).astype(np.int32)
+    if kind == "window":
+        lo = total // 5
+        return idx[lo: lo + max(1, total // 2)].astype(np.int32)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"n{c[0]}_m{c[1]}_{c[4]}" for c in CASES])
+@pytest.mark.parametrize("k_major", [False, True], ids=["mn", "kmajor"])
+def test_random_parity_all_stats(case, k_major):
+    n_tot, m_tot, bs, chunk, rk, ck = case
+    rng = np.random.default_rng(n_tot * 1000 + m_tot)
+    raw = random_bk(rng, n_tot, m_tot, 0.08, codes=(0, 1, 2, 3, 4, 5, 6, 255))
+    X = fbm_of(raw, n_tot, m_tot)
+    rows, cols = pick(rk, n_tot, rng), pick(ck, m_tot, rng)
+    kw = dict(gpu_chunk_loci=chunk, flags=L.FLAG_PLANES_K_MAJOR if k_major else 0)
+    ref_k = O.snp_king(raw, n_tot, m_tot, rows, cols, block_size_=bs)
+    king, K, N = tpg.snp_king_counts(X, rows, cols, block_size=bs, **kw)
+    assert np.array_equal(K, ref_k["K"]), "KING numerator"
+    assert np.array_equal(N, ref_k["N_Aa_i"]), "N_Aa_i"
+    assert same(king, ref_k["king"]), "KING"
+    for typ in ("raw_counts", "proportion", "adjusted_counts"):
+        ref_i = O.snp_ibs(raw, n_tot, m_tot, rows, cols, type=typ, block_size_=bs)
+        got = tpg.snp_ibs(X, rows, cols, type=typ, block_size=bs, **kw)
+        if typ == "raw_counts":
+            assert np.array_equal(got["ibs"][:], ref_i["ibs"]) and np.array_equal(got["valid_n"][:], ref_i["valid_n"])
+        else:
+            assert same(got, ref_i["out"]), typ
+    ref_a = O.snp_allele_sharing(raw, n_tot, m_tot, rows, cols, block_size_=bs)
+    a, num, den = tpg.snp_allele_sharing_counts(X, rows, cols, block_size=bs, **kw)
+    assert np.array_equal(num, ref_a["num"]) and np.array_equal(den, ref_a["denom"])
+    assert same(a, ref_a["as"]) and np.array_equal(O.is_na(a), O.is_na(ref_a["as"]))
+    g = tpg.snp_grm(X, rows, cols, block_size=bs, **kw)
+    ref_g, _ = O.grm_from_as(ref_a["as"])
+    ok = ~np.isnan(ref_g)
+    assert np.array_equal(np.isnan(g), ~ok) and np.allclose(g[ok], ref_g[ok], rtol=0, atol=GRM_ATOL)
+
+
+def test_pad_quirk_switch():
+    rng = np.random.default_rng(5)
+    raw = random_bk(rng, 50, 1001)
+    X = fbm_of(raw, 50, 1001)
+    assert O.n_short(1001, 100) > 0
+    with_q, num_q, _ = tpg.snp_allele_sharing_counts(X, block_size=100)
+    clean, num_c, _ = tpg.snp_allele_sharing_counts(X, block_size=100, pad_quirk=False)
+    assert np.array_equal(num_q, num_c + O.n_short(1001, 100))
+    assert same(with_q, O.snp_allele_sharing(raw, 50, 1001, block_size_=100)["as"])
+    assert same(clean, O.snp_allele_sharing(raw, 50, 1001, block_size_=1001)["as"])  # one block: no quirk
+
+
+def test_all_missing_and_haploid_na_code():
+    # every genotype missing -> KING NaN, IBS NaN, AS NA_real_
+    raw = np.full(20 * 10, 3, np.uint8)
+    X = fbm_of(raw, 10, 20)
+    assert np.all(np.isnan(tpg.snp_king(X))) and np.all(np.isnan(tpg.snp_ibs(X)))
+    assert np.all(O.is_na(tpg.snp_allele_sharing(X)))
+    # all-haploid FBM: NA byte is 2 (max_ploidy + 1) and this path counts it as hom-alt
+    rng = np.random.default_rng(9)
+    raw = rng.choice(np.array([0, 1, 2], np.uint8), size=40 * 9).astype(np.uint8)
+    assert same(tpg.snp_king(fbm_of(raw, 9, 40)), O.snp_king(raw, 9, 40)["king"])
+
+
+def test_sources_file_host_device_agree(families):
+    import torch
+    f = families
+    X = tpg.FBMCode256(f["path"], f["n"], f["m"])
+    ref = O.snp_king(f["raw"], 12, 961)["king"]
+    a = tpg.snp_king(X)
+    host = np.array(f["raw"])
+    b = tpg.snp_king(X, src=(L.SRC_HOST, host.ctypes.data, host))
+    dev = torch.from_numpy(host).cuda()
+    c = tpg.snp_king(X, src=(L.SRC_DEVICE, dev.data_ptr(), dev), ind_col=np.arange(961, 0, -1))
+    pinned = torch.from_numpy(host).pin_memory()
+    d = tpg.snp_king(X, src=(L.SRC_HOST, pinned.data_ptr(), pinned))
+    assert same(a, ref) and same(b, ref) and same(c, ref) and same(d, ref)
+
+
+def test_errors():
+    X = tpg.FBMCode256.from_matrix(TOY_3x6)
+    with pytest.raises(L.TpgError, match="out of bounds") as e:
+        tpg.snp_king(X, ind_row=[1, 4])
+    assert e.value.code == L.ERR_ARG
+    with pytest.raises(L.TpgError, match="out of bounds"):
+        tpg.snp_ibs(X, ind_col=[0, 1])
+    with pytest.raises(ValueError):
+        tpg.snp_king(X, ind_row=[])
+    X.backingfile = "/nonexistent/file.bk"
+    with pytest.raises(L.TpgError) as e:
+        tpg.snp_king(X)
+    assert e.value.code == L.ERR_IO
+
+
+# ------------------------------------------------------------------ kernel-level parity
+
+def planes_ref(g):
+    return ((g == 2).astype(np.int8) - (g == 0).astype(np.int8), (g <= 2).astype(np.int8), (g == 1).astype(np.int8))
+
+
+@pytest.mark.parametrize("k_major", [False, True])
+@pytest.mark.parametrize("gather", [False, True])
+def test_decode_planes_kernel(k_major, gather):
+    import torch
+    ctx = L.Context(0)
+    rng = np.random.default_rng(1)
+    nrow, ncol = 929, 700
+    raw = rng.integers(0, 256, size=(ncol, nrow)).astype(np.uint8)
+    raw[rng.random(raw.shape) < 0.8] %= 4
+    if gather:
+        rows = rng.permutation(nrow)[:613].astype(np.int32)
+        cols = rng.permutation(ncol)[:391].astype(np.int32)
+    else:
+        rows = np.arange(5, 5 + 801, dtype=np.int32)
+        cols = np.arange(3, 3 + 515, dtype=np.int32)
+    n, lc = len(rows), len(cols)
+    n_pad, lc_pad = (n + 255) // 256 * 256, (lc + 127) // 128 * 128
+    d_raw = torch.from_numpy(raw.reshape(-1)).cuda()
+    d_rows, d_cols = torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda()
+    ps = n_pad * lc_pad
+    d_planes = torch.full((3 * ps,), 77, dtype=torch.int8, device="cuda")
+    eb = L.errbuf()
+    L.check(L.lib().tpg_decode_planes(ctx.handle, d_raw.data_ptr(), raw.size, nrow,
+                                      d_rows.data_ptr() if gather else None, int(rows[0]), n, n_pad,
+                                      d_cols.data_ptr() if gather else None, int(cols[0]), lc, lc_pad,
+                                      d_planes.data_ptr(), ps, int(k_major), eb, len(eb)), eb)
+    got = d_planes.cpu().numpy().reshape(3, -1)
+    ref = np.zeros((3, n_pad, lc_pad), np.int8)
+    for p, x in enumerate(planes_ref(raw[np.ix_(cols, rows)].T)):
+        ref[p, :n, :lc] = x
+    got = got.reshape(3, n_pad, lc_pad) if k_major else got.reshape(3, lc_pad, n_pad).transpose(0, 2, 1)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("k_major", [False, True])
+@pytest.mark.parametrize("shape", [(256, 128), (512, 1152), (1024, 4096)])
+def test_gram_kernel(k_major, shape):
+    import torch
+    n_pad, lc_pad = shape
+    ctx = L.Context(0)
+    rng = np.random.default_rng(2)
+    g = rng.choice(np.array([0, 1, 2, 3], np.uint8), size=(n_pad, lc_pad), p=[.4, .3, .25, .05])
+    planes = planes_ref(g)
+    host = np.stack([p if k_major else p.T for p in planes]).copy()
+    d_planes = torch.from_numpy(host.reshape(-1)).cuda()
+    d_counts = torch.zeros(4 * n_pad * n_pad, dtype=torch.int32, device="cuda")
+    eb, ms = L.errbuf(), C.c_float(0)
+    for rep in range(2):  # two launches accumulate
+        L.check(L.lib().tpg_gram(ctx.handle, d_planes.data_ptr(), n_pad * lc_pad, n_pad, lc_pad, int(k_major),
+                                 0b1111, 0, 1, d_counts.data_ptr(), C.byref(ms), eb, len(eb)), eb)
+    got = d_counts.cpu().numpy().reshape(4, n_pad, n_pad).transpose(0, 2, 1)  # [mat][i][j]
+    d, nm, h1 = [p.astype(np.float64) for p in planes]
+    iu = np.triu_indices(n_pad)
+    for mat, ref in ((L.MAT_DD, d @ d.T), (L.MAT_NN, nm @ nm.T), (L.MAT_HH, h1 @ h1.T)):
+        assert np.array_equal(got[mat][iu], 2 * ref[iu].astype(np.int64)), mat
+    assert np.array_equal(got[L.MAT_HN], 2 * (h1 @ nm.T).astype(np.int64))
+
+
+def test_synth_device_equals_host():
+    import torch
+    ctx = L.Context(0)
+    nrow, ncol = 301, 999
+    d = torch.zeros(nrow * ncol, dtype=torch.uint8, device="cuda")
+    eb = L.errbuf()
+    for mode in (0, 1, 2):
+        L.check(L.lib().tpg_synth_fill(ctx.handle, d.data_ptr(), nrow, ncol, 17, 2026, 0.1, mode, eb, len(eb)), eb)
+        h = np.zeros(nrow * ncol, np.uint8)
+        L.lib().tpg_synth_fill_host(h.ctypes.data, nrow, ncol, 17, 2026, 0.1, mode)
+        assert np.array_equal(d.cpu().numpy(), h), mode
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE configs[1])
+
+def test_hgdp_shape_properties():
+    """929 x 650,000, 2% missing — too big for the oracle; size-independent properties instead:
+    linearity over loci (counts of A u B = counts(A) + counts(B)), chunk-size invariance,
+    operand-layout invariance, symmetry, diagonal identities, and a subsample checked
+    against the oracle."""
+    import torch
+    n, m = 929, 650_000
+    ctx = L.Context(0)
+    dev = torch.empty(n * m, dtype=torch.uint8, device="cuda")
+    eb = L.errbuf()
+    L.check(L.lib().tpg_synth_fill(ctx.handle, dev.data_ptr(), n, m, 0, 20260002, 0.02, 0, eb, len(eb)), eb)
+    X = tpg.FBMCode256.__new__(tpg.FBMCode256)
+    X.backingfile, X.nrow, X.ncol, X.code256 = "<device>", n, m, None
+    src = (L.SRC_DEVICE, dev.data_ptr(), dev)
+    king, K, N = tpg.snp_king_counts(X, src=src)
+    cut = 271_001
+    a = tpg.snp_king_counts(X, ind_col=np.arange(1, cut + 1, dtype=np.int32), src=src, gpu_chunk_loci=65536)
+    b = tpg.snp_king_counts(X, ind_col=np.arange(cut + 1, m + 1, dtype=np.int32), src=src,
+                            flags=L.FLAG_PLANES_K_MAJOR)
+    assert np.array_equal(K, a[1] + b[1]) and np.array_equal(N, a[2] + b[2])          # linearity
+    assert np.array_equal(king, king.T) and np.array_equal(K, K.T)                     # symmetry
+    assert np.array_equal(np.diag(king), np.full(n, 0.5))                              # KING(i,i) = 0.5
+    het = np.diag(N)
+    assert np.array_equal(np.diag(K), het)                                             # K(i,i) = #het_i
+    r = tpg.snp_ibs(X, type="raw_counts", src=src)
+    ibs, valid = r["ibs"][:], r["valid_n"][:]
+    assert np.array_equal(np.diag(ibs), np.diag(valid)) and np.all(ibs <= valid) and valid.max() <= 2 * m
+    assert abs(np.diag(valid).mean() / (2 * m) - 0.98) < 0.002                         # 2% missing
+    # a 1,200-locus subsample against the oracle
+    cols = np.sort(np.random.default_rng(0).choice(m, 1200, replace=False)).astype(np.int32) + 1
+    host = np.zeros(n * m, np.uint8)
+    L.lib().tpg_synth_fill_host(host.ctypes.data, n, m, 0, 20260002, 0.02, 0)
+    assert np.array_equal(dev.cpu().numpy(), host)
+    sub = tpg.snp_king_counts(X, ind_col=cols, src=src)
+    ref = O.snp_king(host, n, m, None, cols)
+    assert np.array_equal(sub[1], ref["K"]) and np.array_equal(sub[2], ref["N_Aa_i"]) and same(sub[0], ref["king"])

@@ -104,6 +104,9 @@ SIGNATURES = {
     "tpg_grm_from_as": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_double)] + _ERR),
     "tpg_ctx_create": (C.c_void_p, [C.c_int] + _ERR),
     "tpg_ctx_destroy": (None, [C.c_void_p]),
+    "tpg_ctx_trim": (None, [C.c_void_p]),
+    "tpg_release": (None, [C.c_int]),
+    "tpg_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "tpg_counts_ld": (C.c_int64, [C.c_int64]),
     "tpg_counts_elems": (C.c_int64, [C.c_int64]),
     "tpg_accumulate": (C.c_int, [C.c_void_p, C.POINTER(Job), C.c_void_p, C.POINTER(Stats)] + _ERR),

@@ -130,6 +130,43 @@ int check_err_flag(Ctx* ctx, const Err& E) {
   return TPG_OK;
 }
 
+int ensure_slot(Ctx::Slot* s, size_t bytes, bool host, const char* what, const Err& E) {
+  if (s->cap >= bytes && s->p) return TPG_OK;
+  if (s->p) { if (host) cudaFreeHost(s->p); else cudaFree(s->p); }
+  s->p = nullptr;
+  s->cap = 0;
+  const size_t want = bytes + bytes / 16 + 256;  // a little headroom against near-miss regrowth
+  cudaError_t e = host ? cudaMallocHost(&s->p, want) : cudaMalloc(&s->p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    s->p = nullptr;
+    return E.fail(TPG_ERR_NOMEM, "cannot allocate %zu bytes of %s (%s)", want, what, cudaGetErrorString(e));
+  }
+  s->cap = want;
+  return TPG_OK;
+}
+
+void trim_ctx(Ctx* c) {
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  Ctx::Slot* dev[] = {&c->d_raw[0], &c->d_raw[1], &c->d_planes[0], &c->d_planes[1], &c->d_rows,
+                      &c->d_cols, &c->d_counts, &c->d_out[0], &c->d_out[1], &c->d_out[2],
+                      &c->d_out[3], &c->d_red};
+  for (Ctx::Slot* s : dev) { if (s->p) cudaFree(s->p); s->p = nullptr; s->cap = 0; }
+  for (Ctx::Slot& s : c->h_pin) { if (s.p) cudaFreeHost(s.p); s.p = nullptr; s.cap = 0; }
+}
+
+cudaEvent_t pooled_event(Ctx* c, bool timing) {
+  std::vector<cudaEvent_t>& pool = timing ? c->ev_timing : c->ev_plain;
+  size_t& used = timing ? c->ev_timing_used : c->ev_plain_used;
+  if (used == pool.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming);
+    pool.push_back(e);
+  }
+  return pool[used++];
+}
+
 // ------------------------------------------------------------------ job plumbing
 
 struct Plan {
@@ -272,32 +309,6 @@ static int open_source(const tpg_job* job, Mapped* mp, const Err& E) {
   return E.fail(TPG_ERR_ARG, "unknown src_kind %d", job->src_kind);
 }
 
-// RAII bundle of the per-job device / pinned buffers.
-struct Buffers {
-  uint8_t* d_raw[2] = {nullptr, nullptr};
-  int8_t* d_planes[2] = {nullptr, nullptr};
-  uint8_t* h_pin[2] = {nullptr, nullptr};
-  int32_t* d_rows = nullptr;
-  int32_t* d_cols = nullptr;
-  std::vector<cudaEvent_t> events;
-  ~Buffers() {
-    for (int b = 0; b < 2; ++b) {
-      if (d_raw[b]) cudaFree(d_raw[b]);
-      if (d_planes[b]) cudaFree(d_planes[b]);
-      if (h_pin[b]) cudaFreeHost(h_pin[b]);
-    }
-    if (d_rows) cudaFree(d_rows);
-    if (d_cols) cudaFree(d_cols);
-    for (cudaEvent_t e : events) cudaEventDestroy(e);
-  }
-  cudaEvent_t ev(bool timing) {
-    cudaEvent_t e = nullptr;
-    cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming);
-    events.push_back(e);
-    return e;
-  }
-};
-
 static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_stats* st,
                            const Err& E) {
   const double t_begin = now_ms();
@@ -339,26 +350,36 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   const int64_t n_chunks = (pl.m_shard + lc - 1) / lc;
   const int64_t plane_stride = pl.n_pad * lc;
 
-  Buffers B;
+  struct { uint8_t* d_raw[2]; int8_t* d_planes[2]; uint8_t* h_pin[2]; int32_t* d_rows; int32_t* d_cols;
+           Ctx* c; cudaEvent_t ev(bool t) { return pooled_event(c, t); } } B{};
+  B.c = ctx;
+  ctx->ev_timing_used = ctx->ev_plain_used = 0;
   for (int b = 0; b < 2 && b < n_chunks; ++b) {
-    if (cudaMalloc(&B.d_planes[b], size_t(plane_stride) * pl.nplanes) != cudaSuccess)
-      return E.fail(TPG_ERR_NOMEM, "cannot allocate %lld bytes of plane storage", (long long)plane_stride * pl.nplanes);
+    rc = ensure_slot(&ctx->d_planes[b], size_t(plane_stride) * pl.nplanes, false, "plane storage", E);
+    if (rc) return rc;
+    B.d_planes[b] = static_cast<int8_t*>(ctx->d_planes[b].p);
     if (!on_device) {
-      if (cudaMalloc(&B.d_raw[b], size_t(span * lc) + 16) != cudaSuccess)
-        return E.fail(TPG_ERR_NOMEM, "cannot allocate %lld bytes of raw chunk storage", (long long)(span * lc));
-      if (cudaMallocHost(&B.h_pin[b], size_t(span * lc)) != cudaSuccess)
-        return E.fail(TPG_ERR_NOMEM, "cannot allocate %lld bytes of pinned staging", (long long)(span * lc));
+      rc = ensure_slot(&ctx->d_raw[b], size_t(span * lc) + 16, false, "raw chunk storage", E);
+      if (rc) return rc;
+      rc = ensure_slot(&ctx->h_pin[b], size_t(span * lc), true, "pinned staging", E);
+      if (rc) return rc;
+      B.d_raw[b] = static_cast<uint8_t*>(ctx->d_raw[b].p);
+      B.h_pin[b] = static_cast<uint8_t*>(ctx->h_pin[b].p);
     }
   }
   if (!pl.rows_contig) {
     // staged columns start at raw row rlo
     std::vector<int32_t> rel(pl.rows0);
     if (!on_device) for (auto& r : rel) r -= int32_t(rlo);
-    TPG_CUDA_OK(cudaMalloc(&B.d_rows, sizeof(int32_t) * pl.n), E);
+    rc = ensure_slot(&ctx->d_rows, sizeof(int32_t) * pl.n, false, "row index", E);
+    if (rc) return rc;
+    B.d_rows = static_cast<int32_t*>(ctx->d_rows.p);
     TPG_CUDA_OK(cudaMemcpy(B.d_rows, rel.data(), sizeof(int32_t) * pl.n, cudaMemcpyHostToDevice), E);
   }
   if (on_device && !pl.cols_contig) {
-    TPG_CUDA_OK(cudaMalloc(&B.d_cols, sizeof(int32_t) * pl.m_shard), E);
+    rc = ensure_slot(&ctx->d_cols, sizeof(int32_t) * pl.m_shard, false, "column index", E);
+    if (rc) return rc;
+    B.d_cols = static_cast<int32_t*>(ctx->d_cols.p);
     TPG_CUDA_OK(cudaMemcpy(B.d_cols, pl.cols0.data(), sizeof(int32_t) * pl.m_shard, cudaMemcpyHostToDevice), E);
   }
 
@@ -498,17 +519,18 @@ static int finish_impl(Ctx* ctx, const tpg_job* job, const int32_t* d_counts, tp
   double* host[4] = {res->out0, res->out1, res->aux0, res->aux1};
   double* dev[4] = {nullptr, nullptr, nullptr, nullptr};
   const size_t bytes = sizeof(double) * size_t(n) * size_t(n);
-  struct Guard { double** d; bool own; ~Guard() { if (own) for (int o = 0; o < 4; ++o) if (d[o]) cudaFree(d[o]); } } guard{dev, !res->out_on_device};
   for (int o = 0; o < 4; ++o) {
     if (!host[o]) continue;
     if (res->out_on_device) { dev[o] = host[o]; continue; }
-    if (cudaMalloc(&dev[o], bytes) != cudaSuccess) return E.fail(TPG_ERR_NOMEM, "cannot allocate %zu bytes for the result", bytes);
+    int rc0 = ensure_slot(&ctx->d_out[o], bytes, false, "result matrix", E);
+    if (rc0) return rc0;
+    dev[o] = static_cast<double*>(ctx->d_out[o].p);
     if (fa.shard_world > 1)  // blocks of other ranks: leave the caller's values untouched
       TPG_CUDA_OK(cudaMemcpyAsync(dev[o], host[o], bytes, cudaMemcpyHostToDevice, ctx->s_compute), E);
   }
   fa.out0 = dev[0]; fa.out1 = dev[1]; fa.aux0 = dev[2]; fa.aux1 = dev[3];
-  cudaEvent_t e0, e1, e2;
-  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  ctx->ev_timing_used = 0;
+  cudaEvent_t e0 = pooled_event(ctx, true), e1 = pooled_event(ctx, true), e2 = pooled_event(ctx, true);
   cudaEventRecord(e0, ctx->s_compute);
   int rc = launch_finish(ctx, fa, ctx->s_compute, E);
   cudaEventRecord(e1, ctx->s_compute);
@@ -528,7 +550,6 @@ static int finish_impl(Ctx* ctx, const tpg_job* job, const int32_t* d_counts, tp
     cudaEventElapsedTime(&ms, e0, e1); res->stats.ms_finish += ms;
     cudaEventElapsedTime(&ms, e1, e2); res->stats.ms_d2h += ms;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
   res->stats.ms_total += now_ms() - t_begin;
   res->stats.n_launches = ctx->launches;
   return rc;
@@ -589,12 +610,27 @@ tpg_ctx* tpg_ctx_create(int device, char* err, size_t errlen) {
 void tpg_ctx_destroy(tpg_ctx* h) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
   if (!c) return;
-  cudaSetDevice(c->device);
+  trim_ctx(c);
+  for (cudaEvent_t e : c->ev_timing) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_plain) cudaEventDestroy(e);
   if (c->s_compute) cudaStreamDestroy(c->s_compute);
   if (c->s_copy) cudaStreamDestroy(c->s_copy);
   if (c->d_err_flag) cudaFree(c->d_err_flag);
   if (c->d_items) cudaFree(c->d_items);
   delete c;
+}
+
+void tpg_ctx_trim(tpg_ctx* h) {
+  if (h) trim_ctx(reinterpret_cast<Ctx*>(h));
+}
+
+void* tpg_ctx_stream(tpg_ctx* h) {
+  return h ? reinterpret_cast<void*>(reinterpret_cast<Ctx*>(h)->s_compute) : nullptr;
+}
+
+void tpg_release(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (device >= 0 && device < 64 && g_ctx[device]) trim_ctx(g_ctx[device]);
 }
 
 int tpg_accumulate(tpg_ctx* h, const tpg_job* job, int32_t* d_counts, tpg_stats* stats, char* err,
@@ -639,17 +675,16 @@ int tpg_pairwise(const tpg_job* job, tpg_result* res, char* err, size_t errlen) 
   const int64_t n = job->ind_row ? job->n : job->nrow_total;
   if (n <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row");
   TPG_CUDA_OK(cudaSetDevice(c->device), E);
-  int32_t* d_counts = nullptr;
   const size_t cbytes = sizeof(int32_t) * size_t(tpg_counts_elems(n));
-  if (cudaMalloc(&d_counts, cbytes) != cudaSuccess)
-    return E.fail(TPG_ERR_NOMEM, "cannot allocate %zu bytes for the count matrices", cbytes);
+  rc = ensure_slot(&c->d_counts, cbytes, false, "count matrices", E);
+  if (rc) return rc;
+  int32_t* d_counts = static_cast<int32_t*>(c->d_counts.p);
   cudaError_t e = cudaMemsetAsync(d_counts, 0, cbytes, c->s_compute);
-  if (e != cudaSuccess) { cudaFree(d_counts); return E.fail(TPG_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) return E.fail(TPG_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
   rc = accumulate_impl(c, job, d_counts, &res->stats, E);
   if (rc == TPG_OK) {
     rc = finish_impl(c, job, d_counts, res, E);
   }
-  cudaFree(d_counts);
   res->stats.n_launches = c->launches - l0;
   return rc;
 }

@@ -179,8 +179,10 @@ grm_apply_kernel(const double* as, int64_t total, const double* mbp, double* out
 
 int launch_grm(Ctx* ctx, const double* d_as, int64_t n, double* d_grm, double* mb_host,
                cudaStream_t st, const Err& E) {
-  double* d_ps = nullptr;
-  TPG_CUDA_OK(cudaMalloc(&d_ps, kRedBlocks * (sizeof(double) + sizeof(unsigned long long)) + 16), E);
+  int rc = ensure_slot(&ctx->d_red, kRedBlocks * (sizeof(double) + sizeof(unsigned long long)) + 16,
+                       false, "reduction scratch", E);
+  if (rc) return rc;
+  double* d_ps = static_cast<double*>(ctx->d_red.p);
   unsigned long long* d_pc = reinterpret_cast<unsigned long long*>(d_ps + kRedBlocks);
   double* d_mb = reinterpret_cast<double*>(d_pc + kRedBlocks);
   const int64_t total = n * n;
@@ -194,7 +196,6 @@ int launch_grm(Ctx* ctx, const double* d_as, int64_t n, double* d_grm, double* m
   double mb = 0;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&mb, d_mb, sizeof(double), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(d_ps);
   if (e != cudaSuccess) return E.fail(TPG_ERR_CUDA, "grm kernels failed: %s", cudaGetErrorString(e));
   if (mb_host) *mb_host = mb;
   return TPG_OK;

@@ -38,7 +38,17 @@ struct Ctx {
   std::string items_key;           // geometry the uploaded list was built for
   void* encode_tiled = nullptr;    // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
   int64_t launches = 0;
+  // Grow-only buffer cache, reused across jobs (cudaMalloc / cudaMallocHost / cudaFree are
+  // slow and synchronising; a job must not pay them every call).  tpg_ctx_trim() frees it.
+  struct Slot { void* p = nullptr; size_t cap = 0; };
+  Slot d_raw[2], d_planes[2], h_pin[2], d_rows, d_cols, d_counts, d_out[4], d_red;
+  std::vector<cudaEvent_t> ev_timing, ev_plain;
+  size_t ev_timing_used = 0, ev_plain_used = 0;
 };
+// Ensures slot holds >= bytes (device memory, or pinned host memory when host = true).
+int ensure_slot(Ctx::Slot* s, size_t bytes, bool host, const char* what, const struct Err& E);
+void trim_ctx(Ctx* c);
+cudaEvent_t pooled_event(Ctx* c, bool timing);
 
 struct Err {
   char* buf;
