@@ -192,14 +192,14 @@ def test_random_parity_all_stats(case, k_major):
 
 def test_pad_quirk_switch():
     rng = np.random.default_rng(5)
-    raw = random_bk(rng, 50, 1001)
-    X = fbm_of(raw, 50, 1001)
-    assert O.n_short(1001, 100) > 0
+    raw = random_bk(rng, 50, 1003)
+    X = fbm_of(raw, 50, 1003)
+    assert O.n_short(1003, 100) > 0
     with_q, num_q, _ = tpg.snp_allele_sharing_counts(X, block_size=100)
     clean, num_c, _ = tpg.snp_allele_sharing_counts(X, block_size=100, pad_quirk=False)
-    assert np.array_equal(num_q, num_c + O.n_short(1001, 100))
-    assert same(with_q, O.snp_allele_sharing(raw, 50, 1001, block_size_=100)["as"])
-    assert same(clean, O.snp_allele_sharing(raw, 50, 1001, block_size_=1001)["as"])  # one block: no quirk
+    assert np.array_equal(num_q, num_c + O.n_short(1003, 100))
+    assert same(with_q, O.snp_allele_sharing(raw, 50, 1003, block_size_=100)["as"])
+    assert same(clean, O.snp_allele_sharing(raw, 50, 1003, block_size_=1003)["as"])  # one block: no quirk
 
 
 def test_all_missing_and_haploid_na_code():

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <fcntl.h>
 #include <mutex>
+#include <thread>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -309,6 +310,29 @@ static int open_source(const tpg_job* job, Mapped* mp, const Err& E) {
   return E.fail(TPG_ERR_ARG, "unknown src_kind %d", job->src_kind);
 }
 
+// Host staging is a memory-bandwidth job: split it over a few threads (one memcpy stream
+// tops out far below what PCIe 5 can take).
+template <class F>
+static void parallel_for(int64_t n, int64_t grain, F&& body) {
+  int nt = int(std::min<int64_t>(8, std::max<int64_t>(1, n / std::max<int64_t>(grain, 1))));
+  const unsigned hw = std::thread::hardware_concurrency();
+  if (hw && nt > int(hw)) nt = int(hw);
+  if (nt <= 1) { body(int64_t(0), n); return; }
+  std::vector<std::thread> th;
+  th.reserve(nt);
+  for (int t = 0; t < nt; ++t) {
+    const int64_t a = n * t / nt, b = n * (t + 1) / nt;
+    th.emplace_back([&body, a, b] { body(a, b); });
+  }
+  for (auto& x : th) x.join();
+}
+
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
 static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_stats* st,
                            const Err& E) {
   const double t_begin = now_ms();
@@ -332,7 +356,10 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     rlo = nrow; rhi = 0;
     for (int32_t r : pl.rows0) { rlo = std::min<int64_t>(rlo, r); rhi = std::max<int64_t>(rhi, r + 1); }
   }
-  const int64_t span = on_device ? nrow : rhi - rlo;  // bytes per staged column
+  int64_t span = on_device ? nrow : rhi - rlo;  // bytes per staged column
+  // Pinned (or cudaHostRegister'ed) source with whole contiguous columns: DMA straight from it.
+  const bool direct = !on_device && job->src_kind == TPG_SRC_HOST && pl.cols_contig && is_pinned_host(src.base);
+  if (direct) { span = nrow; rlo = 0; }
 
   // ---- chunk size (loci per GPU chunk), decoupled from R's block.size
   size_t free_b = 0, total_b = 0;
@@ -361,10 +388,12 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     if (!on_device) {
       rc = ensure_slot(&ctx->d_raw[b], size_t(span * lc) + 16, false, "raw chunk storage", E);
       if (rc) return rc;
-      rc = ensure_slot(&ctx->h_pin[b], size_t(span * lc), true, "pinned staging", E);
-      if (rc) return rc;
       B.d_raw[b] = static_cast<uint8_t*>(ctx->d_raw[b].p);
-      B.h_pin[b] = static_cast<uint8_t*>(ctx->h_pin[b].p);
+      if (!direct) {
+        rc = ensure_slot(&ctx->h_pin[b], size_t(span * lc), true, "pinned staging", E);
+        if (rc) return rc;
+        B.h_pin[b] = static_cast<uint8_t*>(ctx->h_pin[b].p);
+      }
     }
   }
   if (!pl.rows_contig) {
@@ -419,16 +448,27 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       TPG_CUDA_OK(cudaEventRecord(tm[c].c1, ctx->s_copy), E);
     } else {
       // ---- stage the chunk's columns into pinned memory (compact, rows [rlo, rhi) only)
-      if (c >= 2) TPG_CUDA_OK(cudaEventSynchronize(ev_h2d_done[b]), E);
+      const uint8_t* hp;
       const double t0 = now_ms();
-      uint8_t* hp = B.h_pin[b];
-      if (pl.cols_contig && span == nrow) {
-        memcpy(hp, src.base + (pl.col0 + k0) * nrow, size_t(lcc * nrow));
+      if (direct) {
+        hp = src.base + (pl.col0 + k0) * nrow;
       } else {
-        for (int64_t k = k0; k < k1; ++k) {
-          const int64_t col = pl.cols_contig ? pl.col0 + k : pl.cols0[k];
-          memcpy(hp + (k - k0) * span, src.base + col * nrow + rlo, size_t(span));
+        if (c >= 2) TPG_CUDA_OK(cudaEventSynchronize(ev_h2d_done[b]), E);
+        uint8_t* stage = B.h_pin[b];
+        const uint8_t* base = src.base;
+        if (pl.cols_contig && span == nrow) {
+          const uint8_t* from = base + (pl.col0 + k0) * nrow;
+          parallel_for(lcc * nrow, int64_t(8) << 20, [=](int64_t a, int64_t e) { memcpy(stage + a, from + a, size_t(e - a)); });
+        } else {
+          const Plan* plp = &pl;
+          parallel_for(lcc, std::max<int64_t>(1, (int64_t(4) << 20) / span), [=](int64_t a, int64_t e) {
+            for (int64_t k = k0 + a; k < k0 + e; ++k) {
+              const int64_t col = plp->cols_contig ? plp->col0 + k : plp->cols0[k];
+              memcpy(stage + (k - k0) * span, base + col * nrow + rlo, size_t(span));
+            }
+          });
         }
+        hp = stage;
       }
       ms_read += now_ms() - t0;
       // ---- H2D on the copy stream, after the decode that last read this raw buffer
@@ -442,7 +482,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       da.raw = B.d_raw[b];
       da.raw_bytes = lcc * span;
       da.raw_stride = span;
-      da.row0 = pl.rows_contig ? pl.row0 - rlo : 0;
+      da.row0 = pl.rows_contig ? pl.row0 - rlo : 0;  // (direct: rlo = 0, whole columns)
       da.col_idx = nullptr;
       da.col0 = 0;
     }

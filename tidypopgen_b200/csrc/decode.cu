@@ -70,6 +70,9 @@ struct RowSel {
   bool ld;         // this lane's aligned word is needed (by itself or by lane-1's funnel shift)
 };
 
+// kSafe = the caller proved that every word this block can touch lies inside the raw buffer,
+// so the loads are unconditional and branch-free (8-16 of them stay in flight per lane).
+template <bool kSafe>
 __device__ __forceinline__ uint32_t load4(const DecodeParams& p, const RowSel& rs, int64_t col,
                                           int lane) {
   const uint8_t* cbase = p.raw + col * p.raw_stride;
@@ -83,13 +86,38 @@ __device__ __forceinline__ uint32_t load4(const DecodeParams& p, const RowSel& r
     const uint8_t* a = cbase + rs.off;
     const uint32_t sh = uint32_t(reinterpret_cast<uintptr_t>(a) & 3u);
     const uint8_t* al = a - sh;
-    // Lanes far beyond the last individual skip the load (their bytes are masked anyway).
-    uint32_t w0 = rs.ld ? guarded_ld32(al, p.raw, p.raw_end) : 0u;
-    uint32_t w1 = __shfl_down_sync(0xFFFFFFFFu, w0, 1);
-    if (lane == 31 && sh && rs.keep) w1 = guarded_ld32(al + 4, p.raw, p.raw_end);
+    uint32_t w0, w1;
+    if (kSafe) {
+      w0 = __ldg(reinterpret_cast<const uint32_t*>(al));
+      w1 = __shfl_down_sync(0xFFFFFFFFu, w0, 1);
+      if (lane == 31) w1 = __ldg(reinterpret_cast<const uint32_t*>(al) + 1);
+    } else {
+      // Lanes far beyond the last individual skip the load (their bytes are masked anyway).
+      w0 = rs.ld ? guarded_ld32(al, p.raw, p.raw_end) : 0u;
+      w1 = __shfl_down_sync(0xFFFFFFFFu, w0, 1);
+      if (lane == 31 && sh && rs.keep) w1 = guarded_ld32(al + 4, p.raw, p.raw_end);
+    }
     w = __funnelshift_r(w0, w1, sh * 8);
   }
   return (w & rs.keep) | (0x03030303u & ~rs.keep);
+}
+
+// True when all word loads of a block covering individuals [i_lo, i_hi) and the loci
+// [l0, l0 + nl) stay inside the raw buffer (3 bytes of alignment slack below, 8 above).
+__device__ __forceinline__ bool block_is_safe(const DecodeParams& p, int l0, int nl, int i_lo, int i_hi) {
+  if (p.row_idx) return true;  // gathered rows are validated indices: byte loads, always in range
+  int64_t cmin = INT64_MAX, cmax = -1;
+  for (int k = 0; k < nl; ++k) {
+    const int l = l0 + k;
+    if (l >= p.lc) break;
+    const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
+    cmin = col < cmin ? col : cmin;
+    cmax = col > cmax ? col : cmax;
+  }
+  if (cmax < 0) return true;
+  const int64_t lo = cmin * p.raw_stride + p.row0 + i_lo - 3;
+  const int64_t hi = cmax * p.raw_stride + p.row0 + i_hi + 8;
+  return lo >= 0 && hi <= int64_t(p.raw_end - p.raw);
 }
 
 __device__ __forceinline__ RowSel make_rowsel(const DecodeParams& p, int i0) {
@@ -108,16 +136,9 @@ __device__ __forceinline__ RowSel make_rowsel(const DecodeParams& p, int i0) {
 constexpr int kDecThreads = 256;
 constexpr int kDecLociPerBlock = 16;  // two batches of 8 independent loads per lane
 
-__global__ void __launch_bounds__(kDecThreads)
-decode_planes_mn_kernel(const DecodeParams p) {
-  const int lane = threadIdx.x & 31;
-  // 1-D grid, individual blocks fastest: CTAs resident together sweep whole raw columns.
-  const int nib = (p.n_pad + kDecThreads * 4 - 1) / (kDecThreads * 4);
-  const int ib = blockIdx.x % nib, lb = blockIdx.x / nib;
-  const int i0 = (ib * kDecThreads + threadIdx.x) * 4;
-  if (i0 >= p.n_pad) return;  // n_pad is a multiple of 128: whole warps leave together
-  const RowSel rs = make_rowsel(p, i0);
-  const int l0 = lb * kDecLociPerBlock;
+template <bool kSafe>
+__device__ __forceinline__ void decode_mn_body(const DecodeParams& p, const RowSel& rs, int i0, int l0,
+                                               int lane) {
 #pragma unroll
   for (int half = 0; half < kDecLociPerBlock / 8; ++half) {
     uint32_t g[8];
@@ -126,7 +147,7 @@ decode_planes_mn_kernel(const DecodeParams p) {
       const int l = l0 + half * 8 + u;
       if (l < p.lc) {
         const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
-        g[u] = load4(p, rs, col, lane);
+        g[u] = load4<kSafe>(p, rs, col, lane);
       } else {
         g[u] = 0x03030303u;  // padding loci decode to zeros
       }
@@ -145,6 +166,90 @@ decode_planes_mn_kernel(const DecodeParams p) {
   }
 }
 
+// Straight-line fast path for interior blocks (all 16 loci real, every load in range): the
+// row-gather / column-index choices are template parameters so that no branch separates the
+// loads and 8 (contiguous rows) or 32 (gathered rows) of them are in flight per lane.
+template <bool kGather, bool kColIdx>
+__device__ __forceinline__ void decode_mn_fast(const DecodeParams& p, const RowSel& rs, int i0, int l0,
+                                               int lane) {
+#pragma unroll
+  for (int half = 0; half < kDecLociPerBlock / 8; ++half) {
+    const uint8_t* cb[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int l = l0 + half * 8 + u;
+      const int64_t col = kColIdx ? int64_t(__ldg(p.col_idx + l)) : p.col0 + l;
+      cb[u] = p.raw + col * p.raw_stride;
+    }
+    uint32_t g[8];
+    if (kGather) {
+      uint32_t b0[8], b1[8], b2[8], b3[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {  // rows of padding individuals are 0 (a valid address)
+        b0[u] = __ldg(cb[u] + rs.r[0]);
+        b1[u] = __ldg(cb[u] + rs.r[1]);
+        b2[u] = __ldg(cb[u] + rs.r[2]);
+        b3[u] = __ldg(cb[u] + rs.r[3]);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) g[u] = b0[u] | (b1[u] << 8) | (b2[u] << 16) | (b3[u] << 24);
+    } else {
+      uint32_t w0[8], wx[8], sh[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint8_t* a = cb[u] + rs.off;
+        sh[u] = uint32_t(reinterpret_cast<uintptr_t>(a) & 3u);
+        const uint32_t* al = reinterpret_cast<const uint32_t*>(a - sh[u]);
+        w0[u] = __ldg(al);
+        wx[u] = 0;
+        if (lane == 31) wx[u] = __ldg(al + 1);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        uint32_t w1 = __shfl_down_sync(0xFFFFFFFFu, w0[u], 1);
+        if (lane == 31) w1 = wx[u];
+        g[u] = __funnelshift_r(w0[u], w1, sh[u] * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int l = l0 + half * 8 + u;
+      uint32_t d, nm, h1;
+      decode4((g[u] & rs.keep) | (0x03030303u & ~rs.keep), d, nm, h1);
+      int8_t* o = p.planes + int64_t(l) * p.n_pad + i0;
+      *reinterpret_cast<uint32_t*>(o) = d;
+      *reinterpret_cast<uint32_t*>(o + p.plane_stride) = nm;
+      if (p.nplanes > 2) *reinterpret_cast<uint32_t*>(o + 2 * p.plane_stride) = h1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kDecThreads)
+decode_planes_mn_kernel(const DecodeParams p) {
+  const int lane = threadIdx.x & 31;
+  // 1-D grid, individual blocks fastest: CTAs resident together sweep whole raw columns.
+  const int nib = (p.n_pad + kDecThreads * 4 - 1) / (kDecThreads * 4);
+  const int ib = blockIdx.x % nib, lb = blockIdx.x / nib;
+  const int i0 = (ib * kDecThreads + threadIdx.x) * 4;
+  if (i0 >= p.n_pad) return;  // n_pad is a multiple of 128: whole warps leave together
+  const RowSel rs = make_rowsel(p, i0);
+  const int l0 = lb * kDecLociPerBlock;
+  const bool safe = block_is_safe(p, l0, kDecLociPerBlock, ib * kDecThreads * 4, (ib + 1) * kDecThreads * 4);
+  if (safe && l0 + kDecLociPerBlock <= p.lc) {
+    if (p.row_idx) {
+      if (p.col_idx) decode_mn_fast<true, true>(p, rs, i0, l0, lane);
+      else decode_mn_fast<true, false>(p, rs, i0, l0, lane);
+    } else {
+      if (p.col_idx) decode_mn_fast<false, true>(p, rs, i0, l0, lane);
+      else decode_mn_fast<false, false>(p, rs, i0, l0, lane);
+    }
+  } else if (safe) {
+    decode_mn_body<true>(p, rs, i0, l0, lane);
+  } else {
+    decode_mn_body<false>(p, rs, i0, l0, lane);
+  }
+}
+
 // ------------------------------------------------------------------ K-major (transposing)
 // Block = 128 individuals x 128 loci; warp w owns loci [16w, 16w+16), lane owns 4 individuals.
 __global__ void __launch_bounds__(256)
@@ -156,13 +261,15 @@ decode_planes_k_kernel(const DecodeParams p) {
   const int l0 = int(blockIdx.x / nib) * 128 + warp * 16;
   if (l0 >= p.lc_pad) return;
   const RowSel rs = make_rowsel(p, i0);
+  const int ib0 = int(blockIdx.x % nib) * 128;
+  const bool safe = block_is_safe(p, l0, 16, ib0, ib0 + 128);
   uint32_t g[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     const int l = l0 + k;
     if (l < p.lc) {
       const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
-      g[k] = load4(p, rs, col, lane);
+      g[k] = safe ? load4<true>(p, rs, col, lane) : load4<false>(p, rs, col, lane);
     } else {
       g[k] = 0x03030303u;
     }
