@@ -9,13 +9,13 @@
  * Reference today                                   Replacement
  * ------------------------------------------------  -----------------------------
  * .Call(_tidypopgen_increment_king_numerator) once  ONE tpg_pairwise() per job
- *   per loci block   src/RcppExports.cpp:256-275    (stat = TPG_STAT_KING)
+ *   per loci block   src/RcppExports.cpp:289-306    (stat = TPG_STAT_KING)
  *   kernel           src/snp_king.cpp:21-74
  *   driver + finish  R/snp_king.R:32-103
  * .Call(_tidypopgen_increment_ibs_counts)           tpg_pairwise(TPG_STAT_IBS_*)
- *   src/RcppExports.cpp:276-292, src/snp_ibs.cpp:22-74, R/snp_ibs.R:42-104
+ *   src/RcppExports.cpp:272-288, src/snp_ibs.cpp:22-74, R/snp_ibs.R:42-104
  * .Call(_tidypopgen_increment_as_counts)            tpg_pairwise(TPG_STAT_AS)
- *   src/RcppExports.cpp:293-306, src/snp_as.cpp:22-67, R/snp_allele_sharing.R:33-82
+ *   src/RcppExports.cpp:256-271, src/snp_as.cpp:22-67, R/snp_allele_sharing.R:33-82
  * pairwise_grm post-processing R/pairwise_grm.R:42-50   tpg_pairwise(TPG_STAT_GRM),
  *                                                       tpg_grm_from_as()
  * CutBySize -> bigparallelr::split_len              tpg_split_len(), tpg_as_pad_count()
