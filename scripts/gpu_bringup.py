@@ -224,6 +224,60 @@ def step_bench(k_major):
     return out
 
 
+def step_bench_large(n, lc, mask=0b1011):
+    """Large-n Gram timing (tile-order / L2 behaviour): n x lc chunk, KING products."""
+    import torch
+    from tidypopgen_b200 import _lib as L
+
+    ctx = L.Context(0)
+    n_pad = (n + 255) // 256 * 256
+    d_raw = torch.empty(n * lc + 16, dtype=torch.uint8, device="cuda")
+    eb = L.errbuf()
+    L.check(L.lib().tpg_synth_fill(ctx.handle, d_raw.data_ptr(), n, lc, 0, 20260004, 0.01, 0, eb, len(eb)), eb)
+    ps = n_pad * lc
+    d_planes = torch.empty(3 * ps, dtype=torch.int8, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.ExternalStream(L.lib().tpg_ctx_stream(ctx.handle))
+    out = {"n": n, "lc": lc}
+    ts = []
+    for r in range(3):
+        e0.record(stream)
+        L.check(L.lib().tpg_decode_planes(ctx.handle, d_raw.data_ptr(), n * lc, n, None, 0, n, n_pad, None, 0, lc, lc,
+                                          d_planes.data_ptr(), ps, 0, eb, len(eb)), eb)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    out["decode_ms"] = ts
+    out["decode_GBps_alg"] = 4 * n * lc / (min(ts) * 1e-3) / 1e9
+    d_counts = torch.zeros(4 * n_pad * n_pad, dtype=torch.int32, device="cuda")
+    ms = C.c_float(0)
+    tt = []
+    for r in range(3):
+        L.check(L.lib().tpg_gram(ctx.handle, d_planes.data_ptr(), ps, n_pad, lc, 0, mask, 0, 1,
+                                 d_counts.data_ptr(), C.byref(ms), eb, len(eb)), eb)
+        tt.append(ms.value)
+    out["gram_ms"] = tt
+    out["alg_TOPS"] = 4.0 * n * n * lc / (min(tt) * 1e-3) / 1e12
+    out["pairSNP_per_s"] = n * n * lc / (min(tt) * 1e-3)
+    # spot check a few entries against numpy on the host
+    host = d_raw[: n * lc].cpu().numpy().reshape(lc, n)
+    rng = np.random.default_rng(0)
+    got = d_counts.view(4, n_pad, n_pad)
+    bad = 0
+    for _ in range(40):
+        i, j = sorted(int(x) for x in rng.integers(0, n, 2))
+        gi, gj = host[:, i].astype(np.int64), host[:, j].astype(np.int64)
+        di = (gi == 2).astype(np.int64) - (gi == 0)
+        dj = (gj == 2).astype(np.int64) - (gj == 0)
+        dd = int((di * dj).sum()) * 3
+        hn = int(((gi == 1) & (gj <= 2)).sum()) * 3
+        bad += int(got[0, j, i].item()) != dd
+        bad += int(got[3, j, i].item()) != hn
+    out["spot_bad"] = bad
+    out["ok"] = bad == 0
+    return out
+
+
 STEPS = {
     "decode_mn": lambda: step_decode(False, False),
     "decode_mn_gather": lambda: step_decode(False, True),
@@ -239,6 +293,9 @@ STEPS = {
     "as_mn": lambda: step_pairwise(4, False),
     "bench_mn": lambda: step_bench(False),
     "bench_k": lambda: step_bench(True),
+    "large_8k": lambda: step_bench_large(8192, 65536),
+    "large_20k": lambda: step_bench_large(20000, 32768),
+    "large_50k": lambda: step_bench_large(50000, 8192),
 }
 
 

@@ -359,3 +359,61 @@ def test_hgdp_shape_properties():
     sub = tpg.snp_king_counts(X, ind_col=cols, src=src)
     ref = O.snp_king(host, n, m, None, cols)
     assert np.array_equal(sub[1], ref["K"]) and np.array_equal(sub[2], ref["N_Aa_i"]) and same(sub[0], ref["king"])
+
+
+# ------------------------------------------------------------------ sharding (staged C-ABI), ranks emulated on one GPU
+
+def _staged(engine, X, stat, bs, mode, rank, world, counts=None, finish=True, **kw):
+    from tidypopgen_b200 import snp
+    shard = {"loci": L.SHARD_LOCI, "tiles": L.SHARD_TILES, "none": L.SHARD_NONE}[mode]
+    job, keep = snp.make_job(X, kw.get("rows"), kw.get("cols"), stat, bs, shard_mode=shard, shard_rank=rank,
+                             shard_world=world, gpu_chunk_loci=kw.get("chunk", 0))
+    n = job.n if job.ind_row else X.nrow
+    counts = engine.new_counts(n) if counts is None else counts
+    engine.accumulate(job, counts)
+    if not finish:
+        return counts, job, keep
+    return engine.finish(job, counts, n, stat == L.STAT_IBS_RAW)[:2]
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_loci_and_tile_sharding_emulated(world):
+    from tidypopgen_b200 import dist as tdist
+    rng = np.random.default_rng(world)
+    n, m = 700, 6000
+    raw = random_bk(rng, n, m, 0.06)
+    X = fbm_of(raw, n, m)
+    eng = tdist.CudaEngine(0)
+    cols = pick("every3", m, rng)
+    ref_king = tpg.snp_king(X, ind_col=cols, block_size=500)
+    ref_as = tpg.snp_allele_sharing(X, ind_col=cols, block_size=500)
+    # loci: every rank adds its slice into the same buffer (what the all-reduce sums), finish once
+    for stat, ref in ((L.STAT_KING, ref_king), (L.STAT_AS, ref_as)):
+        counts = None
+        for r in range(world):
+            counts, job, keep = _staged(eng, X, stat, 500, "loci", r, world, counts, finish=False, cols=cols, chunk=512)
+        job.shard_mode, job.shard_world, job.shard_rank = L.SHARD_NONE, 1, 0
+        out, _, _ = eng.finish(job, counts, n, False)
+        assert same(out, ref)
+    # tiles: each rank's blocks, merged by ownership
+    merged = np.full((n, n), -7.0)
+    for r in range(world):
+        out, _ = _staged(eng, X, L.STAT_KING, 500, "tiles", r, world, cols=cols)
+        mask = tdist.owned_mask(n, r, world)
+        assert np.all(out[~mask] == 0)
+        merged[mask] = out[mask]
+    assert same(merged, ref_king)
+
+
+def test_two_gpus_nccl_if_available():
+    """Real NCCL run (torchrun, 2 ranks) when the box has >= 2 GPUs; skipped on the 1-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = __import__("pathlib").Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(root / "scripts" / "dist_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
