@@ -369,7 +369,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   const int64_t mem_cap = std::max<int64_t>(kLociPad, int64_t(double(free_b) * 0.45 / double(per_locus)));
   if (lc <= 0) {
     if (on_device) lc = int64_t(1) << 20;
-    else lc = std::max<int64_t>(8192, (int64_t(256) << 20) / std::max<int64_t>(span, 1));
+    else lc = std::min<int64_t>(262144, std::max<int64_t>(16384, (int64_t(256) << 20) / std::max<int64_t>(span, 1)));
   }
   lc = std::min(lc, mem_cap);
   lc = std::min(lc, round_up(pl.m_shard, kLociPad));
