@@ -293,6 +293,7 @@ STEPS = {
     "as_mn": lambda: step_pairwise(4, False),
     "bench_mn": lambda: step_bench(False),
     "bench_k": lambda: step_bench(True),
+    "ab_hgdp": lambda: step_bench(False),
     "large_8k": lambda: step_bench_large(8192, 65536),
     "large_20k": lambda: step_bench_large(20000, 32768),
     "large_50k": lambda: step_bench_large(50000, 8192),

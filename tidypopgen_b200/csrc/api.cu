@@ -111,6 +111,7 @@ static int ctx_init(Ctx* c, int device, const Err& E) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   TPG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking), E);
+  TPG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_decode, cudaStreamNonBlocking), E);
   TPG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking), E);
   TPG_CUDA_OK(cudaMalloc(&c->d_err_flag, sizeof(int)), E);
   TPG_CUDA_OK(cudaMemset(c->d_err_flag, 0, sizeof(int)), E);
@@ -368,7 +369,11 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   const int64_t per_locus = (on_device ? 0 : 2 * span) + 2 * int64_t(pl.nplanes) * pl.n_pad;
   const int64_t mem_cap = std::max<int64_t>(kLociPad, int64_t(double(free_b) * 0.45 / double(per_locus)));
   if (lc <= 0) {
-    if (on_device) lc = int64_t(1) << 20;
+    if (on_device) {
+      // no copy to hide, but decode(c+1) overlaps gram(c): aim for 4-16 chunks of >= 32k loci
+      const int64_t nch = std::min<int64_t>(16, std::max<int64_t>(1, pl.m_shard / 131072));
+      lc = std::max<int64_t>(32768, round_up((pl.m_shard + nch - 1) / nch, kLociPad));
+    }
     else lc = std::min<int64_t>(262144, std::max<int64_t>(16384, (int64_t(256) << 20) / std::max<int64_t>(span, 1)));
   }
   lc = std::min(lc, mem_cap);
@@ -414,7 +419,13 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
 
   cudaEvent_t ev_h2d_done[2] = {B.ev(false), B.ev(false)};
   cudaEvent_t ev_dec_done[2] = {B.ev(false), B.ev(false)};
-  struct Tm { cudaEvent_t c0, c1, d0, d1, g1; };
+  cudaEvent_t ev_gram_done[2] = {B.ev(false), B.ev(false)};
+  // decode must not start before everything already queued on the compute stream (the
+  // caller's zeroing of the counts, a previous job's finish) — cheap, and keeps jobs ordered.
+  cudaEvent_t ev_start = B.ev(false);
+  TPG_CUDA_OK(cudaEventRecord(ev_start, ctx->s_compute), E);
+  TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_decode, ev_start, 0), E);
+  struct Tm { cudaEvent_t c0, c1, d0, d1, g0, g1; };
   std::vector<Tm> tm(n_chunks);
   int64_t macs = 0;
   double ms_read = 0;
@@ -424,7 +435,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     const int64_t k0 = c * lc, k1 = std::min(pl.m_shard, k0 + lc);
     const int64_t lcc = k1 - k0;
     const int64_t lc_pad = round_up(lcc, kLociPad);
-    tm[c] = {B.ev(true), B.ev(true), B.ev(true), B.ev(true), B.ev(true)};
+    tm[c] = {B.ev(true), B.ev(true), B.ev(true), B.ev(true), B.ev(true), B.ev(true)};
 
     DecodeArgs da;
     da.n = pl.n;
@@ -477,7 +488,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       TPG_CUDA_OK(cudaMemcpyAsync(B.d_raw[b], hp, size_t(lcc * span), cudaMemcpyHostToDevice, ctx->s_copy), E);
       TPG_CUDA_OK(cudaEventRecord(tm[c].c1, ctx->s_copy), E);
       TPG_CUDA_OK(cudaEventRecord(ev_h2d_done[b], ctx->s_copy), E);
-      TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ev_h2d_done[b], 0), E);
+      TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_decode, ev_h2d_done[b], 0), E);
       st->bytes_h2d += lcc * span;
       da.raw = B.d_raw[b];
       da.raw_bytes = lcc * span;
@@ -486,11 +497,14 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       da.col_idx = nullptr;
       da.col0 = 0;
     }
-    TPG_CUDA_OK(cudaEventRecord(tm[c].d0, ctx->s_compute), E);
-    rc = launch_decode(ctx, da, ctx->s_compute, E);
+    // planes[b] were last read by the gram of chunk c-2
+    if (c >= 2) TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_decode, ev_gram_done[b], 0), E);
+    TPG_CUDA_OK(cudaEventRecord(tm[c].d0, ctx->s_decode), E);
+    rc = launch_decode(ctx, da, ctx->s_decode, E);
     if (rc) return rc;
-    TPG_CUDA_OK(cudaEventRecord(tm[c].d1, ctx->s_compute), E);
-    TPG_CUDA_OK(cudaEventRecord(ev_dec_done[b], ctx->s_compute), E);
+    TPG_CUDA_OK(cudaEventRecord(tm[c].d1, ctx->s_decode), E);
+    TPG_CUDA_OK(cudaEventRecord(ev_dec_done[b], ctx->s_decode), E);
+    TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ev_dec_done[b], 0), E);
 
     GramArgs ga;
     ga.planes = B.d_planes[b];
@@ -505,13 +519,16 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     ga.counts = d_counts;
     ga.ld = pl.n_pad;
     int64_t mm = 0;
+    TPG_CUDA_OK(cudaEventRecord(tm[c].g0, ctx->s_compute), E);
     rc = launch_gram(ctx, ga, ctx->s_compute, &mm, E);
     if (rc) return rc;
     macs += mm;
     TPG_CUDA_OK(cudaEventRecord(tm[c].g1, ctx->s_compute), E);
+    TPG_CUDA_OK(cudaEventRecord(ev_gram_done[b], ctx->s_compute), E);
     if (no_overlap) TPG_CUDA_OK(cudaStreamSynchronize(ctx->s_compute), E);
   }
   cudaError_t e = cudaStreamSynchronize(ctx->s_compute);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_decode);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_copy);
   if (e != cudaSuccess) {
     Err quiet{nullptr, 0};
@@ -524,7 +541,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     float ms = 0;
     cudaEventElapsedTime(&ms, tm[c].c0, tm[c].c1); st->ms_h2d += ms;
     cudaEventElapsedTime(&ms, tm[c].d0, tm[c].d1); st->ms_decode += ms;
-    cudaEventElapsedTime(&ms, tm[c].d1, tm[c].g1); st->ms_gram += ms;
+    cudaEventElapsedTime(&ms, tm[c].g0, tm[c].g1); st->ms_gram += ms;
   }
   st->ms_read += ms_read;
   st->n_chunks += n_chunks;
@@ -654,6 +671,7 @@ void tpg_ctx_destroy(tpg_ctx* h) {
   for (cudaEvent_t e : c->ev_timing) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_plain) cudaEventDestroy(e);
   if (c->s_compute) cudaStreamDestroy(c->s_compute);
+  if (c->s_decode) cudaStreamDestroy(c->s_decode);
   if (c->s_copy) cudaStreamDestroy(c->s_copy);
   if (c->d_err_flag) cudaFree(c->d_err_flag);
   if (c->d_items) cudaFree(c->d_items);

@@ -19,8 +19,6 @@
 // list so that CTAs running at the same time share operand panels in L2.
 #include <algorithm>
 #include <cstring>
-#include <functional>
-#include <queue>
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -40,14 +38,9 @@ __device__ __forceinline__ void prod_planes(int prod, int& pa, int& pb) {
   pb = (prod == TPG_MAT_DD) ? 0 : (prod == TPG_MAT_HH) ? 2 : 1;
 }
 
-// WorkItem.prod_ti: product in bits [0,4), B columns / 16 in [4,9) (1..16), A row tile in [9,32).
-__host__ __device__ __forceinline__ int item_prod(const WorkItem& w) { return w.prod_ti & 15; }
-__host__ __device__ __forceinline__ int item_ncols(const WorkItem& w) { return ((w.prod_ti >> 4) & 31) * 16; }
-__host__ __device__ __forceinline__ int item_ti(const WorkItem& w) { return w.prod_ti >> 9; }
-
 struct GramParams {
-  const WorkItem* items;   // grouped by CTA
-  const int32_t* cta_off;  // [gridDim.x + 1] item ranges
+  const WorkItem* items;
+  int n_items;
   int32_t* counts;
   int64_t mat_stride;  // elements between count matrices
   int64_t ld;
@@ -95,35 +88,32 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int it0 = p.cta_off[blockIdx.x], it1 = p.cta_off[blockIdx.x + 1];
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = it0; it < it1; ++it) {
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
         const WorkItem w = p.items[it];
-        const int prod = item_prod(w), ti = item_ti(w), c0 = w.c0, nc = item_ncols(w);
+        const int prod = w.prod_ti & 15, ti = w.prod_ti >> 4, tj = w.tj;
         int pa, pb;
         prod_planes(prod, pa, pb);
         const CUtensorMap* ma = pa == 0 ? &tm_d : pa == 1 ? &tm_nm : &tm_h1;
         const CUtensorMap* mb = pb == 0 ? &tm_d : pb == 1 ? &tm_nm : &tm_h1;
-        const bool two = nc > 128;  // the second 128-row box of B is only fetched when used
-        const uint32_t bytes = two ? kStageBytes : kStageBytes - kABytes;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
           if (kMajorK) {  // planes[row][locus]: coords (locus, row)
             tma_load_2d(sa, ma, &full_bar[stage], kb * kTileK, ti * kTileM);
-            tma_load_2d(sb, mb, &full_bar[stage], kb * kTileK, c0);
-            if (two) tma_load_2d(sb + kABytes, mb, &full_bar[stage], kb * kTileK, c0 + 128);
+            tma_load_2d(sb, mb, &full_bar[stage], kb * kTileK, tj * kTileN);
+            tma_load_2d(sb + kABytes, mb, &full_bar[stage], kb * kTileK, tj * kTileN + 128);
           } else {        // planes[locus][row]: coords (row, locus)
             tma_load_2d(sa, ma, &full_bar[stage], ti * kTileM, kb * kTileK);
-            tma_load_2d(sb, mb, &full_bar[stage], c0, kb * kTileK);
-            if (two) tma_load_2d(sb + kABytes, mb, &full_bar[stage], c0 + 128, kb * kTileK);
+            tma_load_2d(sb, mb, &full_bar[stage], tj * kTileN, kb * kTileK);
+            tma_load_2d(sb + kABytes, mb, &full_bar[stage], tj * kTileN + 128, kb * kTileK);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -133,7 +123,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc0 = make_idesc_i8(kTileM, 0, !kMajorK);  // N is per work item
+      constexpr uint32_t idesc = make_idesc_i8(kTileM, kTileN, !kMajorK);
       // K-major  SW128: 8-row groups 1024 B apart (SBO); one MMA consumes 32 B of K.
       // MN-major SW128: 8-locus groups 1024 B apart (SBO), 128-row blocks 16 KiB apart (LBO);
       //                 one MMA consumes 32 loci = 4096 B.
@@ -144,9 +134,8 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int it = it0; it < it1; ++it) {
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
         const WorkItem w = p.items[it];
-        const uint32_t idesc = idesc0 | (uint32_t(item_ncols(w) >> 3) << 17);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(acc * kTileN);
@@ -175,33 +164,32 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int it = it0; it < it1; ++it) {
+    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
       const WorkItem w = p.items[it];
-      const int prod = item_prod(w), ti = item_ti(w), nc = item_ncols(w);
+      const int prod = w.prod_ti & 15, ti = w.prod_ti >> 4, tj = w.tj;
       const bool sym = prod != TPG_MAT_HN;
       mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
       tc_fence_after();
       const int i = ti * kTileM + q * 32 + lane;  // A row  = count-matrix row
-      const int j0 = w.c0;                        // B rows = count-matrix columns
+      const int j0 = tj * kTileN;                 // B rows = count-matrix columns
       int32_t* cbase = p.counts + int64_t(prod) * p.mat_stride + i;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kTileN);
 #pragma unroll 1
-      for (int c = 0; c < nc; c += 32) {
+      for (int c = 0; c < kTileN; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + uint32_t(c), v);
         tmem_ld_wait();
-        if (c + 32 >= nc) {  // accumulator drained: hand it back before the last adds
+        if (c + 32 == kTileN) {  // accumulator drained: hand it back before the last adds
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
         if (j0 + c < p.n && i < p.n) {
-          const int lim = min(32, nc - c);
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
             const int j = j0 + c + jj;
             // X(i,j) at X[i + j*ld]: the 32 lanes of a warp hit 32 consecutive ints.
-            if (jj < lim && j < p.n && (!sym || i <= j)) atomicAdd(cbase + int64_t(j) * p.ld, int32_t(v[jj]));
+            if (j < p.n && (!sym || i <= j)) atomicAdd(cbase + int64_t(j) * p.ld, int32_t(v[jj]));
           }
         }
       }
@@ -240,107 +228,82 @@ static int make_plane_map(Ctx* ctx, CUtensorMap* out, const int8_t* base, uint64
   return TPG_OK;
 }
 
-// How many k-splits a tile gets: enough work items per CTA (>= 16) that the list schedule
-// below ends within a few percent of the ideal makespan, while an item keeps >= 16 k-blocks
-// so its epilogue (drained while the next item's MMAs run) stays amortised.
-static int choose_ksplit(int64_t n_tiles, int64_t kblocks, int sms) {
-  if (n_tiles >= int64_t(16) * sms) return 1;
-  int64_t ks = (int64_t(16) * sms + n_tiles - 1) / n_tiles;
-  ks = std::min<int64_t>(ks, std::max<int64_t>(1, kblocks / 16));
-  return int(std::max<int64_t>(1, ks));
+// Chooses how many k-splits a tile gets so that the persistent CTAs finish together.
+static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms) {
+  if (n_tile_items >= int64_t(8) * sms) return 1;
+  int best = 1;
+  double best_cost = 1e300;
+  const int max_ks = int(std::min<int64_t>(kblocks, 512));
+  for (int ks = 1; ks <= max_ks; ++ks) {
+    const int64_t per = (kblocks + ks - 1) / ks;      // k-blocks per item
+    if (ks > 1 && per < 8) break;                     // keep the epilogue amortised
+    const int64_t waves = (n_tile_items * ks + sms - 1) / sms;
+    const double cost = double(waves) * (double(per) + 2.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = ks; }
+  }
+  return best;
 }
 
 int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out, const Err& E) {
   if (a.n_pad % kRowPad || a.lc_pad % kLociPad || a.lc_pad <= 0)
     return E.fail(TPG_ERR_ARG, "gram: n_pad (%lld) / lc_pad (%lld) not tile multiples",
                   (long long)a.n_pad, (long long)a.lc_pad);
-  const int64_t n = std::min(a.n, a.n_pad);
-  const int64_t tiles_m = (n + kTileM - 1) / kTileM, tiles_n = (n + kTileN - 1) / kTileN;
-  const int64_t nblocks = a.n_pad / kTileN;  // ownership grid (256 x 256 blocks)
+  const int64_t tiles_m = a.n_pad / kTileM, tiles_n = a.n_pad / kTileN;
   const int64_t kblocks = a.lc_pad / kTileK;
 
-  // ---- tile list in L2-friendly order: 1024x1024 regions, then tiles, then products.
-  // A tile is 128 rows x up to 256 columns; the column extent is trimmed to the valid
-  // individuals (multiple of 16) and, for symmetric products, to start at the diagonal.
-  struct T { int prod, ti, c0, nc; };
+  // ---- tile list in L2-friendly order: 1024x1024 regions, then tiles, then products
+  struct T { int prod, ti, tj; };
   std::vector<T> tiles;
   const int64_t RI = 8, RJ = 4;
-  int64_t macs_per_locus = 0;
   for (int64_t rj = 0; rj < tiles_n; rj += RJ)
     for (int64_t ri = 0; ri < tiles_m; ri += RI)
       for (int64_t tj = rj; tj < std::min(rj + RJ, tiles_n); ++tj)
         for (int64_t ti = ri; ti < std::min(ri + RI, tiles_m); ++ti) {
-          const int64_t col_lo = kTileN * tj;
-          const int64_t col_hi = std::min<int64_t>(col_lo + kTileN, (n + 15) / 16 * 16);  // exclusive
+          const bool upper = kTileN * tj + (kTileN - 1) >= kTileM * ti;
+          // 256x256 ownership block of the tile (rows ti/2, cols tj); lower blocks mirror
           const int64_t bi = ti / 2, bj = tj;
-          const int64_t lo = std::min(bi, bj), hi = std::max(bi, bj);
-          if (!block_owned(lo, hi, nblocks, a.shard_rank, a.shard_world)) continue;
           for (int prod = 0; prod < TPG_NUM_COUNT_MATS; ++prod) {
             if (!(a.prod_mask & (1 << prod))) continue;
-            int64_t c0 = col_lo;
-            if (prod != TPG_MAT_HN) c0 = std::max<int64_t>(c0, kTileM * ti);  // nothing left of the diagonal
-            if (c0 >= col_hi) continue;
-            tiles.push_back({prod, int(ti), int(c0), int(col_hi - c0)});
-            macs_per_locus += int64_t(kTileM) * (col_hi - c0);
+            if (prod != TPG_MAT_HN && !upper) continue;
+            const int64_t lo = std::min(bi, bj), hi = std::max(bi, bj);
+            if (!block_owned(lo, hi, tiles_n, a.shard_rank, a.shard_world)) continue;
+            tiles.push_back({prod, int(ti), int(tj)});
           }
         }
-  if (macs_out) *macs_out = macs_per_locus * a.lc_pad;
-  if (tiles.empty()) return TPG_OK;
+  if (tiles.empty()) { if (macs_out) *macs_out = 0; return TPG_OK; }
 
   const int sms = ctx->num_sms;
   const int ks = choose_ksplit(int64_t(tiles.size()), kblocks, sms);
+  if (macs_out) *macs_out = int64_t(tiles.size()) * kTileM * kTileN * a.lc_pad;
 
   // The work list only depends on the geometry; chunks of equal size reuse the upload.
   char key[160];
-  snprintf(key, sizeof key, "%lld/%lld/%lld/%d/%d/%d/%d", (long long)n, (long long)a.n_pad,
-           (long long)a.lc_pad, a.prod_mask, a.shard_rank, a.shard_world, ks);
-  const int grid = int(std::min<size_t>(tiles.size() * size_t(ks), size_t(sms)));
+  snprintf(key, sizeof key, "%lld/%lld/%d/%d/%d/%d", (long long)a.n_pad, (long long)a.lc_pad,
+           a.prod_mask, a.shard_rank, a.shard_world, ks);
   if (ctx->items_key != key) {
-    // List scheduling on the host (deterministic stand-in for a device-side work queue):
-    // items in k-split-major order go to the CTA with the least accumulated MMA time.
-    std::vector<std::vector<WorkItem>> per(grid);
-    typedef std::pair<int64_t, int> Load;  // (accumulated cost, cta)
-    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
-    for (int c = 0; c < grid; ++c) heap.push({0, c});
+    std::vector<WorkItem>& items = ctx->h_items;
+    items.clear();
+    items.reserve(tiles.size() * ks);
     for (int s = 0; s < ks; ++s) {
       const int32_t kb0 = int32_t(kblocks * s / ks), kb1 = int32_t(kblocks * (s + 1) / ks);
       if (kb1 <= kb0) continue;
-      for (const T& t : tiles) {
-        Load l = heap.top();
-        heap.pop();
-        per[l.second].push_back({int32_t(t.prod | ((t.nc / 16) << 4) | (t.ti << 9)), t.c0, kb0, kb1});
-        // an MMA costs max(N, ~64) cycles-equivalents; the epilogue adds a little per item
-        l.first += int64_t(std::max(t.nc, 64)) * (kb1 - kb0) + 64;
-        heap.push(l);
-      }
+      for (const T& t : tiles) items.push_back({int32_t(t.prod | (t.ti << 4)), t.tj, kb0, kb1});
     }
-    std::vector<WorkItem>& blob = ctx->h_items;  // [offsets (as WorkItem-sized words) | items]
-    const size_t off_words = (size_t(grid) + 1 + 3) / 4;  // int32 offsets packed 4 per WorkItem
-    size_t total = 0;
-    for (auto& v : per) total += v.size();
-    blob.assign(off_words + total, WorkItem{0, 0, 0, 0});
-    int32_t* offs = reinterpret_cast<int32_t*>(blob.data());
-    size_t pos = 0;
-    for (int c = 0; c < grid; ++c) {
-      offs[c] = int32_t(pos);
-      for (const WorkItem& w : per[c]) blob[off_words + pos++] = w;
-    }
-    offs[grid] = int32_t(pos);
-    if (blob.size() > ctx->d_items_cap) {
+    if (items.size() > ctx->d_items_cap) {
       TPG_CUDA_OK(cudaStreamSynchronize(st), E);
       if (ctx->d_items) cudaFree(ctx->d_items);
       ctx->d_items = nullptr;
       ctx->d_items_cap = 0;
-      const size_t cap = blob.size() + blob.size() / 4 + 1024;
+      const size_t cap = items.size() + items.size() / 4 + 1024;
       TPG_CUDA_OK(cudaMalloc(&ctx->d_items, cap * sizeof(WorkItem)), E);
       ctx->d_items_cap = cap;
     }
     // Stream-ordered after any kernel still reading the previous list.
-    TPG_CUDA_OK(cudaMemcpyAsync(ctx->d_items, blob.data(), blob.size() * sizeof(WorkItem),
+    TPG_CUDA_OK(cudaMemcpyAsync(ctx->d_items, items.data(), items.size() * sizeof(WorkItem),
                                 cudaMemcpyHostToDevice, st), E);
     ctx->items_key = key;
-    ctx->items_off_words = off_words;
   }
+  const size_t n_items = ctx->h_items.size();
 
   CUtensorMap maps[3];
   for (int pl = 0; pl < 3; ++pl) {
@@ -354,14 +317,15 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   }
 
   GramParams p;
-  p.items = ctx->d_items + ctx->items_off_words;
-  p.cta_off = reinterpret_cast<const int32_t*>(ctx->d_items);
+  p.items = ctx->d_items;
+  p.n_items = int(n_items);
   p.counts = a.counts;
   p.mat_stride = a.ld * a.ld;
   p.ld = a.ld;
   p.n = int(a.n);
   p.err_flag = ctx->d_err_flag;
 
+  const int grid = int(std::min<size_t>(n_items, size_t(sms)));
   if (a.k_major) {
     TPG_CUDA_OK(cudaFuncSetAttribute(gram_i8_kernel<true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), E);

@@ -18,8 +18,8 @@ constexpr int kRowPad = 256;  // individuals are padded to this multiple
 constexpr int kLociPad = 128; // loci per chunk are padded to this multiple
 
 struct __align__(16) WorkItem {
-  int32_t prod_ti;  // product [0,4) | B columns / 16 [4,9) | A row tile (128 rows) [9,32)
-  int32_t c0;       // first B row (= first count-matrix column) of the tile
+  int32_t prod_ti;  // prod in bits [0,4), ti in bits [4,32)
+  int32_t tj;
   int32_t kb0;      // first k-block (units of kTileK loci)
   int32_t kb1;      // one past the last k-block
 };
@@ -29,14 +29,14 @@ struct __align__(16) WorkItem {
 struct Ctx {
   int device = 0;
   int num_sms = 0;
-  cudaStream_t s_compute = nullptr;
-  cudaStream_t s_copy = nullptr;
+  cudaStream_t s_compute = nullptr;  // gram_i8, finish (the stream tpg_ctx_stream exposes)
+  cudaStream_t s_decode = nullptr;   // decode_planes of chunk c+1 runs beside gram_i8 of chunk c
+  cudaStream_t s_copy = nullptr;     // H2D
   int* d_err_flag = nullptr;       // device-side watchdog flag
-  WorkItem* d_items = nullptr;     // [cta offsets | work items grouped by CTA] of the last gram launch
+  WorkItem* d_items = nullptr;     // work list of the last gram launch
   size_t d_items_cap = 0;
   std::vector<WorkItem> h_items;   // host copy (kept alive for the async upload)
   std::string items_key;           // geometry the uploaded list was built for
-  size_t items_off_words = 0;      // WorkItem-sized words taken by the CTA offset table
   void* encode_tiled = nullptr;    // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
   int64_t launches = 0;
   // Grow-only buffer cache, reused across jobs (cudaMalloc / cudaMallocHost / cudaFree are
