@@ -199,8 +199,11 @@ void tpg_ctx_destroy(tpg_ctx* ctx);
  * caches per device. */
 void tpg_ctx_trim(tpg_ctx* ctx);
 void tpg_release(int device);
-/* The cudaStream_t all kernels of this context are launched on (for event timing). */
+/* The cudaStream_t the Gram / finish kernels of this context are launched on (for event timing). */
 void* tpg_ctx_stream(tpg_ctx* ctx);
+/* tpg_pairwise on a caller-owned context (so a caller can bracket whole jobs with CUDA
+ * events on tpg_ctx_stream); tpg_pairwise itself uses a context cached per device. */
+int tpg_pairwise_ctx(tpg_ctx* ctx, const tpg_job* job, tpg_result* res, char* err, size_t errlen);
 
 /* Layout of the int32 count buffer for n individuals: TPG_NUM_COUNT_MATS matrices,
  * each column-major with leading dimension ld = n_pad (X(i,j) at X[i + j*ld]);

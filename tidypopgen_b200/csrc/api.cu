@@ -113,8 +113,9 @@ static int ctx_init(Ctx* c, int device, const Err& E) {
   TPG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking), E);
   TPG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_decode, cudaStreamNonBlocking), E);
   TPG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking), E);
-  TPG_CUDA_OK(cudaMalloc(&c->d_err_flag, sizeof(int)), E);
-  TPG_CUDA_OK(cudaMemset(c->d_err_flag, 0, sizeof(int)), E);
+  TPG_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_err_flag), sizeof(int), cudaHostAllocMapped), E);
+  *c->h_err_flag = 0;
+  TPG_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_err_flag), c->h_err_flag, 0), E);
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
   e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -125,9 +126,7 @@ static int ctx_init(Ctx* c, int device, const Err& E) {
 }
 
 int check_err_flag(Ctx* ctx, const Err& E) {
-  int flag = 0;
-  cudaError_t e = cudaMemcpy(&flag, ctx->d_err_flag, sizeof(int), cudaMemcpyDeviceToHost);
-  if (e != cudaSuccess) return E.fail(TPG_ERR_CUDA, "device error: %s", cudaGetErrorString(e));
+  const int flag = *reinterpret_cast<volatile int*>(ctx->h_err_flag);
   if (flag) return E.fail(TPG_ERR_KERNEL, "gram_i8 pipeline watchdog tripped (role %d)", flag);
   return TPG_OK;
 }
@@ -334,8 +333,32 @@ static bool is_pinned_host(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
+// Waits for an enqueued accumulate, checks the watchdog word and folds the per-chunk event
+// timings into st.
+static int collect_accumulate(Ctx* ctx, tpg_stats* st, const Err& E) {
+  if (!ctx->pending) return TPG_OK;
+  ctx->pending = false;
+  cudaError_t e = cudaStreamSynchronize(ctx->s_compute);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_decode);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_copy);
+  if (e != cudaSuccess) {
+    Err quiet{nullptr, 0};
+    if (check_err_flag(ctx, quiet) == TPG_ERR_KERNEL) return check_err_flag(ctx, E);
+    return E.fail(TPG_ERR_CUDA, "accumulate failed on device: %s", cudaGetErrorString(e));
+  }
+  int rc = check_err_flag(ctx, E);
+  if (rc) return rc;
+  for (const Ctx::ChunkEv& t : ctx->pend_ev) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t.c0, t.c1); st->ms_h2d += ms;
+    cudaEventElapsedTime(&ms, t.d0, t.d1); st->ms_decode += ms;
+    cudaEventElapsedTime(&ms, t.g0, t.g1); st->ms_gram += ms;
+  }
+  return TPG_OK;
+}
+
 static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_stats* st,
-                           const Err& E) {
+                           const Err& E, bool defer = false) {
   const double t_begin = now_ms();
   Plan pl;
   int rc = make_plan(job, &pl, E);
@@ -369,11 +392,9 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   const int64_t per_locus = (on_device ? 0 : 2 * span) + 2 * int64_t(pl.nplanes) * pl.n_pad;
   const int64_t mem_cap = std::max<int64_t>(kLociPad, int64_t(double(free_b) * 0.45 / double(per_locus)));
   if (lc <= 0) {
-    if (on_device) {
-      // no copy to hide, but decode(c+1) overlaps gram(c): aim for 4-16 chunks of >= 32k loci
-      const int64_t nch = std::min<int64_t>(16, std::max<int64_t>(1, pl.m_shard / 131072));
-      lc = std::max<int64_t>(32768, round_up((pl.m_shard + nch - 1) / nch, kLociPad));
-    }
+    // device-resident bytes: nothing to overlap with (decode and gram contend for HBM when run
+    // side by side — measured), so one big chunk = fewest launches and atomics
+    if (on_device) lc = int64_t(1) << 20;
     else lc = std::min<int64_t>(262144, std::max<int64_t>(16384, (int64_t(256) << 20) / std::max<int64_t>(span, 1)));
   }
   lc = std::min(lc, mem_cap);
@@ -425,8 +446,8 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   cudaEvent_t ev_start = B.ev(false);
   TPG_CUDA_OK(cudaEventRecord(ev_start, ctx->s_compute), E);
   TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_decode, ev_start, 0), E);
-  struct Tm { cudaEvent_t c0, c1, d0, d1, g0, g1; };
-  std::vector<Tm> tm(n_chunks);
+  std::vector<Ctx::ChunkEv>& tm = ctx->pend_ev;
+  tm.assign(n_chunks, Ctx::ChunkEv{});
   int64_t macs = 0;
   double ms_read = 0;
 
@@ -527,21 +548,10 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     TPG_CUDA_OK(cudaEventRecord(ev_gram_done[b], ctx->s_compute), E);
     if (no_overlap) TPG_CUDA_OK(cudaStreamSynchronize(ctx->s_compute), E);
   }
-  cudaError_t e = cudaStreamSynchronize(ctx->s_compute);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_decode);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_copy);
-  if (e != cudaSuccess) {
-    Err quiet{nullptr, 0};
-    if (check_err_flag(ctx, quiet) == TPG_ERR_KERNEL) return check_err_flag(ctx, E);
-    return E.fail(TPG_ERR_CUDA, "accumulate failed on device: %s", cudaGetErrorString(e));
-  }
-  rc = check_err_flag(ctx, E);
-  if (rc) return rc;
-  for (int64_t c = 0; c < n_chunks; ++c) {
-    float ms = 0;
-    cudaEventElapsedTime(&ms, tm[c].c0, tm[c].c1); st->ms_h2d += ms;
-    cudaEventElapsedTime(&ms, tm[c].d0, tm[c].d1); st->ms_decode += ms;
-    cudaEventElapsedTime(&ms, tm[c].g0, tm[c].g1); st->ms_gram += ms;
+  ctx->pending = true;
+  if (!defer) {
+    rc = collect_accumulate(ctx, st, E);
+    if (rc) return rc;
   }
   st->ms_read += ms_read;
   st->n_chunks += n_chunks;
@@ -586,7 +596,7 @@ static int finish_impl(Ctx* ctx, const tpg_job* job, const int32_t* d_counts, tp
       TPG_CUDA_OK(cudaMemcpyAsync(dev[o], host[o], bytes, cudaMemcpyHostToDevice, ctx->s_compute), E);
   }
   fa.out0 = dev[0]; fa.out1 = dev[1]; fa.aux0 = dev[2]; fa.aux1 = dev[3];
-  ctx->ev_timing_used = 0;
+  if (!ctx->pending) ctx->ev_timing_used = 0;
   cudaEvent_t e0 = pooled_event(ctx, true), e1 = pooled_event(ctx, true), e2 = pooled_event(ctx, true);
   cudaEventRecord(e0, ctx->s_compute);
   int rc = launch_finish(ctx, fa, ctx->s_compute, E);
@@ -600,6 +610,10 @@ static int finish_impl(Ctx* ctx, const tpg_job* job, const int32_t* d_counts, tp
     }
   }
   cudaEventRecord(e2, ctx->s_compute);
+  if (ctx->pending) {  // the accumulate of the same job was enqueued without a sync
+    const int rc2 = collect_accumulate(ctx, &res->stats, E);
+    if (rc == TPG_OK) rc = rc2;
+  }
   cudaError_t e = cudaStreamSynchronize(ctx->s_compute);
   if (rc == TPG_OK && e != cudaSuccess) rc = E.fail(TPG_ERR_CUDA, "finish failed on device: %s", cudaGetErrorString(e));
   if (rc == TPG_OK) {
@@ -673,7 +687,7 @@ void tpg_ctx_destroy(tpg_ctx* h) {
   if (c->s_compute) cudaStreamDestroy(c->s_compute);
   if (c->s_decode) cudaStreamDestroy(c->s_decode);
   if (c->s_copy) cudaStreamDestroy(c->s_copy);
-  if (c->d_err_flag) cudaFree(c->d_err_flag);
+  if (c->h_err_flag) cudaFreeHost(c->h_err_flag);
   if (c->d_items) cudaFree(c->d_items);
   delete c;
 }
@@ -719,32 +733,49 @@ int tpg_finish(tpg_ctx* h, const tpg_job* job, const int32_t* d_counts, tpg_resu
   return rc;
 }
 
-int tpg_pairwise(const tpg_job* job, tpg_result* res, char* err, size_t errlen) {
-  Err E{err, errlen};
-  if (!job || !res) return E.fail(TPG_ERR_ARG, "job / result is NULL");
+static int pairwise_on(Ctx* c, const tpg_job* job, tpg_result* res, const Err& E) {
   if (job->shard_mode == TPG_SHARD_LOCI && job->shard_world > 1)
     return E.fail(TPG_ERR_ARG, "loci-sharded jobs need the staged interface (tpg_accumulate, "
                                "all-reduce of the counts, tpg_finish)");
-  int rc = TPG_OK;
-  Ctx* c = cached_ctx(job->device, E, &rc);
-  if (!c) return rc;
   const int64_t l0 = c->launches;
   memset(&res->stats, 0, sizeof res->stats);
   const int64_t n = job->ind_row ? job->n : job->nrow_total;
   if (n <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row");
+  if (!res->out0) return E.fail(TPG_ERR_ARG, "result / out0 is NULL");
   TPG_CUDA_OK(cudaSetDevice(c->device), E);
   const size_t cbytes = sizeof(int32_t) * size_t(tpg_counts_elems(n));
-  rc = ensure_slot(&c->d_counts, cbytes, false, "count matrices", E);
+  int rc = ensure_slot(&c->d_counts, cbytes, false, "count matrices", E);
   if (rc) return rc;
   int32_t* d_counts = static_cast<int32_t*>(c->d_counts.p);
   cudaError_t e = cudaMemsetAsync(d_counts, 0, cbytes, c->s_compute);
   if (e != cudaSuccess) return E.fail(TPG_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
-  rc = accumulate_impl(c, job, d_counts, &res->stats, E);
-  if (rc == TPG_OK) {
-    rc = finish_impl(c, job, d_counts, res, E);
+  c->launches++;
+  // memset -> decode -> gram -> finish are enqueued back to back; one sync at the very end
+  rc = accumulate_impl(c, job, d_counts, &res->stats, E, /*defer=*/true);
+  if (rc == TPG_OK) rc = finish_impl(c, job, d_counts, res, E);
+  if (c->pending) {  // finish bailed out early: still drain the device work
+    tpg_stats scratch;
+    memset(&scratch, 0, sizeof scratch);
+    Err quiet{nullptr, 0};
+    collect_accumulate(c, &scratch, quiet);
   }
   res->stats.n_launches = c->launches - l0;
   return rc;
+}
+
+int tpg_pairwise(const tpg_job* job, tpg_result* res, char* err, size_t errlen) {
+  Err E{err, errlen};
+  if (!job || !res) return E.fail(TPG_ERR_ARG, "job / result is NULL");
+  int rc = TPG_OK;
+  Ctx* c = cached_ctx(job->device, E, &rc);
+  if (!c) return rc;
+  return pairwise_on(c, job, res, E);
+}
+
+int tpg_pairwise_ctx(tpg_ctx* h, const tpg_job* job, tpg_result* res, char* err, size_t errlen) {
+  Err E{err, errlen};
+  if (!h || !job || !res) return E.fail(TPG_ERR_ARG, "ctx / job / result is NULL");
+  return pairwise_on(reinterpret_cast<Ctx*>(h), job, res, E);
 }
 
 int tpg_grm_from_as(int device, const double* as_in, int64_t n, double* grm_out, double* mb_out,

@@ -32,7 +32,8 @@ struct Ctx {
   cudaStream_t s_compute = nullptr;  // gram_i8, finish (the stream tpg_ctx_stream exposes)
   cudaStream_t s_decode = nullptr;   // decode_planes of chunk c+1 runs beside gram_i8 of chunk c
   cudaStream_t s_copy = nullptr;     // H2D
-  int* d_err_flag = nullptr;       // device-side watchdog flag
+  int* d_err_flag = nullptr;       // device alias of the host-mapped watchdog word
+  int* h_err_flag = nullptr;       // ... and its host address (read without a copy)
   WorkItem* d_items = nullptr;     // work list of the last gram launch
   size_t d_items_cap = 0;
   std::vector<WorkItem> h_items;   // host copy (kept alive for the async upload)
@@ -44,6 +45,10 @@ struct Ctx {
   struct Slot { void* p = nullptr; size_t cap = 0; };
   Slot d_raw[2], d_planes[2], h_pin[2], d_rows, d_cols, d_counts, d_out[4], d_red;
   std::vector<cudaEvent_t> ev_timing, ev_plain;
+  // accumulate enqueued but not yet collected (tpg_pairwise defers the sync to the end of finish)
+  struct ChunkEv { cudaEvent_t c0, c1, d0, d1, g0, g1; };
+  std::vector<ChunkEv> pend_ev;
+  bool pending = false;
   size_t ev_timing_used = 0, ev_plain_used = 0;
 };
 // Ensures slot holds >= bytes (device memory, or pinned host memory when host = true).

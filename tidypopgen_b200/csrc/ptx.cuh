@@ -56,7 +56,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3FFu) == 0) {
       if (globaltimer_ns() - t0 > 4000000000ull) {
-        if (err_flag) atomicExch(err_flag, code);
+        if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = code;  // host-mapped word
         __threadfence_system();
         asm volatile("trap;");
       }
