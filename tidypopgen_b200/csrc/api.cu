@@ -386,20 +386,32 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   if (direct) { span = nrow; rlo = 0; }
 
   // ---- chunk size (loci per GPU chunk), decoupled from R's block.size
-  size_t free_b = 0, total_b = 0;
-  TPG_CUDA_OK(cudaMemGetInfo(&free_b, &total_b), E);
   int64_t lc = job->gpu_chunk_loci;
   const int64_t per_locus = (on_device ? 0 : 2 * span) + 2 * int64_t(pl.nplanes) * pl.n_pad;
-  const int64_t mem_cap = std::max<int64_t>(kLociPad, int64_t(double(free_b) * 0.45 / double(per_locus)));
   if (lc <= 0) {
     // device-resident bytes: nothing to overlap with (decode and gram contend for HBM when run
     // side by side — measured), so one big chunk = fewest launches and atomics
     if (on_device) lc = int64_t(1) << 20;
     else lc = std::min<int64_t>(262144, std::max<int64_t>(16384, (int64_t(256) << 20) / std::max<int64_t>(span, 1)));
   }
-  lc = std::min(lc, mem_cap);
   lc = std::min(lc, round_up(pl.m_shard, kLociPad));
   lc = std::max<int64_t>(kLociPad, lc / kLociPad * kLociPad);
+  {
+    // Cap by free HBM — but cudaMemGetInfo is slow, so only ask when the cached buffers
+    // would have to grow for this chunk size.
+    const size_t need_planes = size_t(pl.n_pad) * size_t(lc) * size_t(pl.nplanes);
+    const size_t need_raw = on_device ? 0 : size_t(span) * size_t(lc) + 16;
+    const bool fits = ctx->d_planes[0].cap >= need_planes && (pl.m_shard <= lc || ctx->d_planes[1].cap >= need_planes) &&
+                      (on_device || (ctx->d_raw[0].cap >= need_raw && (pl.m_shard <= lc || ctx->d_raw[1].cap >= need_raw)));
+    if (!fits) {
+      size_t free_b = 0, total_b = 0;
+      TPG_CUDA_OK(cudaMemGetInfo(&free_b, &total_b), E);
+      const size_t held = ctx->d_planes[0].cap + ctx->d_planes[1].cap + ctx->d_raw[0].cap + ctx->d_raw[1].cap;
+      const int64_t mem_cap = std::max<int64_t>(kLociPad, int64_t(double(free_b + held) * 0.45 / double(per_locus)));
+      lc = std::min(lc, mem_cap);
+      lc = std::max<int64_t>(kLociPad, lc / kLociPad * kLociPad);
+    }
+  }
   const int64_t n_chunks = (pl.m_shard + lc - 1) / lc;
   const int64_t plane_stride = pl.n_pad * lc;
 

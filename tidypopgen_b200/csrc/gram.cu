@@ -326,15 +326,15 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   p.err_flag = ctx->d_err_flag;
 
   const int grid = int(std::min<size_t>(n_items, size_t(sms)));
-  if (a.k_major) {
+  if (!ctx->gram_attr_set) {  // once per context (= per device)
     TPG_CUDA_OK(cudaFuncSetAttribute(gram_i8_kernel<true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), E);
-    gram_i8_kernel<true><<<grid, kGramThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
-  } else {
     TPG_CUDA_OK(cudaFuncSetAttribute(gram_i8_kernel<false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), E);
-    gram_i8_kernel<false><<<grid, kGramThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
+    ctx->gram_attr_set = true;
   }
+  if (a.k_major) gram_i8_kernel<true><<<grid, kGramThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
+  else gram_i8_kernel<false><<<grid, kGramThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
   TPG_CUDA_OK(cudaGetLastError(), E);
   ctx->launches++;
   return TPG_OK;

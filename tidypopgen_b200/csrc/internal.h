@@ -40,6 +40,7 @@ struct Ctx {
   std::string items_key;           // geometry the uploaded list was built for
   void* encode_tiled = nullptr;    // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
   int64_t launches = 0;
+  bool gram_attr_set = false;
   // Grow-only buffer cache, reused across jobs (cudaMalloc / cudaMallocHost / cudaFree are
   // slow and synchronising; a job must not pay them every call).  tpg_ctx_trim() frees it.
   struct Slot { void* p = nullptr; size_t cap = 0; };
