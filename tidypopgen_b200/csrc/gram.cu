@@ -18,6 +18,7 @@
 // MMAs of the next.  A work item is (product, tile, k-block range); the host orders the
 // list so that CTAs running at the same time share operand panels in L2.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include "internal.h"
 #include "ptx.cuh"
@@ -230,7 +231,16 @@ static int make_plane_map(Ctx* ctx, CUtensorMap* out, const int8_t* base, uint64
 
 // Chooses how many k-splits a tile gets so that the persistent CTAs finish together.
 static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms) {
-  if (n_tile_items >= int64_t(8) * sms) return 1;
+  // Large problems: every CTA runs many items, balance is not the issue — L2 is.  CTAs that
+  // run side by side share operand panels only while they stream the same loci; over a long
+  // k range they drift apart and every CTA ends up fetching its panels from HBM by itself
+  // (measured, KING: n = 20,000 x 100,000 loci in one item: 110 ms; items of 256 k-blocks: 50 ms;
+  // n = 50,000 x 500,000: 256 k-blocks 3.25 s, 128 k-blocks 1.71 s).  With items of 128 k-blocks
+  // (16,384 loci) the operand panels of a whole 1024 x 1024 tile region (~100 MB) fit in the
+  // 126 MB L2, so the reuse no longer depends on the CTAs staying in lock step.
+  const int max_per = getenv("TPG_GRAM_MAXKB") ? std::max(8, atoi(getenv("TPG_GRAM_MAXKB"))) : 128;
+  const int ks_l2 = int((kblocks + max_per - 1) / max_per);
+  if (n_tile_items >= int64_t(8) * sms) return std::max(1, ks_l2);
   int best = 1;
   double best_cost = 1e300;
   const int max_ks = int(std::min<int64_t>(kblocks, 512));
@@ -241,7 +251,7 @@ static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms) {
     const double cost = double(waves) * (double(per) + 2.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = ks; }
   }
-  return best;
+  return std::max(best, std::min(ks_l2, max_ks));
 }
 
 int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out, const Err& E) {
