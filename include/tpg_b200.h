@@ -181,6 +181,14 @@ int64_t tpg_as_pad_count(int64_t m, int64_t block_size);
  * reported as success). */
 int tpg_pairwise(const tpg_job* job, tpg_result* res, char* err, size_t errlen);
 
+/* The same job spread over several GPUs of one box from ONE process (what an R session
+ * needs): one host thread per device accumulates its shard — shard_mode TPG_SHARD_LOCI
+ * (contiguous slices of ind_col) or TPG_SHARD_TILES (owned 256x256 output blocks, all loci);
+ * TPG_SHARD_NONE picks by n — the int32 count matrices are summed onto devices[0] over
+ * NVLink and finished there.  Results are identical to the single-GPU job. */
+int tpg_pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* devices, int32_t ndev,
+                       int32_t shard_mode, char* err, size_t errlen);
+
 /* pairwise_grm(x, allele_sharing_mat = <precomputed>) — R/pairwise_grm.R:42-50.
  * as_in / grm_out: n x n column-major host doubles (may alias). */
 int tpg_grm_from_as(int device, const double* as_in, int64_t n, double* grm_out, double* mb_out,

@@ -417,3 +417,110 @@ def test_two_gpus_nccl_if_available():
                         "--master-addr", "127.0.0.1", "--master-port", "29611", str(root / "scripts" / "dist_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------ BASELINE configs[2] and [4] at full size
+
+def _device_fbm(n, m):
+    X = tpg.FBMCode256.__new__(tpg.FBMCode256)
+    X.backingfile, X.nrow, X.ncol, X.code256 = "<device>", n, m, None
+    return X
+
+
+def test_1000g_shape_grm_imputed_bytes():
+    """2504 x 1,000,000, imputed codes 4/5/6 (configs[2]): the raw-byte rule makes imputed files
+    identical to NA files; default block.size gives the pad-quirk constant 8; GRM is centred;
+    a subsample is checked against the oracle."""
+    import torch
+    n, m = 2504, 1_000_000
+    ctx = L.Context(0)
+    eb = L.errbuf()
+    X = _device_fbm(n, m)
+    res = {}
+    for mode in (1, 0):
+        dev = torch.empty(n * m, dtype=torch.uint8, device="cuda")
+        L.check(L.lib().tpg_synth_fill(ctx.handle, dev.data_ptr(), n, m, 0, 20260003, 0.01, mode, eb, len(eb)), eb)
+        src = (L.SRC_DEVICE, dev.data_ptr(), dev)
+        res[mode] = tpg.snp_allele_sharing_counts(X, src=src)           # default block.size = block_size(2504)
+        if mode == 1:
+            assert tpg.snp.last_stats["n_short"] == 8 == O.n_short(m, O.block_size(n))
+            assert set(torch.unique(dev[:10_000_000]).tolist()) <= {0, 1, 2, 4, 5, 6}
+            grm = tpg.snp_grm(X, src=src)
+            clean = tpg.snp_allele_sharing_counts(X, src=src, pad_quirk=False)
+            cols = np.sort(np.random.default_rng(1).choice(m, 700, replace=False)).astype(np.int32) + 1
+            sub = tpg.snp_allele_sharing_counts(X, ind_col=cols, src=src, block_size=101)
+            host_cols = dev.view(m, n)[torch.from_numpy(cols.astype(np.int64) - 1).cuda()].cpu().numpy()
+        del dev
+    a1, num1, den1 = res[1]
+    a0, num0, den0 = res[0]
+    assert np.array_equal(num1, num0) and np.array_equal(den1, den0) and same(a1, a0)     # Q2: imputed == missing
+    assert np.array_equal(num1, clean[1] + 8) and np.array_equal(den1, clean[2])          # Q1: +n_short
+    assert np.array_equal(num1, num1.T) and np.array_equal(np.diag(clean[1]) <= np.diag(den1), np.ones(n, bool))
+    off = ~np.eye(n, dtype=bool)
+    assert abs(grm[off].mean()) < 1e-12                                                    # centred by mb
+    mb = a1[off].mean()
+    assert np.allclose(grm, 2 * (a1 - mb) / (1 - mb), rtol=0, atol=GRM_ATOL)
+    ref = O.snp_allele_sharing(host_cols.reshape(-1), n, 700, block_size_=101)
+    assert np.array_equal(sub[1], ref["num"]) and np.array_equal(sub[2], ref["denom"]) and same(sub[0], ref["as"])
+
+
+def test_mixed_ploidy_shape_ibs_subsets():
+    """10,000 x 1,000,000, 10% missing, pseudohaploid + tetraploid-coded rows (configs[4]):
+    snp_ibs with a shuffled 70% row subset and every-3rd + shuffled-tail loci, all three types."""
+    import torch
+    n_tot, m_tot = 10_000, 1_000_000
+    ctx = L.Context(0)
+    eb = L.errbuf()
+    dev = torch.empty(n_tot * m_tot, dtype=torch.uint8, device="cuda")
+    L.check(L.lib().tpg_synth_fill(ctx.handle, dev.data_ptr(), n_tot, m_tot, 0, 20260005, 0.10, 2, eb, len(eb)), eb)
+    assert set(torch.unique(dev[:20_000_000]).tolist()) == {0, 1, 2, 3, 4, 5}
+    X = _device_fbm(n_tot, m_tot)
+    src = (L.SRC_DEVICE, dev.data_ptr(), dev)
+    rng = np.random.default_rng(5)
+    rows = (rng.permutation(n_tot)[: n_tot * 7 // 10] + 1).astype(np.int32)
+    tail = rng.permutation(m_tot)[: m_tot // 20]
+    cols = (np.concatenate([np.arange(0, m_tot, 3), tail]) + 1).astype(np.int32)
+    n, m = len(rows), len(cols)
+    raw_counts = tpg.snp_ibs(X, rows, cols, type="raw_counts", src=src)
+    ibs, valid = raw_counts["ibs"][:], raw_counts["valid_n"][:]
+    prop = tpg.snp_ibs(X, rows, cols, type="proportion", src=src)
+    adj = tpg.snp_ibs(X, rows, cols, type="adjusted_counts", src=src)
+    with np.errstate(all="ignore"):
+        assert same(prop, ibs / valid) and same(adj, (ibs / valid) * m)
+    assert np.array_equal(ibs, ibs.T) and np.array_equal(np.diag(ibs), np.diag(valid)) and valid.max() <= 2 * m
+    assert 0.78 < np.diag(valid).mean() / (2 * m) < 0.92   # 10% missing, tetraploid rows lose dosages 3 and 4 too
+    # exact check of a 48-row x 900-locus sub-job against the oracle (bytes pulled from the device)
+    r_sub, c_sub = rows[:48], cols[rng.permutation(m)[:900]]
+    host = dev.view(m_tot, n_tot)[torch.from_numpy(c_sub.astype(np.int64) - 1).cuda()].cpu().numpy()  # [900, n_tot]
+    got = tpg.snp_ibs(X, r_sub, c_sub, type="raw_counts", src=src)
+    ref = O.snp_ibs(host.reshape(-1), n_tot, 900, r_sub, None, type="raw_counts")
+    assert np.array_equal(got["ibs"][:], ref["ibs"]) and np.array_equal(got["valid_n"][:], ref["valid_n"])
+    # and the same 48 individuals inside the big job
+    assert np.array_equal(ibs[:48, :48].diagonal(), np.diag(valid)[:48])
+
+
+@pytest.mark.parametrize("shard", ["loci", "tiles"])
+def test_in_process_multi_gpu_driver(shard, families):
+    """tpg_pairwise_multi (one process, one host thread per device, counts summed on the first
+    device).  With one GPU the ranks share it (devices = [0, 0, 0]); with more they spread out."""
+    import torch
+    ndev = torch.cuda.device_count()
+    devices = [r % ndev for r in range(3)]
+    rng = np.random.default_rng(21)
+    n, m = 600, 9000
+    raw = random_bk(rng, n, m, 0.07, codes=(0, 1, 2, 3, 5))
+    X = fbm_of(raw, n, m)
+    rows, cols = pick("subset", n, rng), pick("every3", m, rng)
+    for fn, kw in ((tpg.snp_king, {}), (tpg.snp_allele_sharing, {"block_size": 333}), (tpg.snp_grm, {"block_size": 333})):
+        ref = fn(X, rows, cols, **kw)
+        got = fn(X, rows, cols, devices=devices, shard=shard, gpu_chunk_loci=1024, **kw)
+        if fn is tpg.snp_grm:
+            assert np.allclose(got, ref, rtol=0, atol=GRM_ATOL, equal_nan=True)
+        else:
+            assert same(got, ref)
+    r1 = tpg.snp_ibs(X, type="raw_counts")
+    r2 = tpg.snp_ibs(X, type="raw_counts", devices=devices, shard=shard)
+    assert np.array_equal(r1["ibs"][:], r2["ibs"][:]) and np.array_equal(r1["valid_n"][:], r2["valid_n"][:])
+    f = families
+    Xf = tpg.FBMCode256(f["path"], 12, 961)   # fewer loci blocks than ranks in places: still exact
+    assert same(tpg.snp_king(Xf, devices=[0] * 8, shard=shard), O.snp_king(f["raw"], 12, 961)["king"])

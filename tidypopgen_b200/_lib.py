@@ -101,6 +101,7 @@ SIGNATURES = {
     "tpg_split_len": (C.c_int64, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "tpg_as_pad_count": (C.c_int64, [C.c_int64, C.c_int64]),
     "tpg_pairwise": (C.c_int, [C.POINTER(Job), C.POINTER(Result)] + _ERR),
+    "tpg_pairwise_multi": (C.c_int, [C.POINTER(Job), C.POINTER(Result), C.c_void_p, C.c_int32, C.c_int32] + _ERR),
     "tpg_pairwise_ctx": (C.c_int, [C.c_void_p, C.POINTER(Job), C.POINTER(Result)] + _ERR),
     "tpg_grm_from_as": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_double)] + _ERR),
     "tpg_ctx_create": (C.c_void_p, [C.c_int] + _ERR),

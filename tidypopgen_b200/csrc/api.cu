@@ -654,6 +654,129 @@ static Ctx* cached_ctx(int device, const Err& E, int* rc) {
   return c;
 }
 
+// One context per (rank slot) for the in-process multi-GPU driver; a slot is rebuilt when
+// the caller maps it to another device.
+static Ctx* g_rank_ctx[64] = {nullptr};
+
+static Ctx* rank_ctx(int slot, int device, const Err& E, int* rc) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (slot < 0 || slot >= 64) { *rc = E.fail(TPG_ERR_ARG, "too many devices"); return nullptr; }
+  Ctx* c = g_rank_ctx[slot];
+  if (c && c->device == device) return c;
+  if (c) {
+    trim_ctx(c);
+    g_rank_ctx[slot] = nullptr;  // streams/events of the old slot are leaked on purpose (rare path)
+  }
+  c = new Ctx();
+  *rc = ctx_init(c, device, E);
+  if (*rc) { delete c; return nullptr; }
+  g_rank_ctx[slot] = c;
+  return c;
+}
+
+// a += b, launched on device 0's stream (finish.cu)
+int launch_add_counts(Ctx* ctx, int32_t* a, const int32_t* b, int64_t elems, cudaStream_t st, const Err& E);
+
+// In-process multi-GPU job (the R process is one process): one host thread per device
+// accumulates its shard (loci slice, or owned output blocks) into its own count matrices;
+// the int32 matrices are then summed onto the first device over NVLink (peer copies) and
+// finished there once.  Exact for both partitions, because counts are integer sums and the
+// tile partition's per-rank matrices are disjoint.
+static int pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* devices, int ndev,
+                          int shard_mode, const Err& E) {
+  if (ndev <= 0 || !devices) return E.fail(TPG_ERR_ARG, "no devices given");
+  if (ndev > 64) return E.fail(TPG_ERR_ARG, "at most 64 devices");
+  if (ndev > 1 && job->src_kind == TPG_SRC_DEVICE)
+    return E.fail(TPG_ERR_ARG, "a device-resident source lives on one GPU; multi-GPU jobs take a file or host source");
+  if (!res || !res->out0) return E.fail(TPG_ERR_ARG, "result / out0 is NULL");
+  const int64_t n = job->ind_row ? job->n : job->nrow_total;
+  if (n <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row");
+  if (shard_mode != TPG_SHARD_LOCI && shard_mode != TPG_SHARD_TILES)
+    shard_mode = n <= 30000 ? TPG_SHARD_LOCI : TPG_SHARD_TILES;
+  const double t_begin = now_ms();
+  memset(&res->stats, 0, sizeof res->stats);
+  const size_t celems = size_t(tpg_counts_elems(n));
+  const size_t cbytes = sizeof(int32_t) * celems;
+
+  std::vector<Ctx*> ctxs(ndev, nullptr);
+  for (int r = 0; r < ndev; ++r) {
+    int rc = TPG_OK;
+    ctxs[r] = rank_ctx(r, devices[r], E, &rc);
+    if (!ctxs[r]) return rc;
+  }
+  std::vector<int> rcs(ndev, TPG_OK);
+  std::vector<std::string> msgs(ndev);
+  std::vector<tpg_stats> sts(ndev);
+  std::vector<std::thread> th;
+  for (int r = 0; r < ndev; ++r) {
+    th.emplace_back([&, r] {
+      char buf[512] = {0};
+      Err Er{buf, sizeof buf};
+      Ctx* c = ctxs[r];
+      memset(&sts[r], 0, sizeof(tpg_stats));
+      tpg_job j = *job;
+      j.device = devices[r];
+      j.shard_mode = ndev > 1 ? shard_mode : TPG_SHARD_NONE;
+      j.shard_rank = r;
+      j.shard_world = ndev;
+      int rc = TPG_OK;
+      if (cudaSetDevice(c->device) != cudaSuccess) rc = Er.fail(TPG_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+      if (rc == TPG_OK) rc = ensure_slot(&c->d_counts, cbytes, false, "count matrices", Er);
+      if (rc == TPG_OK && cudaMemsetAsync(c->d_counts.p, 0, cbytes, c->s_compute) != cudaSuccess)
+        rc = Er.fail(TPG_ERR_CUDA, "memset failed");
+      if (rc == TPG_OK) { c->launches++; rc = accumulate_impl(c, &j, static_cast<int32_t*>(c->d_counts.p), &sts[r], Er); }
+      rcs[r] = rc;
+      msgs[r] = buf;
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int r = 0; r < ndev; ++r)
+    if (rcs[r]) return E.fail(rcs[r], "device %d (rank %d): %s", devices[r], r, msgs[r].c_str());
+
+  // ---- sum the count matrices onto rank 0's device
+  Ctx* c0 = ctxs[0];
+  TPG_CUDA_OK(cudaSetDevice(c0->device), E);
+  const int mask = prod_mask_for(job->stat);
+  const int64_t ld = tpg_counts_ld(n), ms = ld * ld;
+  const double t_red = now_ms();
+  if (ndev > 1) {
+    int rc = ensure_slot(&c0->d_out[3], sizeof(int32_t) * size_t(ms), false, "reduction staging", E);
+    if (rc) return rc;
+    int32_t* tmp = static_cast<int32_t*>(c0->d_out[3].p);
+    for (int r = 1; r < ndev; ++r)
+      for (int k = 0; k < TPG_NUM_COUNT_MATS; ++k) {
+        if (!(mask & (1 << k))) continue;
+        const int32_t* from = static_cast<const int32_t*>(ctxs[r]->d_counts.p) + k * ms;
+        TPG_CUDA_OK(cudaMemcpyPeerAsync(tmp, c0->device, from, ctxs[r]->device, sizeof(int32_t) * size_t(ms),
+                                        c0->s_compute), E);
+        rc = launch_add_counts(c0, static_cast<int32_t*>(c0->d_counts.p) + k * ms, tmp, ms, c0->s_compute, E);
+        if (rc) return rc;
+      }
+    TPG_CUDA_OK(cudaStreamSynchronize(c0->s_compute), E);
+  }
+  const double ms_reduce = now_ms() - t_red;
+  tpg_job j0 = *job;
+  j0.device = c0->device;
+  j0.shard_mode = TPG_SHARD_NONE;
+  j0.shard_rank = 0;
+  j0.shard_world = 1;
+  int rc = finish_impl(c0, &j0, static_cast<int32_t*>(c0->d_counts.p), res, E);
+  // stats: stage times are the max over devices (they ran side by side); bytes and MACs add up
+  for (int r = 0; r < ndev; ++r) {
+    res->stats.ms_read = std::max(res->stats.ms_read, sts[r].ms_read);
+    res->stats.ms_h2d = std::max(res->stats.ms_h2d, sts[r].ms_h2d);
+    res->stats.ms_decode = std::max(res->stats.ms_decode, sts[r].ms_decode);
+    res->stats.ms_gram = std::max(res->stats.ms_gram, sts[r].ms_gram);
+    res->stats.bytes_h2d += sts[r].bytes_h2d;
+    res->stats.n_chunks += sts[r].n_chunks;
+    res->stats.mma_macs += sts[r].mma_macs;
+    res->stats.n_launches += sts[r].n_launches;
+  }
+  res->stats.ms_finish += ms_reduce;  // the NVLink reduction is accounted with the finish stage
+  res->stats.ms_total = now_ms() - t_begin;
+  return rc;
+}
+
 }  // namespace tpg
 
 using namespace tpg;
@@ -788,6 +911,13 @@ int tpg_pairwise_ctx(tpg_ctx* h, const tpg_job* job, tpg_result* res, char* err,
   Err E{err, errlen};
   if (!h || !job || !res) return E.fail(TPG_ERR_ARG, "ctx / job / result is NULL");
   return pairwise_on(reinterpret_cast<Ctx*>(h), job, res, E);
+}
+
+int tpg_pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* devices, int32_t ndev,
+                       int32_t shard_mode, char* err, size_t errlen) {
+  Err E{err, errlen};
+  if (!job || !res) return E.fail(TPG_ERR_ARG, "job / result is NULL");
+  return pairwise_multi(job, res, devices, ndev, shard_mode, E);
 }
 
 int tpg_grm_from_as(int device, const double* as_in, int64_t n, double* grm_out, double* mb_out,

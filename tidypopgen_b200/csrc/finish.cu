@@ -239,6 +239,25 @@ int launch_finish(Ctx* ctx, const FinishArgs& a, cudaStream_t st, const Err& E) 
   return TPG_OK;
 }
 
+// ------------------------------------------------------------------ count reduction (multi-GPU)
+__global__ void __launch_bounds__(256) add_counts_kernel(int4* a, const int4* b, int64_t n4) {
+  for (int64_t e = int64_t(blockIdx.x) * 256 + threadIdx.x; e < n4; e += int64_t(gridDim.x) * 256) {
+    int4 x = a[e];
+    const int4 y = b[e];
+    x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    a[e] = x;
+  }
+}
+
+int launch_add_counts(Ctx* ctx, int32_t* a, const int32_t* b, int64_t elems, cudaStream_t st, const Err& E) {
+  const int64_t n4 = elems / 4;  // ld is a multiple of 256: always divisible
+  const int gb = int(std::min<int64_t>(148 * 16, (n4 + 255) / 256));
+  add_counts_kernel<<<gb, 256, 0, st>>>(reinterpret_cast<int4*>(a), reinterpret_cast<const int4*>(b), n4);
+  TPG_CUDA_OK(cudaGetLastError(), E);
+  ctx->launches++;
+  return TPG_OK;
+}
+
 // ------------------------------------------------------------------ synthetic genotypes
 __global__ void __launch_bounds__(256)
 synth_kernel(uint8_t* raw, int64_t nrow, int64_t ncol, int64_t col_offset, uint64_t seed,

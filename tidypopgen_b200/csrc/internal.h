@@ -136,6 +136,7 @@ int launch_synth(Ctx* ctx, uint8_t* d_raw, int64_t nrow, int64_t ncol, int64_t c
                  uint64_t seed, double missing_rate, int mode, cudaStream_t st, const Err& E);
 
 int check_err_flag(Ctx* ctx, const Err& E);
+int launch_add_counts(Ctx* ctx, int32_t* a, const int32_t* b, int64_t elems, cudaStream_t st, const Err& E);
 
 // ---- host helpers (split.cpp)
 int64_t block_size_default(int64_t n);

@@ -97,9 +97,12 @@ def _colmajor(n: int) -> np.ndarray:
 
 
 def run_job(X: FBMCode256, ind_row, ind_col, stat: int, block_size_: int, *, want_aux: bool = False,
-            out0=None, out1=None, **kw):
-    """One tpg_pairwise call.  Returns (out0, out1, aux0, aux1) as [i, j]-indexed arrays."""
+            out0=None, out1=None, devices=None, shard: str = "auto", **kw):
+    """One tpg_pairwise call (or tpg_pairwise_multi when `devices` lists several GPUs).
+    Returns (out0, out1, aux0, aux1) as [i, j]-indexed arrays."""
     global last_stats
+    if devices is not None and len(devices) >= 1:
+        kw.setdefault("device", int(devices[0]))
     job, keep = make_job(X, ind_row, ind_col, stat, block_size_, **kw)
     n = job.n if job.ind_row else X.nrow
     if n <= 0 or (job.m if job.ind_col else X.ncol) <= 0:
@@ -117,7 +120,12 @@ def run_job(X: FBMCode256, ind_row, ind_col, stat: int, block_size_: int, *, wan
     res.aux1 = a1.ctypes.data if a1 is not None else None
     res.out_on_device = 0
     eb = L.errbuf()
-    rc = L.lib().tpg_pairwise(C.byref(job), C.byref(res), eb, len(eb))
+    if devices is not None and len(devices) > 1:
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        mode = {"auto": L.SHARD_NONE, "loci": L.SHARD_LOCI, "tiles": L.SHARD_TILES}[shard]
+        rc = L.lib().tpg_pairwise_multi(C.byref(job), C.byref(res), devs.ctypes.data, len(devs), mode, eb, len(eb))
+    else:
+        rc = L.lib().tpg_pairwise(C.byref(job), C.byref(res), eb, len(eb))
     del keep
     L.check(rc, eb)
     last_stats = res.stats.as_dict()
