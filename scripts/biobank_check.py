@@ -2,9 +2,9 @@
 upper-triangle tile-sharded across the ranks of one node (no data-path collective), with an
 exact parity check on sampled pairs.
 
-    python scripts/biobank_check.py [--n 50000] [--m 500000]                 # 1 GPU
+    python scripts/biobank_check.py [--indiv 50000] [--loci 500000]                 # 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
-        --master-port 29540 scripts/biobank_check.py --n 50000 --m 500000       # 8 GPUs
+        --master-port 29540 scripts/biobank_check.py --indiv 50000 --loci 500000       # 8 GPUs
 
 Every rank generates the same synthetic .bk image on its GPU (counter-based RNG), streams all
 loci, and computes + finishes only the 256x256 output blocks it owns.  The full-size oracle is
@@ -42,8 +42,8 @@ def king_pair(gi, gj):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=50000)
-    ap.add_argument("--m", type=int, default=500000)
+    ap.add_argument("--indiv", dest="n", type=int, default=50000)
+    ap.add_argument("--loci", dest="m", type=int, default=500000)
     ap.add_argument("--missing", type=float, default=0.01)
     ap.add_argument("--pairs", type=int, default=64)
     args = ap.parse_args()
