@@ -110,6 +110,7 @@ typedef struct tpg_job {
 
 #define TPG_FLAG_PLANES_K_MAJOR 1 /* transpose in decode, K-major UMMA operands (default: MN-major) */
 #define TPG_FLAG_NO_OVERLAP 2     /* serialise copy / decode / gram (debugging)                      */
+#define TPG_FLAG_GRAM_1CTA 4      /* single-CTA gram kernel (default: CTA pairs, cta_group::2)       */
 
 /* Per-stage figures for the caller (R glue prints them when verbose). */
 typedef struct tpg_stats {
@@ -255,7 +256,8 @@ int tpg_decode_planes(tpg_ctx* ctx, const uint8_t* d_raw, int64_t raw_bytes, int
 /* gram_i8: int8 tcgen05 Gram products of the planes into the int32 count buffer
  * (atomic adds, so calls accumulate).  Replaces the dsyrk/dgemm products
  * src/snp_king.cpp:70-72, src/snp_ibs.cpp:67-72, src/snp_as.cpp:64-65.
- * prod_mask: bit TPG_MAT_* set = compute that product. */
+ * prod_mask: bit TPG_MAT_* set = compute that product.
+ * k_major: bit 0 = K-major planes, bit 1 = single-CTA kernel (default: CTA pairs). */
 int tpg_gram(tpg_ctx* ctx, const int8_t* d_planes, int64_t plane_stride, int64_t n_pad,
              int64_t lc_pad, int32_t k_major, int32_t prod_mask, int32_t shard_rank,
              int32_t shard_world, int32_t* d_counts, float* ms_out, char* err, size_t errlen);

@@ -160,14 +160,15 @@ def pick(kind, total, rng):
 
 
 @pytest.mark.parametrize("case", CASES, ids=[f"n{c[0]}_m{c[1]}_{c[4]}" for c in CASES])
-@pytest.mark.parametrize("k_major", [False, True], ids=["mn", "kmajor"])
-def test_random_parity_all_stats(case, k_major):
+@pytest.mark.parametrize("variant", [0, L.FLAG_PLANES_K_MAJOR, L.FLAG_GRAM_1CTA, L.FLAG_PLANES_K_MAJOR | L.FLAG_GRAM_1CTA],
+                         ids=["mn", "kmajor", "mn_1cta", "kmajor_1cta"])
+def test_random_parity_all_stats(case, variant):
     n_tot, m_tot, bs, chunk, rk, ck = case
     rng = np.random.default_rng(n_tot * 1000 + m_tot)
     raw = random_bk(rng, n_tot, m_tot, 0.08, codes=(0, 1, 2, 3, 4, 5, 6, 255))
     X = fbm_of(raw, n_tot, m_tot)
     rows, cols = pick(rk, n_tot, rng), pick(ck, m_tot, rng)
-    kw = dict(gpu_chunk_loci=chunk, flags=L.FLAG_PLANES_K_MAJOR if k_major else 0)
+    kw = dict(gpu_chunk_loci=chunk, flags=variant)
     ref_k = O.snp_king(raw, n_tot, m_tot, rows, cols, block_size_=bs)
     king, K, N = tpg.snp_king_counts(X, rows, cols, block_size=bs, **kw)
     assert np.array_equal(K, ref_k["K"]), "KING numerator"
@@ -284,9 +285,10 @@ def test_decode_planes_kernel(k_major, gather):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("ctas", [2, 1])
 @pytest.mark.parametrize("k_major", [False, True])
-@pytest.mark.parametrize("shape", [(256, 128), (512, 1152), (1024, 4096)])
-def test_gram_kernel(k_major, shape):
+@pytest.mark.parametrize("shape", [(256, 128), (512, 1152), (1024, 4096), (2560, 2048)])
+def test_gram_kernel(k_major, shape, ctas):
     import torch
     n_pad, lc_pad = shape
     ctx = L.Context(0)
@@ -298,8 +300,8 @@ def test_gram_kernel(k_major, shape):
     d_counts = torch.zeros(4 * n_pad * n_pad, dtype=torch.int32, device="cuda")
     eb, ms = L.errbuf(), C.c_float(0)
     for rep in range(2):  # two launches accumulate
-        L.check(L.lib().tpg_gram(ctx.handle, d_planes.data_ptr(), n_pad * lc_pad, n_pad, lc_pad, int(k_major),
-                                 0b1111, 0, 1, d_counts.data_ptr(), C.byref(ms), eb, len(eb)), eb)
+        L.check(L.lib().tpg_gram(ctx.handle, d_planes.data_ptr(), n_pad * lc_pad, n_pad, lc_pad,
+                                 int(k_major) | (2 if ctas == 1 else 0), 0b1111, 0, 1, d_counts.data_ptr(), C.byref(ms), eb, len(eb)), eb)
     got = d_counts.cpu().numpy().reshape(4, n_pad, n_pad).transpose(0, 2, 1)  # [mat][i][j]
     d, nm, h1 = [p.astype(np.float64) for p in planes]
     iu = np.triu_indices(n_pad)

@@ -546,6 +546,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     ga.n_pad = pl.n_pad;
     ga.lc_pad = lc_pad;
     ga.k_major = k_major;
+    ga.ctas = (job->flags & TPG_FLAG_GRAM_1CTA) ? 1 : 0;
     ga.prod_mask = pl.prod_mask;
     ga.shard_rank = job->shard_mode == TPG_SHARD_TILES ? job->shard_rank : 0;
     ga.shard_world = job->shard_mode == TPG_SHARD_TILES ? job->shard_world : 1;
@@ -971,7 +972,7 @@ int tpg_gram(tpg_ctx* h, const int8_t* d_planes, int64_t plane_stride, int64_t n
   TPG_CUDA_OK(cudaSetDevice(c->device), E);
   GramArgs a;
   a.planes = d_planes; a.plane_stride = plane_stride; a.n = n_pad; a.n_pad = n_pad;
-  a.lc_pad = lc_pad; a.k_major = k_major != 0; a.prod_mask = prod_mask;
+  a.lc_pad = lc_pad; a.k_major = (k_major & 1) != 0; a.ctas = (k_major & 2) ? 1 : 0; a.prod_mask = prod_mask;
   a.shard_rank = shard_rank; a.shard_world = shard_world; a.counts = d_counts; a.ld = n_pad;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);

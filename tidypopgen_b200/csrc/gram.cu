@@ -207,6 +207,180 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair variant
+// Two CTAs of one cluster (a TPC's SM pair) share every MMA: tcgen05.mma.cta_group::2 with
+// M = 256 (128 A rows from each CTA's smem) x N = 256 (128 B rows from each CTA's smem), so
+// a CTA stages 32 KiB per 128 loci instead of 48 KiB — a third less L2 -> smem traffic per
+// MAC, which is what bounds the single-CTA kernel ("gram_i8").  A work item is a
+// 256 x 256 tile; CTA r of the pair owns its rows [128 r, 128 r + 128) (TMEM lanes) and
+// loads B rows [128 r, 128 r + 128).  Only the leader CTA (rank 0) issues MMAs; TMA bytes of
+// both CTAs are counted on the leader's full barrier; tcgen05.commit multicasts the "slot
+// free" / "accumulator ready" arrivals to both CTAs; the peer's epilogue warps hand the
+// accumulator back with a remote arrive on the leader's barrier.
+constexpr int kPairStages = 6;
+constexpr int kPairTileM = 256;
+constexpr int kHalfBytes = 128 * kTileK;              // one 128 x 128 box, 16 KiB
+constexpr int kPairStageBytes = 2 * kHalfBytes;       // per CTA: A half + B half
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + 1024 + 256;
+
+template <bool kMajorK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGramThreads, 1)
+gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_nm,
+                    const __grid_constant__ CUtensorMap tm_h1, const GramParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes);
+  uint64_t* full_bar = bars;                          // [kPairStages] used in the leader only
+  uint64_t* empty_bar = bars + kPairStages;           // [kPairStages] in each CTA
+  uint64_t* tfull_bar = bars + 2 * kPairStages;       // [2] in each CTA
+  uint64_t* tempty_bar = bars + 2 * kPairStages + 2;  // [2] used in the leader only (8 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_d);
+    tma_prefetch_desc(&tm_nm);
+    tma_prefetch_desc(&tm_h1);
+    for (int s = 0; s < kPairStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = cluster; it < p.n_items; it += n_clusters) {
+        const WorkItem w = p.items[it];
+        const int prod = w.prod_ti & 15, ti = w.prod_ti >> 4, tj = w.tj;
+        int pa, pb;
+        prod_planes(prod, pa, pb);
+        const CUtensorMap* ma = pa == 0 ? &tm_d : pa == 1 ? &tm_nm : &tm_h1;
+        const CUtensorMap* mb = pb == 0 ? &tm_d : pb == 1 ? &tm_nm : &tm_h1;
+        const int row_a = ti * kPairTileM + int(rank) * 128;
+        const int row_b = tj * kTileN + int(rank) * 128;
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+          uint8_t* sa = smem + stage * kPairStageBytes;
+          uint8_t* sb = sa + kHalfBytes;
+          // the leader expects the bytes of BOTH CTAs on its barrier
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
+          const uint32_t bar0 = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (kMajorK) {
+            tma_load_2d_pair(sa, ma, bar0, kb * kTileK, row_a);
+            tma_load_2d_pair(sb, mb, bar0, kb * kTileK, row_b);
+          } else {
+            tma_load_2d_pair(sa, ma, bar0, row_a, kb * kTileK);
+            tma_load_2d_pair(sb, mb, bar0, row_b, kb * kTileK);
+          }
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_i8(kPairTileM, kTileN, !kMajorK);
+      constexpr uint32_t lbo = kMajorK ? 16u : uint32_t(kHalfBytes);  // one 128-row block: unused
+      constexpr uint32_t sbo = 1024u;
+      constexpr uint32_t kstep = kMajorK ? (32u >> 4) : (4096u >> 4);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int it = cluster; it < p.n_items; it += n_clusters) {
+        const WorkItem w = p.items[it];
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(acc * kTileN);
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kPairStageBytes);
+          const uint64_t da = make_smem_desc_sw128(sa, lbo, sbo);
+          const uint64_t db = make_smem_desc_sw128(sa + kHalfBytes, lbo, sbo);
+#pragma unroll
+          for (int k = 0; k < kTileK / 32; ++k) {
+            umma_i8_pair(tmem_d, da + uint64_t(k * kstep), db + uint64_t(k * kstep), idesc,
+                         (kb > w.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage], 3);  // frees the slot in both CTAs
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tfull_bar[acc], 3);      // accumulators of both CTAs complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue (warps 2..5, both CTAs)
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int it = cluster; it < p.n_items; it += n_clusters) {
+      const WorkItem w = p.items[it];
+      const int prod = w.prod_ti & 15, ti = w.prod_ti >> 4, tj = w.tj;
+      const bool sym = prod != TPG_MAT_HN;
+      mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
+      tc_fence_after();
+      const int i = ti * kPairTileM + int(rank) * 128 + q * 32 + lane;
+      const int j0 = tj * kTileN;
+      int32_t* cbase = p.counts + int64_t(prod) * p.mat_stride + i;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kTileN);
+#pragma unroll 1
+      for (int c = 0; c < kTileN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + uint32_t(c), v);
+        tmem_ld_wait();
+        if (c + 32 == kTileN) {  // accumulator drained: hand it back (to the leader's barrier)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        }
+        if (j0 + c < p.n && i < p.n) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = j0 + c + jj;
+            if (j < p.n && (!sym || i <= j)) atomicAdd(cbase + int64_t(j) * p.ld, int32_t(v[jj]));
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  // No CTA may leave while its partner can still signal its barriers or read its smem.
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -254,24 +428,66 @@ static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms) {
   return std::max(best, std::min(ks_l2, max_ks));
 }
 
+static bool pair_mode(const GramArgs& a) {
+  if (a.ctas == 1) return false;
+  if (a.ctas == 2) return true;
+  const char* e = getenv("TPG_GRAM_CTAS");
+  return !(e && atoi(e) == 1);
+}
+
 int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out, const Err& E) {
   if (a.n_pad % kRowPad || a.lc_pad % kLociPad || a.lc_pad <= 0)
     return E.fail(TPG_ERR_ARG, "gram: n_pad (%lld) / lc_pad (%lld) not tile multiples",
                   (long long)a.n_pad, (long long)a.lc_pad);
-  const int64_t tiles_m = a.n_pad / kTileM, tiles_n = a.n_pad / kTileN;
+  const bool pair = pair_mode(a);
+  const int tile_m = pair ? kPairTileM : kTileM;
+  const int64_t tiles_m = a.n_pad / tile_m, tiles_n = a.n_pad / kTileN;
   const int64_t kblocks = a.lc_pad / kTileK;
+
+  if (!ctx->gram_attr_set) {  // once per context (= per device)
+    TPG_CUDA_OK(cudaFuncSetAttribute(gram_i8_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), E);
+    TPG_CUDA_OK(cudaFuncSetAttribute(gram_i8_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), E);
+    TPG_CUDA_OK(cudaFuncSetAttribute(gram_i8_pair_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes), E);
+    TPG_CUDA_OK(cudaFuncSetAttribute(gram_i8_pair_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes), E);
+    // how many CTA pairs the device keeps resident at once (GPCs with an odd SM count lose one)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(ctx->num_sms / 2 * 2));
+    cfg.blockDim = dim3(kGramThreads);
+    cfg.dynamicSmemBytes = kPairSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, gram_i8_pair_kernel<false>, &cfg);
+    if (e != cudaSuccess) { cudaGetLastError(); nc = 0; }
+    ctx->pair_clusters = std::min(nc, ctx->num_sms / 2);
+    if (const char* ev = getenv("TPG_GRAM_CLUSTERS")) ctx->pair_clusters = std::max(1, std::min(atoi(ev), ctx->num_sms / 2));
+    ctx->gram_attr_set = true;
+  }
+  if (pair && ctx->pair_clusters <= 0)
+    return E.fail(TPG_ERR_CUDA, "gram: the device reports no resident CTA pairs for gram_i8_pair_kernel");
+  // schedulable units: SMs (one CTA each) or resident CTA pairs
+  const int units = pair ? ctx->pair_clusters : ctx->num_sms;
 
   // ---- tile list in L2-friendly order: 1024x1024 regions, then tiles, then products
   struct T { int prod, ti, tj; };
   std::vector<T> tiles;
-  const int64_t RI = 8, RJ = 4;
+  const int64_t RI = 1024 / tile_m, RJ = 4;
   for (int64_t rj = 0; rj < tiles_n; rj += RJ)
     for (int64_t ri = 0; ri < tiles_m; ri += RI)
       for (int64_t tj = rj; tj < std::min(rj + RJ, tiles_n); ++tj)
         for (int64_t ti = ri; ti < std::min(ri + RI, tiles_m); ++ti) {
-          const bool upper = kTileN * tj + (kTileN - 1) >= kTileM * ti;
-          // 256x256 ownership block of the tile (rows ti/2, cols tj); lower blocks mirror
-          const int64_t bi = ti / 2, bj = tj;
+          const bool upper = kTileN * tj + (kTileN - 1) >= tile_m * ti;
+          // 256x256 ownership block of the tile; lower blocks mirror
+          const int64_t bi = ti * tile_m / 256, bj = tj;
           for (int prod = 0; prod < TPG_NUM_COUNT_MATS; ++prod) {
             if (!(a.prod_mask & (1 << prod))) continue;
             if (prod != TPG_MAT_HN && !upper) continue;
@@ -282,14 +498,13 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
         }
   if (tiles.empty()) { if (macs_out) *macs_out = 0; return TPG_OK; }
 
-  const int sms = ctx->num_sms;
-  const int ks = choose_ksplit(int64_t(tiles.size()), kblocks, sms);
-  if (macs_out) *macs_out = int64_t(tiles.size()) * kTileM * kTileN * a.lc_pad;
+  const int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units);
+  if (macs_out) *macs_out = int64_t(tiles.size()) * tile_m * kTileN * a.lc_pad;
 
   // The work list only depends on the geometry; chunks of equal size reuse the upload.
   char key[160];
-  snprintf(key, sizeof key, "%lld/%lld/%d/%d/%d/%d", (long long)a.n_pad, (long long)a.lc_pad,
-           a.prod_mask, a.shard_rank, a.shard_world, ks);
+  snprintf(key, sizeof key, "%lld/%lld/%d/%d/%d/%d/%d", (long long)a.n_pad, (long long)a.lc_pad,
+           a.prod_mask, a.shard_rank, a.shard_world, ks, tile_m);
   if (ctx->items_key != key) {
     std::vector<WorkItem>& items = ctx->h_items;
     items.clear();
@@ -335,16 +550,15 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   p.n = int(a.n);
   p.err_flag = ctx->d_err_flag;
 
-  const int grid = int(std::min<size_t>(n_items, size_t(sms)));
-  if (!ctx->gram_attr_set) {  // once per context (= per device)
-    TPG_CUDA_OK(cudaFuncSetAttribute(gram_i8_kernel<true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), E);
-    TPG_CUDA_OK(cudaFuncSetAttribute(gram_i8_kernel<false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), E);
-    ctx->gram_attr_set = true;
+  if (pair) {
+    const int grid = 2 * int(std::min<size_t>(n_items, size_t(units)));  // cluster dims are compiled in
+    if (a.k_major) gram_i8_pair_kernel<true><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
+    else gram_i8_pair_kernel<false><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
+  } else {
+    const int grid = int(std::min<size_t>(n_items, size_t(units)));
+    if (a.k_major) gram_i8_kernel<true><<<grid, kGramThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
+    else gram_i8_kernel<false><<<grid, kGramThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
   }
-  if (a.k_major) gram_i8_kernel<true><<<grid, kGramThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
-  else gram_i8_kernel<false><<<grid, kGramThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
   TPG_CUDA_OK(cudaGetLastError(), E);
   ctx->launches++;
   return TPG_OK;

@@ -41,6 +41,7 @@ struct Ctx {
   void* encode_tiled = nullptr;    // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
   int64_t launches = 0;
   bool gram_attr_set = false;
+  int pair_clusters = 0;           // CTA pairs resident at once (cudaOccupancyMaxActiveClusters)
   // Grow-only buffer cache, reused across jobs (cudaMalloc / cudaMallocHost / cudaFree are
   // slow and synchronising; a job must not pay them every call).  tpg_ctx_trim() frees it.
   struct Slot { void* p = nullptr; size_t cap = 0; };
@@ -96,6 +97,7 @@ struct GramArgs {
   int64_t n_pad;
   int64_t lc_pad;  // loci in this chunk (padded)
   bool k_major;
+  int ctas = 0;    // 1 = single-CTA kernel, 2 = CTA-pair kernel, 0 = default (pair)
   int prod_mask;
   int shard_rank, shard_world;  // tile sharding (world <= 1: everything)
   int32_t* counts;
