@@ -111,6 +111,7 @@ typedef struct tpg_job {
 #define TPG_FLAG_PLANES_K_MAJOR 1 /* transpose in decode, K-major UMMA operands (default: MN-major) */
 #define TPG_FLAG_NO_OVERLAP 2     /* serialise copy / decode / gram (debugging)                      */
 #define TPG_FLAG_GRAM_1CTA 4      /* single-CTA gram kernel (default: CTA pairs, cta_group::2)       */
+#define TPG_FLAG_NO_PACK 8        /* host sources: ship raw bytes, no 2-bit packing while staging     */
 
 /* Per-stage figures for the caller (R glue prints them when verbose). */
 typedef struct tpg_stats {
@@ -127,6 +128,7 @@ typedef struct tpg_stats {
   int64_t n_launches; /* kernels launched by this library in the call               */
   int64_t mma_macs;   /* int8 MACs issued to the tensor pipe (incl. padding)        */
   int64_t n_short;    /* allele-sharing padding-quirk constant that was applied     */
+  int64_t n_packed_chunks; /* chunks that crossed PCIe 2-bit packed (4 genotypes / byte)  */
 } tpg_stats;
 
 /*
@@ -246,6 +248,8 @@ int tpg_finish(tpg_ctx* ctx, const tpg_job* job, const int32_t* d_counts, tpg_re
  *   d_planes   : device, 3 planes, plane p at d_planes + p*plane_stride
  *   layout     : MN-major (default): plane[l*ld + i], ld = n_pad, lc_pad rows
  *                K-major (k_major=1): plane[i*ld + l], ld = lc_pad, n_pad rows
+ * k_major bit 2 (value 4): d_raw is a pk2 chunk (tpg_pk2_pack_host; raw_stride = tpg_pk2_stride,
+ * no row/column gather, MN-major only).
  * Padding rows/loci are written as zeros. */
 int tpg_decode_planes(tpg_ctx* ctx, const uint8_t* d_raw, int64_t raw_bytes, int64_t raw_stride,
                       const int32_t* d_row_idx, int64_t row0, int64_t n, int64_t n_pad,
@@ -266,6 +270,12 @@ int tpg_gram(tpg_ctx* ctx, const int8_t* d_planes, int64_t plane_stride, int64_t
  * CPU twin, byte-identical): fills column-major nrow x ncol bytes on the device. */
 int tpg_synth_fill(tpg_ctx* ctx, uint8_t* d_raw, int64_t nrow, int64_t ncol, int64_t col_offset,
                    uint64_t seed, double missing_rate, int32_t mode, char* err, size_t errlen);
+
+/* The 2-bit chunk format of the streamer ("pk2", csrc/pack.cpp): bytes per packed column for a
+ * row window of span individuals, and the packer itself (runs on the library's worker pool):
+ * column c is read at src + c*src_stride (span raw bytes) and written at dst + c*stride. */
+int64_t tpg_pk2_stride(int64_t span);
+void tpg_pk2_pack_host(const uint8_t* src, int64_t src_stride, int64_t span, int64_t ncol, uint8_t* dst);
 
 /* Host twin of tpg_synth_fill (byte-identical; include/tpg_synth.h holds the hash). */
 void tpg_synth_fill_host(uint8_t* raw, int64_t nrow, int64_t ncol, int64_t col_offset,

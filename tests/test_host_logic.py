@@ -69,3 +69,30 @@ def test_job_marshalling():
 def test_cut_by_size_and_defaults():
     assert snp.cut_by_size(961, 300)[:, 2].tolist() == [240, 240, 241, 240]
     assert tpg.block_size(929) == 144475
+
+
+def pk2_ref(raw, nrow, ncol, r0, span):
+    """numpy statement of the pk2 chunk format (csrc/pack.cpp)."""
+    st = int(L.lib().tpg_pk2_stride(span))
+    g = np.minimum(raw.reshape(ncol, nrow)[:, r0:r0 + span], 3).astype(np.uint8)
+    pad = np.full((ncol, st * 4), 3, np.uint8)
+    pad[:, :span] = g
+    q = pad.reshape(ncol, st, 4)
+    return (q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("shape", [(929, 300, 0, 929), (131, 77, 5, 101), (7, 6, 0, 7), (1024, 50, 128, 512),
+                                   (4097, 33, 1, 4095), (1, 9, 0, 1), (40, 3000, 2, 31)])
+def test_pk2_packer_matches_numpy(shape):
+    """The streamer's host-side 2-bit packer (AVX2 + scalar tails, worker pool): bytes above 2
+    collapse to code 3, padding is code 3, every column starts on a 16-byte boundary."""
+    nrow, ncol, r0, span = shape
+    rng = np.random.default_rng(nrow * 31 + ncol)
+    raw = rng.integers(0, 256, nrow * ncol).astype(np.uint8)
+    raw[rng.random(raw.size) < 0.8] %= 4
+    lib = L.lib()
+    st = int(lib.tpg_pk2_stride(span))
+    assert st % 16 == 0 and st * 4 >= span
+    out = np.zeros((ncol, st), np.uint8)
+    lib.tpg_pk2_pack_host(raw.ctypes.data + r0, nrow, span, ncol, out.ctypes.data)
+    assert np.array_equal(out, pk2_ref(raw, nrow, ncol, r0, span))

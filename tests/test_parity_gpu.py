@@ -160,8 +160,9 @@ def pick(kind, total, rng):
 
 
 @pytest.mark.parametrize("case", CASES, ids=[f"n{c[0]}_m{c[1]}_{c[4]}" for c in CASES])
-@pytest.mark.parametrize("variant", [0, L.FLAG_PLANES_K_MAJOR, L.FLAG_GRAM_1CTA, L.FLAG_PLANES_K_MAJOR | L.FLAG_GRAM_1CTA],
-                         ids=["mn", "kmajor", "mn_1cta", "kmajor_1cta"])
+@pytest.mark.parametrize("variant", [0, L.FLAG_PLANES_K_MAJOR, L.FLAG_GRAM_1CTA, L.FLAG_PLANES_K_MAJOR | L.FLAG_GRAM_1CTA,
+                                     L.FLAG_NO_PACK],
+                         ids=["mn", "kmajor", "mn_1cta", "kmajor_1cta", "mn_nopack"])
 def test_random_parity_all_stats(case, variant):
     n_tot, m_tot, bs, chunk, rk, ck = case
     rng = np.random.default_rng(n_tot * 1000 + m_tot)
@@ -308,6 +309,60 @@ def test_gram_kernel(k_major, shape, ctas):
     for mat, ref in ((L.MAT_DD, d @ d.T), (L.MAT_NN, nm @ nm.T), (L.MAT_HH, h1 @ h1.T)):
         assert np.array_equal(got[mat][iu], 2 * ref[iu].astype(np.int64)), mat
     assert np.array_equal(got[L.MAT_HN], 2 * (h1 @ nm.T).astype(np.int64))
+
+
+@pytest.mark.parametrize("shape", [(929, 700), (100, 37), (513, 130), (2049, 64)])
+def test_decode_planes_pk2_kernel(shape):
+    """decode of a 2-bit packed chunk (what host-sourced chunks look like after staging)."""
+    import torch
+    n, lc = shape
+    ctx = L.Context(0)
+    rng = np.random.default_rng(11)
+    raw = rng.integers(0, 256, size=(lc, n)).astype(np.uint8)
+    raw[rng.random(raw.shape) < 0.8] %= 4
+    lib = L.lib()
+    st = int(lib.tpg_pk2_stride(n))
+    packed = np.zeros((lc, st), np.uint8)
+    lib.tpg_pk2_pack_host(raw.ctypes.data, n, n, lc, packed.ctypes.data)
+    n_pad, lc_pad = (n + 255) // 256 * 256, (lc + 127) // 128 * 128
+    d_raw = torch.from_numpy(packed.reshape(-1)).cuda()
+    ps = n_pad * lc_pad
+    d_planes = torch.full((3 * ps,), 77, dtype=torch.int8, device="cuda")
+    eb = L.errbuf()
+    L.check(lib.tpg_decode_planes(ctx.handle, d_raw.data_ptr(), packed.size, st, None, 0, n, n_pad,
+                                  None, 0, lc, lc_pad, d_planes.data_ptr(), ps, 4, eb, len(eb)), eb)
+    got = d_planes.cpu().numpy().reshape(3, lc_pad, n_pad).transpose(0, 2, 1)
+    ref = np.zeros((3, n_pad, lc_pad), np.int8)
+    for p, x in enumerate(planes_ref(raw.T)):
+        ref[p, :n, :lc] = x
+    assert np.array_equal(got, ref)
+
+
+def test_hybrid_link_and_pack_chunks(monkeypatch):
+    """Pinned host source, many small chunks: some chunks are DMA'd raw, the rest cross PCIe
+    2-bit packed (the hybrid schedule); the result does not depend on which chunk went how."""
+    import torch
+    rng = np.random.default_rng(21)
+    n, m = 700, 40000
+    raw = random_bk(rng, n, m, 0.05, codes=(0, 1, 2, 3, 9))
+    X = fbm_of(raw, n, m)
+    ref, Kr, Nr = tpg.snp_king_counts(X, flags=L.FLAG_NO_PACK)
+    pinned = torch.from_numpy(raw).pin_memory()
+    src = (L.SRC_HOST, pinned.data_ptr(), pinned)
+    win = np.arange(11, 611, dtype=np.int32)          # contiguous row window: still packable
+    ref_w = tpg.snp_king(X, ind_row=win, flags=L.FLAG_NO_PACK)
+    for link in ("45", "0.5"):                        # a slow modelled link makes later chunks pack
+        monkeypatch.setenv("TPG_LINK_GBPS", link)
+        king, K, N = tpg.snp_king_counts(X, src=src, gpu_chunk_loci=2048)
+        st = dict(tpg.snp.last_stats)
+        assert st["n_chunks"] == 20 and 0 <= st["n_packed_chunks"] <= 20
+        if link == "0.5":
+            assert 1 <= st["n_packed_chunks"] < 20    # chunk 0 always goes raw (idle link)
+        assert np.array_equal(K, Kr) and np.array_equal(N, Nr) and same(king, ref)
+        assert same(tpg.snp_king(X, ind_row=win, src=src, gpu_chunk_loci=2048), ref_w)
+    # file source: every chunk is packed
+    tpg.snp_king(X, gpu_chunk_loci=4096)
+    assert tpg.snp.last_stats["n_packed_chunks"] == tpg.snp.last_stats["n_chunks"] == 10
 
 
 def test_synth_device_equals_host():

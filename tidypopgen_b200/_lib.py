@@ -22,7 +22,7 @@ OK, ERR_ARG, ERR_IO, ERR_CUDA, ERR_NOMEM, ERR_KERNEL = range(6)
 STAT_KING, STAT_IBS_RAW, STAT_IBS_PROPORTION, STAT_IBS_ADJUSTED, STAT_AS, STAT_GRM = range(6)
 SRC_FILE, SRC_HOST, SRC_DEVICE = range(3)
 SHARD_NONE, SHARD_LOCI, SHARD_TILES = range(3)
-FLAG_PLANES_K_MAJOR, FLAG_NO_OVERLAP, FLAG_GRAM_1CTA = 1, 2, 4
+FLAG_PLANES_K_MAJOR, FLAG_NO_OVERLAP, FLAG_GRAM_1CTA, FLAG_NO_PACK = 1, 2, 4, 8
 MAT_DD, MAT_NN, MAT_HH, MAT_HN = range(4)
 NUM_COUNT_MATS = 4
 
@@ -74,6 +74,7 @@ class Stats(C.Structure):
         ("n_launches", C.c_int64),
         ("mma_macs", C.c_int64),
         ("n_short", C.c_int64),
+        ("n_packed_chunks", C.c_int64),
     ]
 
     def as_dict(self) -> dict:
@@ -100,6 +101,8 @@ SIGNATURES = {
     "tpg_block_size": (C.c_int64, [C.c_int64]),
     "tpg_split_len": (C.c_int64, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "tpg_as_pad_count": (C.c_int64, [C.c_int64, C.c_int64]),
+    "tpg_pk2_stride": (C.c_int64, [C.c_int64]),
+    "tpg_pk2_pack_host": (None, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "tpg_pairwise": (C.c_int, [C.POINTER(Job), C.POINTER(Result)] + _ERR),
     "tpg_pairwise_multi": (C.c_int, [C.POINTER(Job), C.POINTER(Result), C.c_void_p, C.c_int32, C.c_int32] + _ERR),
     "tpg_pairwise_ctx": (C.c_int, [C.c_void_p, C.POINTER(Job), C.POINTER(Result)] + _ERR),

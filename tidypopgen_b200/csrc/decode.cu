@@ -301,6 +301,54 @@ decode_planes_k_kernel(const DecodeParams p) {
   }
 }
 
+// ------------------------------------------------------------------ pk2 input (2-bit packed)
+// Host-sourced chunks arrive packed four genotypes per byte (pack.cpp: column k at
+// k * raw_stride, individual i of the staged window in bits [2(i&3), 2(i&3)+2) of byte i>>2,
+// code 3 = missing, columns padded with 0xFF to a multiple of 16 bytes).  A lane owns 16
+// consecutive individuals = one aligned 32-bit word; a warp reads 128 contiguous bytes and
+// writes 512 contiguous bytes per plane and locus; 8 loci (8 independent loads) per warp.
+// Algorithmic traffic: 0.25 byte read + 3 bytes written per genotype.
+constexpr int kPkLociPerWarp = 8;
+
+__device__ __forceinline__ uint32_t spread4(uint32_t t) {  // 4 codes in bits [0,8) -> 4 bytes
+  return (t | (t << 6) | (t << 12) | (t << 18)) & 0x03030303u;
+}
+
+__global__ void __launch_bounds__(kDecThreads)
+decode_planes_pk2_kernel(const DecodeParams p) {
+  const int lane = threadIdx.x & 31;
+  const int nwi = (p.n_pad + 511) / 512;  // warps across the individuals
+  const int64_t gw = (int64_t(blockIdx.x) * kDecThreads + threadIdx.x) >> 5;
+  const int wi = int(gw % nwi);
+  const int l0 = int(gw / nwi) * kPkLociPerWarp;
+  const int i0 = wi * 512 + lane * 16;
+  if (l0 >= p.lc_pad || i0 >= p.n_pad) return;
+  const int64_t boff = int64_t(i0 >> 2);
+  const bool in_col = boff + 4 <= p.raw_stride;  // else: beyond the packed column = missing
+  uint32_t w[kPkLociPerWarp];
+#pragma unroll
+  for (int u = 0; u < kPkLociPerWarp; ++u) {
+    const int l = l0 + u;
+    w[u] = 0xFFFFFFFFu;
+    if (l < p.lc && in_col)
+      w[u] = __ldg(reinterpret_cast<const uint32_t*>(p.raw + int64_t(l) * p.raw_stride + boff));
+  }
+#pragma unroll
+  for (int u = 0; u < kPkLociPerWarp; ++u) {
+    const int l = l0 + u;
+    if (l >= p.lc_pad) break;
+    uint4 vd, vn, vh;
+    decode4(spread4(w[u] & 0xFFu), vd.x, vn.x, vh.x);
+    decode4(spread4((w[u] >> 8) & 0xFFu), vd.y, vn.y, vh.y);
+    decode4(spread4((w[u] >> 16) & 0xFFu), vd.z, vn.z, vh.z);
+    decode4(spread4(w[u] >> 24), vd.w, vn.w, vh.w);
+    int8_t* o = p.planes + int64_t(l) * p.n_pad + i0;
+    *reinterpret_cast<uint4*>(o) = vd;
+    *reinterpret_cast<uint4*>(o + p.plane_stride) = vn;
+    if (p.nplanes > 2) *reinterpret_cast<uint4*>(o + 2 * p.plane_stride) = vh;
+  }
+}
+
 int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E) {
   if (a.n_pad % 128 || a.lc_pad % 16 || a.n > a.n_pad || a.lc > a.lc_pad || a.n <= 0 || a.lc <= 0)
     return E.fail(TPG_ERR_ARG, "decode: bad geometry n=%lld n_pad=%lld lc=%lld lc_pad=%lld",
@@ -322,7 +370,15 @@ int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E) 
   p.planes = a.planes;
   p.plane_stride = a.plane_stride;
   p.nplanes = a.nplanes;
-  if (a.k_major) {
+  if (a.packed) {
+    if (a.k_major || a.row_idx || a.col_idx || a.row0 || a.col0 || a.raw_stride % 16 || a.plane_stride % 16 ||
+        (reinterpret_cast<uintptr_t>(a.raw) & 15) || (reinterpret_cast<uintptr_t>(a.planes) & 15))
+      return E.fail(TPG_ERR_ARG, "decode(pk2): packed chunks are MN-major, ungathered and 16-byte aligned");
+    const int64_t warps = ((a.n_pad + 511) / 512) * ((a.lc_pad + kPkLociPerWarp - 1) / kPkLociPerWarp);
+    const int64_t blocks = (warps * 32 + kDecThreads - 1) / kDecThreads;
+    if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "decode: chunk too large for one launch");
+    decode_planes_pk2_kernel<<<unsigned(blocks), kDecThreads, 0, st>>>(p);
+  } else if (a.k_major) {
     if (a.lc_pad % 128) return E.fail(TPG_ERR_ARG, "decode(K-major): lc_pad must be a multiple of 128");
     const int64_t blocks = (a.n_pad / 128) * (a.lc_pad / 128);
     if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "decode: chunk too large for one launch");

@@ -45,7 +45,7 @@ struct Ctx {
   // Grow-only buffer cache, reused across jobs (cudaMalloc / cudaMallocHost / cudaFree are
   // slow and synchronising; a job must not pay them every call).  tpg_ctx_trim() frees it.
   struct Slot { void* p = nullptr; size_t cap = 0; };
-  Slot d_raw[2], d_planes[2], h_pin[2], d_rows, d_cols, d_counts, d_out[4], d_red;
+  Slot d_raw[2], d_planes[2], h_pin[2], h_out[2], d_rows, d_cols, d_counts, d_out[4], d_red;
   std::vector<cudaEvent_t> ev_timing, ev_plain;
   // accumulate enqueued but not yet collected (tpg_pairwise defers the sync to the end of finish)
   struct ChunkEv { cudaEvent_t c0, c1, d0, d1, g0, g1; };
@@ -87,6 +87,7 @@ struct DecodeArgs {
   int64_t plane_stride;
   int nplanes;  // 2 (d, NM) or 3 (d, NM, H1)
   bool k_major;
+  bool packed = false;  // raw is a pk2 chunk (pack.cpp): raw_stride = packed bytes per column
 };
 int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E);
 
