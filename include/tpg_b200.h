@@ -197,6 +197,49 @@ int tpg_pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* devic
 int tpg_grm_from_as(int device, const double* as_in, int64_t n, double* grm_out, double* mb_out,
                     char* err, size_t errlen);
 
+/* ------------------------------------------------------------------ consumers of the matrices
+ * (SURVEY.md section 8f): what the reference does next with an n x n result, done where the
+ * matrix already is.  `matrix` / `allele_sharing` are n x n column-major doubles, on the host
+ * (on_device = 0) or already in HBM (on_device = 1, e.g. the out0 of a job run with
+ * out_on_device = 1). */
+
+/* filter_high_relatedness(matrix, kings_threshold) — R/filter_high_relatedness.R:26-145.
+ *   keep[k]  (n, original order) = 1 if individual k passes the filter (the reference's [[3]])
+ *   order[r] (n, may be NULL)    = 0-based original index visited r-th (max_abs_cor_order - 1);
+ *                                  passed_filter ([[1]]) is order[] restricted to kept individuals
+ * Returns TPG_ERR_ARG with R's message "missing value where TRUE/FALSE needed" where the
+ * reference stops on a NaN relatedness. */
+int tpg_filter_high_relatedness(int device, const double* matrix, int32_t on_device, int64_t n,
+                                double kings_threshold, int32_t* keep, int32_t* order, int64_t* n_removed,
+                                char* err, size_t errlen);
+
+/* Weir & Goudet (2017) statistics from an allele-sharing matrix:
+ *   inbreeding (n, or NULL)       indiv_inbreeding — R/indiv_inbreeding.R:56-81
+ *   fst  (npop + 1, or NULL)      pop_fst, last entry = global — R/pop_fst.R:31-76
+ *   fis  (npop + 1, or NULL)      pop_fis(method = "WG17"), last = global — R/pop_fis.R:137-191
+ *   mb_out (2, or NULL)           [mean off-diagonal allele sharing, Mb between populations]
+ * group: 0-based population of each individual (NULL = one population; fst / fis need >= 2). */
+int tpg_wg17(int device, const double* allele_sharing, int32_t on_device, int64_t n, const int32_t* group,
+             int64_t npop, double* inbreeding, double* fst, double* fis, double* mb_out, char* err,
+             size_t errlen);
+
+/* One pass over the genotype bytes THROUGH code256 (these callers use SubBMCode256Acc, unlike the
+ * pairwise kernels): per-individual heterozygote / missing counts and per-locus alternate-allele
+ * and missing counts.  Replaces gt_ind_hetero (src/gt_ind_hetero.cpp:12-42; indiv_het_obs,
+ * indiv_missingness, qc_report_indiv), alt_freq_dip_pseudo_cpp (src/alt_freq_dip_pseudo_cpp.cpp:8-58;
+ * loci_alt_freq) and the NA row of big_counts (R/loci_missingness.R:49-60).
+ *   job      source, ind_row / ind_col, device, gpu_chunk_loci (stat and sharding are ignored)
+ *   code256  the FBM's 256 decoded values; NA / <= -1 = missing; typed values must be integers
+ *   ploidy   n doubles, 2 (diploid) or 1 (pseudohaploid); NULL = all 2
+ *   het_n, na_n (n)   counts per individual               (each may be NULL)
+ *   loc0 (m)          as_counts ? n_alt : n_alt / n_valid (NA_real_ where n_valid == 0)
+ *   loc1 (m)          n_valid = sum of ploidy over typed individuals
+ *   loc_na (m)        missing individuals per locus
+ * Every sum is an exact integer (n_alt in half-allele units), so results equal the reference's. */
+int tpg_scan(const tpg_job* job, const double* code256, const double* ploidy, int32_t as_counts,
+             int32_t* het_n, int32_t* na_n, double* loc0, double* loc1, int32_t* loc_na, tpg_stats* stats,
+             char* err, size_t errlen);
+
 /* ------------------------------------------------------------------ staged interface
  * Used by the sharding layer (one process per GPU): accumulate integer counts for a
  * shard, combine them outside (NCCL all-reduce on the device buffer), then finish. */

@@ -290,3 +290,218 @@ int orc_grm(const double* as, int64_t n, double* grm, double* mb_out) {
   }
   return 0;
 }
+
+/* ================================================================== consumers of the path
+ * (SURVEY.md §8f): what the reference does with the pairwise matrices, restated literally. */
+
+/* R's mean(x) for doubles (src/main/summary.c, real_mean): long double sum / n, then one
+ * refinement pass when the first estimate is finite.  mean(numeric(0)) is NaN. */
+static double r_mean(const double* x, int64_t n) {
+  if (n == 0) return NAN;
+  long double s = 0.0L;
+  for (int64_t k = 0; k < n; ++k) s += x[k];
+  s /= (long double)n;
+  if (isfinite((double)s)) {
+    long double t = 0.0L;
+    for (int64_t k = 0; k < n; ++k) t += (x[k] - s);
+    s += t / (long double)n;
+  }
+  return (double)s;
+}
+
+/* filter_high_relatedness (R/filter_high_relatedness.R:26-145), the caret::findCorrelation
+ * style greedy filter.  mat: n x n column-major.  keep[k] (original order) = 1 if individual k
+ * passes; order[r] = 0-based original index at rank r (max_abs_cor_order - 1); deleted_rank[r]
+ * = col_to_delete in the re-ordered space.  Returns 0, or 1 where R would stop with
+ * "missing value where TRUE/FALSE needed" (a NaN relatedness reached by the comparison
+ * at :103). */
+int orc_filter_high_relatedness(const double* mat, int64_t n, double thr, int32_t* keep,
+                                int32_t* order, int32_t* deleted_rank) {
+  if (n == 1) { keep[0] = 1; order[0] = 0; deleted_rank[0] = 0; return 0; }   /* :46-53 */
+  const size_t nn = (size_t)n * (size_t)n;
+  double* A = (double*)malloc(nn * sizeof(double));
+  double* M = (double*)malloc(nn * sizeof(double));
+  double* M2 = (double*)malloc(nn * sizeof(double));
+  double* buf = (double*)malloc(nn * sizeof(double));
+  double* cm = (double*)malloc((size_t)n * sizeof(double));
+  for (size_t e = 0; e < nn; ++e) A[e] = fabs(mat[e]);                        /* :56 */
+  /* :67-72 column means with the diagonal NA, na.rm = TRUE */
+  for (int64_t j = 0; j < n; ++j) {
+    int64_t c = 0;
+    for (int64_t i = 0; i < n; ++i)
+      if (i != j && !isnan(A[i + j * n])) buf[c++] = A[i + j * n];
+    cm[j] = r_mean(buf, c);
+  }
+  /* order(cm, decreasing = TRUE): stable (radix), NaN last */
+  for (int64_t r = 0; r < n; ++r) order[r] = (int32_t)r;
+  for (int64_t a = 1; a < n; ++a) {  /* stable insertion sort */
+    const int32_t v = order[a];
+    int64_t b = a - 1;
+    while (b >= 0) {
+      const double x = cm[order[b]], y = cm[v];
+      const int before = isnan(x) ? !isnan(y) : (!isnan(y) && y > x);  /* v strictly precedes order[b] */
+      if (!before) break;
+      order[b + 1] = order[b];
+      --b;
+    }
+    order[b + 1] = v;
+  }
+  for (int64_t j = 0; j < n; ++j)                                             /* :75 */
+    for (int64_t i = 0; i < n; ++i) M[i + j * n] = A[order[i] + (int64_t)order[j] * n];
+  memcpy(M2, M, nn * sizeof(double));                                         /* :83-84 */
+  for (int64_t i = 0; i < n; ++i) M2[i + i * n] = NAN;
+  memset(deleted_rank, 0, (size_t)n * sizeof(int32_t));
+  int status = 0;
+  for (int64_t i = 0; i < n - 1 && !status; ++i) {                            /* :89 */
+    int any = 0;
+    for (size_t e = 0; e < nn && !any; ++e) any = !isnan(M2[e]) && M2[e] > thr;
+    if (!any) break;                                                          /* :90-95 */
+    if (deleted_rank[i]) continue;                                            /* :96-98 */
+    for (int64_t j = i + 1; j < n; ++j) {
+      if (deleted_rank[i] || deleted_rank[j]) continue;                       /* :100 */
+      const double v = M[i + j * n];
+      if (isnan(v)) { status = 1; break; }                                    /* if (NA) -> error */
+      if (!(v > thr)) continue;                                               /* :101 */
+      int64_t c = 0;
+      for (int64_t b = 0; b < n; ++b)
+        if (!isnan(M2[i + b * n])) buf[c++] = M2[i + b * n];
+      const double mn1 = r_mean(buf, c);                                      /* :102 */
+      c = 0;
+      for (int64_t b = 0; b < n; ++b)                                         /* matrix2[-j, ] in column-major order */
+        for (int64_t a = 0; a < n; ++a)
+          if (a != j && !isnan(M2[a + b * n])) buf[c++] = M2[a + b * n];
+      const double mn2 = r_mean(buf, c);                                      /* :103 */
+      const int64_t k = (mn1 > mn2) ? i : j;                                  /* :117-131 */
+      deleted_rank[k] = 1;
+      for (int64_t b = 0; b < n; ++b) { M2[k + b * n] = NAN; M2[b + k * n] = NAN; }
+    }
+  }
+  for (int64_t r = 0; r < n; ++r) keep[order[r]] = !deleted_rank[r];          /* :138-142 */
+  free(A); free(M); free(M2); free(buf); free(cm);
+  return status;
+}
+
+/* indiv_inbreeding (R/indiv_inbreeding.R:56-81): mii <- diag(AS); diag(AS) <- NA;
+ * mb <- mean(AS, na.rm = TRUE); ((mii * 2 - 1) - mb) / (1 - mb). */
+int orc_indiv_inbreeding(const double* as, int64_t n, double* out, double* mb_out) {
+  double* buf = (double*)malloc((size_t)n * (size_t)n * sizeof(double));
+  int64_t c = 0;
+  for (int64_t j = 0; j < n; ++j)
+    for (int64_t i = 0; i < n; ++i)
+      if (i != j && !isnan(as[i + j * n])) buf[c++] = as[i + j * n];
+  const double mb = r_mean(buf, c);
+  if (mb_out) *mb_out = mb;
+  for (int64_t i = 0; i < n; ++i) out[i] = ((as[i + i * n] * 2 - 1) - mb) / (1 - mb);
+  free(buf);
+  return 0;
+}
+
+/* Shared by pop_fst (R/pop_fst.R:31-76) and pop_fis_wg17 (R/pop_fis.R:137-191):
+ * group = 0-based population of each individual (levels in increasing order, as
+ * factor(group_indices(.x)) gives them), npop populations.
+ * Fsts[p] = mean(Mij[pop p, pop p]) with diag NA; mMij[i,j] = mean(Mij[pop i, pop j]);
+ * Mb = sum_{j<i} mMij[i,j] * 2 / (npop (npop - 1)). */
+static void wg17_means(const double* as, int64_t n, const int32_t* group, int64_t npop,
+                       double* Fsts, double* Mb_out) {
+  double* buf = (double*)malloc((size_t)n * (size_t)n * sizeof(double));
+  for (int64_t p = 0; p < npop; ++p) {
+    int64_t c = 0;
+    for (int64_t j = 0; j < n; ++j) {           /* Mij[wil, wil] in column-major order */
+      if (group[j] != p) continue;
+      for (int64_t i = 0; i < n; ++i)
+        if (group[i] == p && i != j && !isnan(as[i + j * n])) buf[c++] = as[i + j * n];
+    }
+    Fsts[p] = r_mean(buf, c);
+  }
+  double Mb = 0;
+  for (int64_t pi = 1; pi < npop; ++pi)
+    for (int64_t pj = 0; pj < pi; ++pj) {
+      int64_t c = 0;
+      for (int64_t j = 0; j < n; ++j) {         /* Mij[p1, p2]: rows pop pi, columns pop pj */
+        if (group[j] != pj) continue;
+        for (int64_t i = 0; i < n; ++i)
+          if (group[i] == pi && !isnan(as[i + j * n])) buf[c++] = as[i + j * n];
+      }
+      Mb = Mb + r_mean(buf, c);
+    }
+  *Mb_out = Mb * 2 / (double)(npop * (npop - 1));
+  free(buf);
+}
+
+/* pop_fst: fst[p] = (Fsts[p] - Mb) / (1 - Mb); fst[npop] = mean(fst, na.rm = TRUE) (global). */
+int orc_pop_fst(const double* as, int64_t n, const int32_t* group, int64_t npop, double* fst) {
+  double Mb;
+  wg17_means(as, n, group, npop, fst, &Mb);
+  double* buf = (double*)malloc((size_t)npop * sizeof(double));
+  int64_t c = 0;
+  for (int64_t p = 0; p < npop; ++p) {
+    fst[p] = (fst[p] - Mb) / (1 - Mb);
+    if (!isnan(fst[p])) buf[c++] = fst[p];
+  }
+  fst[npop] = r_mean(buf, c);
+  free(buf);
+  return 0;
+}
+
+/* pop_fis_wg17: Mii = diag(AS) * 2 - 1; Fi = (Mii[pop] - Fsts[pop]) / (1 - Fsts[pop]);
+ * fis[p] = mean(Fi, na.rm = TRUE); fis[npop] = mean(fis, na.rm = TRUE) (global). */
+int orc_pop_fis_wg17(const double* as, int64_t n, const int32_t* group, int64_t npop, double* fis) {
+  double Mb;
+  double* Fsts = (double*)malloc((size_t)npop * sizeof(double));
+  wg17_means(as, n, group, npop, Fsts, &Mb);
+  double* buf = (double*)malloc((size_t)(n > npop ? n : npop) * sizeof(double));
+  for (int64_t p = 0; p < npop; ++p) {
+    int64_t c = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      if (group[i] != p) continue;
+      const double mii = as[i + i * n] * 2 - 1;
+      const double fi = (mii - Fsts[p]) / (1 - Fsts[p]);
+      if (!isnan(fi)) buf[c++] = fi;
+    }
+    fis[p] = r_mean(buf, c);
+  }
+  int64_t c = 0;
+  for (int64_t p = 0; p < npop; ++p)
+    if (!isnan(fis[p])) buf[c++] = fis[p];
+  fis[npop] = r_mean(buf, c);
+  free(Fsts); free(buf);
+  return 0;
+}
+
+/* gt_ind_hetero (src/gt_ind_hetero.cpp:12-42) through SubBMCode256Acc: x = code256[byte];
+ * x > -1 ? (x == 1 -> het) : missing.  out: het_n[n], na_n[n]. */
+int orc_gt_ind_hetero(const uint8_t* bk, int64_t nrow, const int32_t* ind_row, int64_t n,
+                      const int32_t* ind_col, int64_t m, const double* code256,
+                      int32_t* het_n, int32_t* na_n) {
+  memset(het_n, 0, (size_t)n * sizeof(int32_t));
+  memset(na_n, 0, (size_t)n * sizeof(int32_t));
+  for (int64_t j = 0; j < m; ++j)
+    for (int64_t i = 0; i < n; ++i) {
+      const double x = code256[macc(bk, nrow, ind_row, ind_col, i, j)];
+      if (x > -1) { if (x == 1) het_n[i] += 1; }
+      else na_n[i] += 1;
+    }
+  return 0;
+}
+
+/* alt_freq_dip_pseudo_cpp (src/alt_freq_dip_pseudo_cpp.cpp:8-58): per locus
+ * n_alt = sum x / (3 - ploidy_i), n_valid = sum ploidy_i over non-missing; freq = n_alt / n_valid
+ * (NA_real_ when n_valid == 0).  out0[m] = n_alt or freq, out1[m] = n_valid. */
+int orc_alt_freq(const uint8_t* bk, int64_t nrow, const int32_t* ind_row, int64_t n,
+                 const int32_t* ind_col, int64_t m, const double* code256, const double* ploidy,
+                 int as_counts, double* out0, double* out1) {
+  double* mult = (double*)malloc((size_t)n * sizeof(double));
+  for (int64_t i = 0; i < n; ++i) mult[i] = 1 / (3 - ploidy[i]);
+  for (int64_t j = 0; j < m; ++j) {
+    double a = 0, v = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      const double x = code256[macc(bk, nrow, ind_row, ind_col, i, j)];
+      if (x > -1) { a += x * mult[i]; v += ploidy[i]; }
+    }
+    out0[j] = a; out1[j] = v;
+  }
+  if (!as_counts)
+    for (int64_t j = 0; j < m; ++j) out0[j] = out1[j] > 0 ? out0[j] / out1[j] : na_real();
+  free(mult);
+  return 0;
+}

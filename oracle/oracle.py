@@ -43,6 +43,18 @@ def lib() -> C.CDLL:
         L.orc_snp_as.argtypes = common + [p, p, p]
         L.orc_grm.restype = C.c_int
         L.orc_grm.argtypes = [p, i64, p, p]
+        L.orc_filter_high_relatedness.restype = C.c_int
+        L.orc_filter_high_relatedness.argtypes = [p, i64, C.c_double, p, p, p]
+        L.orc_indiv_inbreeding.restype = C.c_int
+        L.orc_indiv_inbreeding.argtypes = [p, i64, p, p]
+        L.orc_pop_fst.restype = C.c_int
+        L.orc_pop_fst.argtypes = [p, i64, p, i64, p]
+        L.orc_pop_fis_wg17.restype = C.c_int
+        L.orc_pop_fis_wg17.argtypes = [p, i64, p, i64, p]
+        L.orc_gt_ind_hetero.restype = C.c_int
+        L.orc_gt_ind_hetero.argtypes = [p, i64, p, i64, p, i64, p, p, p]
+        L.orc_alt_freq.restype = C.c_int
+        L.orc_alt_freq.argtypes = [p, i64, p, i64, p, i64, p, p, C.c_int, p, p]
         _lib = L
     return _lib
 
@@ -136,3 +148,71 @@ def grm_from_as(as_):
     mb = C.c_double(0)
     lib().orc_grm(a.ctypes.data, n, out.ctypes.data, C.byref(mb))
     return out, mb.value
+
+
+# ------------------------------------------------------------------ consumers
+
+def filter_high_relatedness(mat, kings_threshold):
+    """R/filter_high_relatedness.R:26-145.  Returns dict(keep [original order], order [0-based
+    visiting order], deleted_rank, error) — error=True where R stops on a NaN comparison."""
+    a = np.asfortranarray(mat, dtype=np.float64)
+    n = a.shape[0]
+    keep, order, dele = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    rc = lib().orc_filter_high_relatedness(a.ctypes.data, n, float(kings_threshold), keep.ctypes.data,
+                                           order.ctypes.data, dele.ctypes.data)
+    return {"keep": keep.astype(bool), "order": order, "deleted_rank": dele.astype(bool), "error": rc != 0}
+
+
+def indiv_inbreeding(as_):
+    """R/indiv_inbreeding.R:56-81."""
+    a = np.asfortranarray(as_, dtype=np.float64)
+    n = a.shape[0]
+    out = np.zeros(n)
+    mb = C.c_double(0)
+    lib().orc_indiv_inbreeding(a.ctypes.data, n, out.ctypes.data, C.byref(mb))
+    return out, mb.value
+
+
+def pop_fst(as_, group, npop):
+    """R/pop_fst.R:31-76: npop population values + the global one."""
+    a = np.asfortranarray(as_, dtype=np.float64)
+    g = np.ascontiguousarray(group, np.int32)
+    out = np.zeros(npop + 1)
+    lib().orc_pop_fst(a.ctypes.data, a.shape[0], g.ctypes.data, npop, out.ctypes.data)
+    return out
+
+
+def pop_fis_wg17(as_, group, npop):
+    """R/pop_fis.R:137-191."""
+    a = np.asfortranarray(as_, dtype=np.float64)
+    g = np.ascontiguousarray(group, np.int32)
+    out = np.zeros(npop + 1)
+    lib().orc_pop_fis_wg17(a.ctypes.data, a.shape[0], g.ctypes.data, npop, out.ctypes.data)
+    return out
+
+
+CODE_012 = np.array([0.0, 1.0, 2.0] + [np.nan] * 253)                       # bigsnpr::CODE_012
+CODE_IMPUTE_PRED = np.array([0.0, 1.0, 2.0, np.nan, 0.0, 1.0, 2.0] + [np.nan] * 249)  # bigsnpr::CODE_IMPUTE_PRED
+
+
+def gt_ind_hetero(bk, nrow_total, ncol_total, ind_row=None, ind_col=None, code256=CODE_012):
+    """src/gt_ind_hetero.cpp:12-42: (het_n, na_n) per individual through code256."""
+    bk, rows, cols = _prep(bk, nrow_total, ncol_total, ind_row, ind_col)
+    n, m = len(rows), len(cols)
+    code = np.ascontiguousarray(code256, np.float64)
+    het, na = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    lib().orc_gt_ind_hetero(bk.ctypes.data, nrow_total, rows.ctypes.data, n, cols.ctypes.data, m, code.ctypes.data,
+                            het.ctypes.data, na.ctypes.data)
+    return het, na
+
+
+def alt_freq(bk, nrow_total, ncol_total, ind_row=None, ind_col=None, code256=CODE_012, ploidy=None, as_counts=False):
+    """src/alt_freq_dip_pseudo_cpp.cpp:8-58: (freq or n_alt, n_valid) per locus."""
+    bk, rows, cols = _prep(bk, nrow_total, ncol_total, ind_row, ind_col)
+    n, m = len(rows), len(cols)
+    code = np.ascontiguousarray(code256, np.float64)
+    pl = np.full(n, 2.0) if ploidy is None else np.ascontiguousarray(ploidy, np.float64)
+    o0, o1 = np.zeros(m), np.zeros(m)
+    lib().orc_alt_freq(bk.ctypes.data, nrow_total, rows.ctypes.data, n, cols.ctypes.data, m, code.ctypes.data,
+                       pl.ctypes.data, int(as_counts), o0.ctypes.data, o1.ctypes.data)
+    return o0, o1

@@ -166,3 +166,53 @@ def test_na_payload():
     bk = to_bk(np.array([[0.0, np.nan], [np.nan, 1.0]]))
     a = O.snp_allele_sharing(bk, 2, 2)["as"]
     assert O.is_na(a)[0, 1] and O.is_na(a)[1, 0] and not O.is_na(a)[0, 0]
+
+
+# ------------------------------------------------------------------ consumers
+
+def test_filter_high_relatedness_reference_property(families):
+    """test_filter_high_relatedness.R: on families.bed at 0.2 only (9,10) and (11,12) are above the
+    threshold (KING binary: 0.2741 and 0.2248); one of each pair goes, and a second pass over the
+    kept individuals keeps everybody."""
+    king = O.snp_king(families["raw"], 12, 961)["king"]
+    r = O.filter_high_relatedness(king, 0.2)
+    keep = r["keep"]
+    assert not r["error"] and keep.sum() == 10 and (keep[8] ^ keep[9]) and (keep[10] ^ keep[11])
+    kept = np.flatnonzero(keep)
+    assert O.filter_high_relatedness(king[np.ix_(kept, kept)], 0.2)["keep"].all()
+    # the visiting order is by decreasing mean |kinship|, ties stable
+    a = np.abs(king)
+    np.fill_diagonal(a, np.nan)
+    cm = np.nanmean(a, axis=0)
+    assert np.all(np.diff(cm[r["order"]]) <= 1e-15)
+
+
+def test_wg17_example_values(example_gt):
+    """indiv_inbreeding = diag(hierfstat::beta.dosage) = diag(GRM) - 1 (test_indiv_inbreeding.R:42-44,
+    test_pairwise_grm.R); SURVEY G2: GRM[1,1] = 0.396947, GRM[2,2] = 1.519084, mb = 0.584126984126984."""
+    a = O.snp_allele_sharing(example_gt["raw"], 7, 6)["as"]
+    inb, mb = O.indiv_inbreeding(a)
+    g, _ = O.grm_from_as(a)
+    assert abs(mb - 0.584126984126984) < 1e-14
+    assert np.allclose(inb, np.diag(g) - 1, rtol=0, atol=1e-15)
+    assert abs(inb[0] + 0.603053) < 1e-6 and abs(inb[1] - 0.519084) < 1e-6
+    grp = np.array([0, 0, 1, 1, 0, 2, 2], np.int32)
+    fst, fis = O.pop_fst(a, grp, 3), O.pop_fis_wg17(a, grp, 3)
+    # definitional cross-check with plain numpy means
+    M = a.copy()
+    np.fill_diagonal(M, np.nan)
+    Fs = np.array([np.nanmean(M[np.ix_(grp == p, grp == p)]) for p in range(3)])
+    Mb = np.mean([np.nanmean(M[np.ix_(grp == i, grp == j)]) for i in range(3) for j in range(i)])
+    assert np.allclose(fst[:3], (Fs - Mb) / (1 - Mb), rtol=0, atol=1e-14) and abs(fst[3] - np.mean(fst[:3])) < 1e-14
+    Mii = np.diag(a) * 2 - 1
+    assert np.allclose(fis[:3], [np.mean((Mii[grp == p] - Fs[p]) / (1 - Fs[p])) for p in range(3)], rtol=0, atol=1e-14)
+
+
+def test_scans_example(example_gt):
+    """indiv_het_obs / indiv_missingness / loci_alt_freq on the 7 x 6 example (test_indiv_het_obs.R,
+    test_indiv_missingness.R: counts by rowSums on the genotype matrix)."""
+    g = EXAMPLE_7x6
+    het, na = O.gt_ind_hetero(example_gt["raw"], 7, 6)
+    assert het.tolist() == np.nansum(g == 1, axis=1).tolist() and na.tolist() == np.isnan(g).sum(axis=1).tolist()
+    f, v = O.alt_freq(example_gt["raw"], 7, 6)
+    assert np.allclose(f, np.nansum(g, axis=0) / (2 * (~np.isnan(g)).sum(axis=0))) and v.tolist() == (2 * (~np.isnan(g)).sum(axis=0)).tolist()

@@ -17,6 +17,18 @@ from .pairwise import (  # noqa: F401
     pairwise_king,
     tidy_dist_matrix,
 )
+from .consumers import (  # noqa: F401
+    filter_high_relatedness,
+    indiv_het_obs,
+    indiv_inbreeding,
+    indiv_missingness,
+    loci_alt_freq,
+    loci_missingness,
+    pop_fis,
+    pop_fst,
+    qc_report_indiv,
+    scan_counts,
+)
 from .snp import (  # noqa: F401
     block_size,
     cut_by_size,

@@ -107,6 +107,12 @@ SIGNATURES = {
     "tpg_pairwise_multi": (C.c_int, [C.POINTER(Job), C.POINTER(Result), C.c_void_p, C.c_int32, C.c_int32] + _ERR),
     "tpg_pairwise_ctx": (C.c_int, [C.c_void_p, C.POINTER(Job), C.POINTER(Result)] + _ERR),
     "tpg_grm_from_as": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_double)] + _ERR),
+    "tpg_filter_high_relatedness": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p,
+                                              C.c_void_p, C.POINTER(C.c_int64)] + _ERR),
+    "tpg_wg17": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                           C.c_void_p, C.c_void_p] + _ERR),
+    "tpg_scan": (C.c_int, [C.POINTER(Job), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                           C.c_void_p, C.c_void_p, C.POINTER(Stats)] + _ERR),
     "tpg_ctx_create": (C.c_void_p, [C.c_int] + _ERR),
     "tpg_ctx_destroy": (None, [C.c_void_p]),
     "tpg_ctx_trim": (None, [C.c_void_p]),

@@ -1,0 +1,215 @@
+"""Consumers of the pairwise matrices, run where the matrix is:
+filter_high_relatedness (the KING consumer behind qc_report_indiv) and the Weir & Goudet
+(2017) statistics built on allele sharing (indiv_inbreeding, pop_fst, pop_fis).
+
+Same names, arguments, return values and error text as the reference
+(R/filter_high_relatedness.R:26-145, R/indiv_inbreeding.R:23-95, R/pop_fst.R:31-76,
+R/pop_fis.R:52-191); the arithmetic is in libtpg_b200.so (csrc/relate.cu, csrc/wg17.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .pairwise import GenTibble, pairwise_allele_sharing
+
+
+def _square(matrix):
+    a = np.asarray(matrix)
+    if a.ndim != 2 or a.shape[0] != a.shape[1]:
+        raise ValueError("matrix should be a square matrix")
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def filter_high_relatedness(matrix, x: GenTibble | None = None, kings_threshold=None, verbose: bool = False,
+                            device: int = 0):
+    """R/filter_high_relatedness.R:26-145.  Returns [passed_filter, to_remove, keep]: the ids
+    to retain (in the order the filter visited them), the ids to remove, and a boolean per
+    individual in the original order."""
+    if kings_threshold is None:
+        raise TypeError("argument \"kings_threshold\" is missing, with no default")
+    a = _square(matrix)
+    n = a.shape[0]
+    names = getattr(matrix, "names", None)
+    if names is None:  # :33-41
+        names = [str(k + 1) for k in range(n)] if x is None else list(x.id)
+    names = list(names)
+    keep = np.zeros(n, np.int32)
+    order = np.zeros(n, np.int32)
+    removed = C.c_int64(0)
+    eb = L.errbuf()
+    rc = L.lib().tpg_filter_high_relatedness(device, a.ctypes.data, 0, n, float(kings_threshold), keep.ctypes.data,
+                                             order.ctypes.data, C.byref(removed), eb, len(eb))
+    L.check(rc, eb)
+    if verbose and removed.value == 0:
+        print(f"All correlations <= {kings_threshold}")
+    kept = keep.astype(bool)
+    passed = [names[k] for k in order if kept[k]]
+    passed_set = set(passed)
+    to_remove = [nm for nm in names if nm not in passed_set]
+    return [passed, to_remove, np.array([nm in passed_set for nm in names])]
+
+
+def _wg17(as_mat, group, npop, want_inb=False, want_fst=False, want_fis=False, device: int = 0):
+    a = _square(as_mat)
+    n = a.shape[0]
+    inb = np.zeros(n) if want_inb else None
+    fst = np.zeros(npop + 1) if want_fst else None
+    fis = np.zeros(npop + 1) if want_fis else None
+    mb = np.zeros(2)
+    g = None if group is None else np.ascontiguousarray(group, dtype=np.int32)
+    eb = L.errbuf()
+    rc = L.lib().tpg_wg17(device, a.ctypes.data, 0, n, None if g is None else g.ctypes.data, npop,
+                          None if inb is None else inb.ctypes.data, None if fst is None else fst.ctypes.data,
+                          None if fis is None else fis.ctypes.data, mb.ctypes.data, eb, len(eb))
+    L.check(rc, eb)
+    return inb, fst, fis, mb
+
+
+def _groups(x: GenTibble):
+    """factor(group_indices(.x)): populations in sorted order of their keys, 0-based codes."""
+    if x.population is None:
+        raise ValueError(".x should be a grouped gen_tibble")
+    keys = sorted(set(x.population))
+    code = {k: i for i, k in enumerate(keys)}
+    return keys, np.array([code[p] for p in x.population], dtype=np.int32)
+
+
+def indiv_inbreeding(x: GenTibble, method: str = "WG17", allele_sharing_mat=None, **kw):
+    """R/indiv_inbreeding.R:23-95.  Ungrouped: one vector; grouped: a list with one vector per
+    population, each computed from that population's own allele-sharing matrix."""
+    if method != "WG17":
+        raise ValueError("'arg' should be 'WG17'")
+    if x.population is not None:
+        if allele_sharing_mat is not None:
+            raise ValueError("allele_sharing_mat can not be provided for grouped_df objects")
+        keys, code = _groups(x)
+        out = []
+        for k in range(len(keys)):
+            sub = x[np.flatnonzero(code == k)]
+            sub.population = None
+            out.append(indiv_inbreeding(sub, method=method, **kw))
+        return out
+    if allele_sharing_mat is None:
+        allele_sharing_mat = pairwise_allele_sharing(x, as_matrix=True, **kw)
+    inb, _, _, _ = _wg17(allele_sharing_mat, None, 1, want_inb=True, device=kw.get("device", 0))
+    return inb
+
+
+def pop_fst(x: GenTibble, include_global: bool = False, allele_sharing_mat=None, **kw):
+    """R/pop_fst.R:31-76: population-specific Fst of Weir & Goudet (2017); a dict keyed by
+    population (plus "global" when asked)."""
+    keys, code = _groups(x)
+    if allele_sharing_mat is None:
+        allele_sharing_mat = pairwise_allele_sharing(x, as_matrix=True, **kw)
+    _, fst, _, _ = _wg17(allele_sharing_mat, code, len(keys), want_fst=True, device=kw.get("device", 0))
+    out = {k: fst[i] for i, k in enumerate(keys)}
+    if include_global:
+        out["global"] = fst[len(keys)]
+    return out
+
+
+def pop_fis(x: GenTibble, method: str = "WG17", include_global: bool = False, allele_sharing_mat=None, **kw):
+    """pop_fis(method = "WG17") — R/pop_fis.R:137-191 (the Nei87 method is a per-locus
+    statistic outside this path)."""
+    if method != "WG17":
+        raise NotImplementedError("only method = 'WG17' is built on the pairwise path")
+    keys, code = _groups(x)
+    if allele_sharing_mat is None:
+        allele_sharing_mat = pairwise_allele_sharing(x, as_matrix=True, **kw)
+    _, _, fis, _ = _wg17(allele_sharing_mat, code, len(keys), want_fis=True, device=kw.get("device", 0))
+    out = {k: fis[i] for i, k in enumerate(keys)}
+    if include_global:
+        out["global"] = fis[len(keys)]
+    return out
+
+
+# ------------------------------------------------------------------ O(n m) scans through code256
+
+CODE_012 = np.array([0.0, 1.0, 2.0] + [np.nan] * 253)  # bigsnpr::CODE_012, the gen_tibble default
+
+
+def scan_counts(X, ind_row=None, ind_col=None, code256=None, ploidy=None, as_counts=False, **kw):
+    """One tpg_scan call: dict(het_n, na_n, loc0, n_valid, loc_na, stats)."""
+    from . import snp
+
+    job, keep = snp.make_job(X, ind_row, ind_col, L.STAT_AS, 1, **kw)
+    n = job.n if job.ind_row else X.nrow
+    m = job.m if job.ind_col else X.ncol
+    if n <= 0 or m <= 0:
+        raise ValueError("ind.row and ind.col must not be empty")
+    code = np.ascontiguousarray(CODE_012 if code256 is None else code256, dtype=np.float64)
+    if code.shape != (256,):
+        raise ValueError("code256 must hold 256 values")
+    pl = None if ploidy is None else np.ascontiguousarray(ploidy, dtype=np.float64)
+    if pl is not None and pl.shape != (n,):
+        raise ValueError("ploidy must have one value per individual")
+    het, na = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    loc0, loc1, loc_na = np.zeros(m), np.zeros(m), np.zeros(m, np.int32)
+    st = L.Stats()
+    eb = L.errbuf()
+    rc = L.lib().tpg_scan(C.byref(job), code.ctypes.data, None if pl is None else pl.ctypes.data, int(as_counts),
+                          het.ctypes.data, na.ctypes.data, loc0.ctypes.data, loc1.ctypes.data, loc_na.ctypes.data,
+                          C.byref(st), eb, len(eb))
+    del keep
+    L.check(rc, eb)
+    return {"het_n": het, "na_n": na, "loc0": loc0, "n_valid": loc1, "loc_na": loc_na, "stats": st.as_dict()}
+
+
+def _code(x: GenTibble):
+    return x.fbm.code256 if getattr(x.fbm, "code256", None) is not None else CODE_012
+
+
+def indiv_het_obs(x: GenTibble, as_counts: bool = False, **kw):
+    """R/indiv_het_obs.R:33-65: het_n / (ncol(X) - na_n) — ncol of the FBM, as the reference
+    writes it — or the (het_n, na_n) count matrix."""
+    r = scan_counts(x.fbm, x.row_index, x.big_index, code256=_code(x), **kw)
+    if as_counts:
+        return np.stack([r["het_n"], r["na_n"]], axis=1)  # columns het_n, na_n
+    return r["het_n"] / (x.fbm.ncol - r["na_n"])
+
+
+def indiv_missingness(x: GenTibble, as_counts: bool = False, **kw):
+    """R/indiv_missingness.R:35-77: na_n (/ count_loci(x))."""
+    r = scan_counts(x.fbm, x.row_index, x.big_index, code256=_code(x), **kw)
+    return r["na_n"] if as_counts else r["na_n"] / len(x.big_index)
+
+
+def loci_alt_freq(x: GenTibble, as_counts: bool = False, ploidy=None, **kw):
+    """loci_alt_freq for diploid / pseudohaploid data (R/loci_alt_freq.R:328-379 over
+    src/alt_freq_dip_pseudo_cpp.cpp): the frequency vector, or the (n_alt, n_valid) matrix."""
+    r = scan_counts(x.fbm, x.row_index, x.big_index, code256=_code(x), ploidy=ploidy, as_counts=as_counts, **kw)
+    if as_counts:
+        return np.stack([r["loc0"], r["n_valid"]], axis=1)
+    return r["loc0"]
+
+
+def loci_missingness(x: GenTibble, as_counts: bool = False, **kw):
+    """R/loci_missingness.R:38-74: missing individuals per locus (/ number of individuals)."""
+    r = scan_counts(x.fbm, x.row_index, x.big_index, code256=_code(x), **kw)
+    return r["loc_na"] if as_counts else r["loc_na"] / len(x)
+
+
+def qc_report_indiv(x: GenTibble, kings_threshold=None, **kw):
+    """qc_report_indiv for an ungrouped diploid gen_tibble (R/qc_report_indiv.R:45-101):
+    het_obs, missingness and — with kings_threshold (a number, "first" = 0.177 or "second" =
+    0.088) — to_keep from filter_high_relatedness on the KING matrix, which is attached as
+    "king"."""
+    from .pairwise import pairwise_king
+
+    if kings_threshold is not None and not isinstance(kings_threshold, (int, float)):
+        if kings_threshold not in ("first", "second"):
+            raise ValueError("kings_threshold must be a numeric or one of 'first' or 'second'")
+        kings_threshold = 0.177 if kings_threshold == "first" else 0.088
+    n_loci = len(x.big_index)
+    r = scan_counts(x.fbm, x.row_index, x.big_index, code256=_code(x), **kw)
+    rep = {"het_obs": r["het_n"] / (n_loci - r["na_n"]), "missingness": r["na_n"] / n_loci}
+    if kings_threshold is not None:
+        king = pairwise_king(x, as_matrix=True, **kw)
+        rel = filter_high_relatedness(king, x, kings_threshold=kings_threshold, device=kw.get("device", 0))
+        rep["to_keep"] = rel[2]
+        rep["id"] = list(x.id)
+        rep["king"] = king
+    return rep

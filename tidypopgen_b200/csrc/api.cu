@@ -7,6 +7,7 @@
 // size is decoupled from R's block.size (which only survives as the allele-sharing
 // padding constant, see tpg_as_pad_count).
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <chrono>
 #include <cmath>
@@ -351,8 +352,10 @@ static int collect_accumulate(Ctx* ctx, tpg_stats* st, const Err& E) {
   return TPG_OK;
 }
 
+// scan != nullptr: the chunks feed scan_counts (through code256) instead of decode + gram; the
+// per-locus arrays of *scan are indexed by the job's locus position.
 static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_stats* st,
-                           const Err& E, bool defer = false) {
+                           const Err& E, bool defer = false, const ScanArgs* scan = nullptr) {
   const double t_begin = now_ms();
   Plan pl;
   int rc = make_plan(job, &pl, E);
@@ -364,7 +367,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   if (rc) return rc;
 
   const bool on_device = job->src_kind == TPG_SRC_DEVICE;
-  const bool k_major = (job->flags & TPG_FLAG_PLANES_K_MAJOR) != 0;
+  const bool k_major = !scan && (job->flags & TPG_FLAG_PLANES_K_MAJOR) != 0;
   const bool no_overlap = (job->flags & TPG_FLAG_NO_OVERLAP) != 0;
   const int64_t nrow = job->nrow_total;
 
@@ -379,7 +382,8 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   const bool direct_ok = !on_device && job->src_kind == TPG_SRC_HOST && pl.cols_contig && is_pinned_host(src.base);
   // 2-bit packing while staging (pack.cpp): 4x fewer bytes over PCIe.  Contiguous row window,
   // MN-major planes only; everything else keeps the raw-byte paths.
-  const bool pack_ok = !on_device && pl.rows_contig && !k_major && !(job->flags & TPG_FLAG_NO_PACK) &&
+  // (scans decode through code256 and need the whole byte)
+  const bool pack_ok = !scan && !on_device && pl.rows_contig && !k_major && !(job->flags & TPG_FLAG_NO_PACK) &&
                        !getenv("TPG_NO_PACK");
   const bool direct_only = direct_ok && !pack_ok;
   if (direct_only) { span = nrow; rlo = 0; }
@@ -430,9 +434,11 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   ctx->ev_timing_used = ctx->ev_plain_used = 0;
   const int64_t stage_per_locus = pack_ok ? pk_stride : span;  // pinned staging bytes per locus
   for (int b = 0; b < 2 && b < n_chunks; ++b) {
-    rc = ensure_slot(&ctx->d_planes[b], size_t(plane_stride) * pl.nplanes, false, "plane storage", E);
-    if (rc) return rc;
-    B.d_planes[b] = static_cast<int8_t*>(ctx->d_planes[b].p);
+    if (!scan) {
+      rc = ensure_slot(&ctx->d_planes[b], size_t(plane_stride) * pl.nplanes, false, "plane storage", E);
+      if (rc) return rc;
+      B.d_planes[b] = static_cast<int8_t*>(ctx->d_planes[b].p);
+    }
     if (!on_device) {
       rc = ensure_slot(&ctx->d_raw[b], size_t(raw_per_locus * lc) + 16, false, "raw chunk storage", E);
       if (rc) return rc;
@@ -479,6 +485,8 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   double pack_gbps = 4.0 * double(HostPool::max_threads());
   if (const char* ev = getenv("TPG_LINK_GBPS")) link_gbps = std::max(1.0, atof(ev));
   const bool hybrid = !getenv("TPG_NO_HYBRID");
+  const bool use_pread = job->src_kind == TPG_SRC_FILE && pl.cols_contig && !getenv("TPG_NO_PREAD");
+  std::atomic<int> io_err{0};
 
   for (int64_t c = 0; c < n_chunks; ++c) {
     const int b = int(c & 1);
@@ -535,13 +543,39 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
         const uint8_t* base = src.base;
         const Plan* plp = &pl;
         if (pack_ok) {
+         packed = true;
+         if (use_pread) {
+          // .bk file, contiguous columns: pread() blocks of whole columns into a per-thread buffer
+          // that stays in L2 and pack from there — a fresh mmap pays one page fault per 4 KiB.
           packed = true;
+          const int fd = src.fd;
+          const int64_t cpb = std::max<int64_t>(1, (int64_t(1) << 20) / nrow);  // columns per block
+          std::atomic<int>* bad = &io_err;
+          parallel_for(lcc, std::max<int64_t>(cpb, (int64_t(1) << 20) / span), [=](int64_t a, int64_t e) {
+            static thread_local std::vector<uint8_t> buf;
+            if (int64_t(buf.size()) < cpb * nrow) buf.resize(size_t(cpb * nrow));
+            for (int64_t k = k0 + a; k < k0 + e; k += cpb) {
+              const int64_t nc = std::min<int64_t>(cpb, k0 + e - k);
+              const int64_t off = (plp->col0 + k) * nrow;
+              int64_t got = 0;
+              while (got < nc * nrow) {
+                const ssize_t r = pread(fd, buf.data() + got, size_t(nc * nrow - got), off_t(off + got));
+                if (r <= 0) { bad->store(1); return; }
+                got += r;
+              }
+              for (int64_t j = 0; j < nc; ++j)
+                pk2_pack_column(buf.data() + j * nrow + rlo, span, stage + (k - k0 + j) * pk_stride, pk_stride);
+            }
+          });
+          if (io_err.load()) return E.fail(TPG_ERR_IO, "reading '%s' failed: %s", job->bk_path, strerror(errno));
+         } else {
           parallel_for(lcc, std::max<int64_t>(1, (int64_t(1) << 20) / span), [=](int64_t a, int64_t e) {
             for (int64_t k = k0 + a; k < k0 + e; ++k) {
               const int64_t col = plp->cols_contig ? plp->col0 + k : plp->cols0[k];
               pk2_pack_column(base + col * nrow + rlo, span, stage + (k - k0) * pk_stride, pk_stride);
             }
           });
+         }
           h2d_bytes = lcc * pk_stride;
           col_stride = pk_stride;
           const double dt = now_ms() - t0;
@@ -586,6 +620,19 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       da.row0 = packed ? 0 : (pl.rows_contig ? pl.row0 - (use_direct ? 0 : rlo) : 0);
       da.col_idx = nullptr;
       da.col0 = 0;
+    }
+    if (scan) {  // one pass over the chunk's bytes; no planes, no products
+      ScanArgs sa = *scan;
+      sa.alt2 += k0; sa.valid += k0; sa.na_l += k0;
+      TPG_CUDA_OK(cudaEventRecord(tm[c].d0, ctx->s_decode), E);
+      rc = launch_scan(ctx, da, sa, ctx->s_decode, E);
+      if (rc) return rc;
+      TPG_CUDA_OK(cudaEventRecord(tm[c].d1, ctx->s_decode), E);
+      TPG_CUDA_OK(cudaEventRecord(ev_dec_done[b], ctx->s_decode), E);
+      TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ev_dec_done[b], 0), E);
+      TPG_CUDA_OK(cudaEventRecord(tm[c].g0, ctx->s_compute), E);
+      TPG_CUDA_OK(cudaEventRecord(tm[c].g1, ctx->s_compute), E);
+      continue;
     }
     // planes[b] were last read by the gram of chunk c-2
     if (c >= 2) TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_decode, ev_gram_done[b], 0), E);
@@ -1036,6 +1083,107 @@ int tpg_grm_from_as(int device, const double* as_in, int64_t n, double* grm_out,
   }
   cudaFree(d);
   return rc;
+}
+
+int tpg_filter_high_relatedness(int device, const double* matrix, int32_t on_device, int64_t n,
+                                double kings_threshold, int32_t* keep, int32_t* order, int64_t* n_removed,
+                                char* err, size_t errlen) {
+  Err E{err, errlen};
+  int rc = TPG_OK;
+  Ctx* c = cached_ctx(device, E, &rc);
+  if (!c) return rc;
+  return run_filter_high_relatedness(c, matrix, on_device != 0, n, kings_threshold, keep, order, n_removed, E);
+}
+
+int tpg_wg17(int device, const double* allele_sharing, int32_t on_device, int64_t n, const int32_t* group,
+             int64_t npop, double* inbreeding, double* fst, double* fis, double* mb_out, char* err,
+             size_t errlen) {
+  Err E{err, errlen};
+  int rc = TPG_OK;
+  Ctx* c = cached_ctx(device, E, &rc);
+  if (!c) return rc;
+  return run_wg17(c, allele_sharing, on_device != 0, n, group, npop, inbreeding, fst, fis, mb_out, E);
+}
+
+int tpg_scan(const tpg_job* job_in, const double* code256, const double* ploidy, int32_t as_counts,
+             int32_t* het_n, int32_t* na_n, double* loc0, double* loc1, int32_t* loc_na, tpg_stats* stats,
+             char* err, size_t errlen) {
+  Err E{err, errlen};
+  if (!job_in || !code256) return E.fail(TPG_ERR_ARG, "job / code256 is NULL");
+  if (job_in->shard_mode != TPG_SHARD_NONE && job_in->shard_world > 1)
+    return E.fail(TPG_ERR_ARG, "scans run on one device");
+  tpg_job job = *job_in;
+  job.stat = TPG_STAT_AS;  // only selects the plan's bookkeeping; no planes or products are made
+  job.shard_mode = TPG_SHARD_NONE;
+  job.shard_world = 1;
+  job.shard_rank = 0;
+  const int64_t n = job.ind_row ? job.n : job.nrow_total;
+  const int64_t m = job.ind_col ? job.m : job.ncol_total;
+  if (n <= 0 || m <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row or ind.col");
+  // code256 -> byte table.  x > -1 is "typed" (src/gt_ind_hetero.cpp:29, alt_freq_dip_pseudo_cpp.cpp:37)
+  uint8_t lut[256];
+  for (int b = 0; b < 256; ++b) {
+    const double x = code256[b];
+    if (!(x > -1)) { lut[b] = 0xFF; continue; }
+    if (x != std::floor(x) || x < 0 || x > 127)
+      return E.fail(TPG_ERR_ARG, "code256[%d] = %g: this path takes integer dosages (CODE_012, CODE_IMPUTE_PRED ...), "
+                                 "not fractional ones", b, x);
+    lut[b] = uint8_t(x);
+  }
+  std::vector<uint8_t> wp(2 * n);
+  for (int64_t i = 0; i < n; ++i) {
+    const double pl = ploidy ? ploidy[i] : 2.0;
+    if (pl != 1.0 && pl != 2.0)
+      return E.fail(TPG_ERR_ARG, "ploidy[%lld] = %g: diploid (2) or pseudohaploid (1) individuals only "
+                                 "(alt_freq_dip_pseudo_cpp)", (long long)i, pl);
+    wp[i] = uint8_t(pl == 2.0 ? 2 : 1);  // 2 / (3 - ploidy)
+    wp[n + i] = uint8_t(pl);
+  }
+  int rc = TPG_OK;
+  Ctx* c = cached_ctx(job.device, E, &rc);
+  if (!c) return rc;
+  TPG_CUDA_OK(cudaSetDevice(c->device), E);
+  tpg_stats local;
+  memset(&local, 0, sizeof local);
+  tpg_stats* st = stats ? stats : &local;
+  memset(st, 0, sizeof *st);
+  const int64_t l0 = c->launches;
+  const size_t bytes = 256 + 2 * size_t(n) + 16 + sizeof(int32_t) * (2 * size_t(n) + 3 * size_t(m));
+  rc = ensure_slot(&c->d_red, bytes, false, "scan accumulators", E);
+  if (rc) return rc;
+  uint8_t* base = static_cast<uint8_t*>(c->d_red.p);
+  const size_t small = (256 + 2 * size_t(n) + 15) / 16 * 16;
+  int32_t* acc = reinterpret_cast<int32_t*>(base + small);
+  TPG_CUDA_OK(cudaMemcpyAsync(base, lut, 256, cudaMemcpyHostToDevice, c->s_compute), E);
+  TPG_CUDA_OK(cudaMemcpyAsync(base + 256, wp.data(), 2 * size_t(n), cudaMemcpyHostToDevice, c->s_compute), E);
+  TPG_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(int32_t) * (2 * size_t(n) + 3 * size_t(m)), c->s_compute), E);
+  c->launches++;
+  ScanArgs sa;
+  sa.lut = base; sa.weight = base + 256; sa.ploidy = base + 256 + n;
+  sa.het_n = acc; sa.na_n = acc + n; sa.alt2 = acc + 2 * n; sa.valid = sa.alt2 + m; sa.na_l = sa.valid + m;
+  rc = accumulate_impl(c, &job, nullptr, st, E, /*defer=*/false, &sa);
+  if (rc) return rc;
+  std::vector<int32_t> h(2 * size_t(n) + 3 * size_t(m));
+  TPG_CUDA_OK(cudaMemcpyAsync(h.data(), acc, sizeof(int32_t) * h.size(), cudaMemcpyDeviceToHost, c->s_compute), E);
+  TPG_CUDA_OK(cudaStreamSynchronize(c->s_compute), E);
+  st->bytes_d2h += int64_t(sizeof(int32_t) * h.size());
+  if (het_n) memcpy(het_n, h.data(), sizeof(int32_t) * size_t(n));
+  if (na_n) memcpy(na_n, h.data() + n, sizeof(int32_t) * size_t(n));
+  const int32_t* alt2 = h.data() + 2 * n;
+  const int32_t* valid = alt2 + m;
+  const int32_t* nal = valid + m;
+  if (loc_na) memcpy(loc_na, nal, sizeof(int32_t) * size_t(m));
+  for (int64_t l = 0; l < m; ++l) {
+    const double a = double(alt2[l]) * 0.5, v = double(valid[l]);  // exact: half-allele units
+    if (loc1) loc1[l] = v;
+    if (loc0) {
+      if (as_counts) loc0[l] = a;
+      else if (v > 0) loc0[l] = a / v;
+      else { const uint64_t na_bits = 0x7FF00000000007A2ull; memcpy(&loc0[l], &na_bits, 8); }  // NA_real_
+    }
+  }
+  st->n_launches = c->launches - l0;
+  return TPG_OK;
 }
 
 int tpg_decode_planes(tpg_ctx* h, const uint8_t* d_raw, int64_t raw_bytes, int64_t raw_stride,

@@ -349,6 +349,129 @@ decode_planes_pk2_kernel(const DecodeParams p) {
   }
 }
 
+// ------------------------------------------------------------------ scans through code256
+// The O(n m) statistics that share this kernel's access pattern:
+//   gt_ind_hetero            src/gt_ind_hetero.cpp:12-42           het_n, na_n per individual
+//   alt_freq_dip_pseudo_cpp  src/alt_freq_dip_pseudo_cpp.cpp:8-58  n_alt, n_valid per locus
+//   big_counts' NA row       R/loci_missingness.R:49-60            n_na per locus
+// Unlike the pairwise kernels these DO decode through code256 (SubBMCode256Acc): the host turns
+// the 256 doubles into a byte table (0xFF = missing, else the integer dosage) and per-individual
+// weights (2 / (3 - ploidy): 2 for diploids, 1 for pseudohaploids), so every sum is an exact
+// integer — n_alt is kept in half-allele units.  One pass, 1 byte read per genotype.
+constexpr int kScanLoci = 256;  // loci per CTA (16 rounds of 16)
+
+struct ScanParams {
+  const uint8_t* lut;     // 256 entries
+  const uint8_t* weight;  // n: 2 / (3 - ploidy)
+  const uint8_t* ploidy;  // n
+  int32_t* het_n;         // n   (atomic)
+  int32_t* na_n;          // n   (atomic)
+  int32_t* alt2;          // this chunk's loci (atomic): sum dosage * weight
+  int32_t* valid;         //                           sum ploidy over non-missing
+  int32_t* na_l;          //                           missing count
+};
+
+__global__ void __launch_bounds__(kDecThreads)
+scan_counts_kernel(const DecodeParams p, const ScanParams sp) {
+  __shared__ uint8_t lut[256];
+  __shared__ unsigned long long part[kDecThreads / 32][16];
+  lut[threadIdx.x] = sp.lut[threadIdx.x];  // kDecThreads == 256
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nib = (p.n + kDecThreads * 4 - 1) / (kDecThreads * 4);
+  const int ib = blockIdx.x % nib, lb = blockIdx.x / nib;
+  const int i0 = (ib * kDecThreads + threadIdx.x) * 4;
+  const RowSel rs = make_rowsel(p, i0);
+  const int nv = min(max(p.n - i0, 0), 4);
+  uint32_t wgt[4], plo[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    wgt[b] = b < nv ? sp.weight[i0 + b] : 0u;
+    plo[b] = b < nv ? sp.ploidy[i0 + b] : 0u;
+  }
+  __syncthreads();
+  int het[4] = {0, 0, 0, 0}, na[4] = {0, 0, 0, 0};
+  const int lbase = lb * kScanLoci;
+  for (int round = 0; round < kScanLoci / 16; ++round) {
+    const int l0 = lbase + round * 16;
+    if (l0 >= p.lc) break;  // uniform over the CTA
+    const bool safe = block_is_safe(p, l0, 16, ib * kDecThreads * 4, (ib + 1) * kDecThreads * 4);
+    uint32_t g[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int l = l0 + u;
+      g[u] = 0x03030303u;
+      if (l < p.lc) {
+        const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
+        g[u] = safe ? load4<true>(p, rs, col, lane) : load4<false>(p, rs, col, lane);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      uint32_t alt = 0, val = 0, nal = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t c = lut[(g[u] >> (8 * b)) & 0xFFu];
+        const bool ok = b < nv, miss = c == 0xFFu;
+        if (ok && miss) { ++na[b]; ++nal; }
+        if (ok && !miss) { alt += c * wgt[b]; val += plo[b]; het[b] += (c == 1u); }
+      }
+      // alt [0,32) | valid [32,48) | na [48,64): one 64-bit butterfly per locus and warp
+      unsigned long long v = (unsigned long long)alt | ((unsigned long long)val << 32) | ((unsigned long long)nal << 48);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+      if (lane == 0) part[warp][u] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && l0 + int(threadIdx.x) < p.lc) {
+      unsigned long long alt = 0, val = 0, nal = 0;
+#pragma unroll
+      for (int w = 0; w < kDecThreads / 32; ++w) {
+        const unsigned long long v = part[w][threadIdx.x];
+        alt += v & 0xFFFFFFFFull; val += (v >> 32) & 0xFFFFull; nal += v >> 48;
+      }
+      const int l = l0 + threadIdx.x;
+      if (nib == 1) { sp.alt2[l] += int32_t(alt); sp.valid[l] += int32_t(val); sp.na_l[l] += int32_t(nal); }
+      else { atomicAdd(sp.alt2 + l, int32_t(alt)); atomicAdd(sp.valid + l, int32_t(val)); atomicAdd(sp.na_l + l, int32_t(nal)); }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+    if (b < nv) {
+      if (het[b]) atomicAdd(sp.het_n + i0 + b, het[b]);
+      if (na[b]) atomicAdd(sp.na_n + i0 + b, na[b]);
+    }
+}
+
+int launch_scan(Ctx* ctx, const DecodeArgs& a, const ScanArgs& s, cudaStream_t st, const Err& E) {
+  if (a.n <= 0 || a.lc <= 0 || a.n > INT32_MAX / 2 || a.lc > INT32_MAX / 2)
+    return E.fail(TPG_ERR_ARG, "scan: bad geometry n=%lld lc=%lld", (long long)a.n, (long long)a.lc);
+  DecodeParams p;
+  p.raw = a.raw;
+  p.raw_end = a.raw + a.raw_bytes;
+  p.raw_stride = a.raw_stride;
+  p.row_idx = a.row_idx;
+  p.row0 = a.row0;
+  p.col_idx = a.col_idx;
+  p.col0 = a.col0;
+  p.n = int(a.n);
+  p.n_pad = int(a.n);
+  p.lc = int(a.lc);
+  p.lc_pad = int(a.lc);
+  p.planes = nullptr;
+  p.plane_stride = 0;
+  p.nplanes = 0;
+  ScanParams sp;
+  sp.lut = s.lut; sp.weight = s.weight; sp.ploidy = s.ploidy;
+  sp.het_n = s.het_n; sp.na_n = s.na_n; sp.alt2 = s.alt2; sp.valid = s.valid; sp.na_l = s.na_l;
+  const int64_t blocks = ((a.n + kDecThreads * 4 - 1) / (kDecThreads * 4)) * ((a.lc + kScanLoci - 1) / kScanLoci);
+  if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "scan: chunk too large for one launch");
+  scan_counts_kernel<<<unsigned(blocks), kDecThreads, 0, st>>>(p, sp);
+  TPG_CUDA_OK(cudaGetLastError(), E);
+  ctx->launches++;
+  return TPG_OK;
+}
+
 int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E) {
   if (a.n_pad % 128 || a.lc_pad % 16 || a.n > a.n_pad || a.lc > a.lc_pad || a.n <= 0 || a.lc <= 0)
     return E.fail(TPG_ERR_ARG, "decode: bad geometry n=%lld n_pad=%lld lc=%lld lc_pad=%lld",

@@ -91,6 +91,20 @@ struct DecodeArgs {
 };
 int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E);
 
+// One-pass scan of a raw chunk through code256 (decode.cu): device pointers; the per-locus
+// arrays are already offset to the chunk's first locus.  Uses a.raw / row / col addressing only.
+struct ScanArgs {
+  const uint8_t* lut;
+  const uint8_t* weight;
+  const uint8_t* ploidy;
+  int32_t* het_n;
+  int32_t* na_n;
+  int32_t* alt2;
+  int32_t* valid;
+  int32_t* na_l;
+};
+int launch_scan(Ctx* ctx, const DecodeArgs& a, const ScanArgs& s, cudaStream_t st, const Err& E);
+
 struct GramArgs {
   const int8_t* planes;
   int64_t plane_stride;
@@ -137,6 +151,12 @@ int launch_grm(Ctx* ctx, const double* d_as, int64_t n, double* d_grm, double* m
 
 int launch_synth(Ctx* ctx, uint8_t* d_raw, int64_t nrow, int64_t ncol, int64_t col_offset,
                  uint64_t seed, double missing_rate, int mode, cudaStream_t st, const Err& E);
+
+// ---- consumers of the pairwise matrices (relate.cu, wg17.cu)
+int run_filter_high_relatedness(Ctx* ctx, const double* mat, bool on_device, int64_t n, double thr, int32_t* keep,
+                                int32_t* order, int64_t* n_removed, const Err& E);
+int run_wg17(Ctx* ctx, const double* as_in, bool on_device, int64_t n, const int32_t* group, int64_t npop,
+             double* inbreeding, double* fst, double* fis, double* mb_out, const Err& E);
 
 int check_err_flag(Ctx* ctx, const Err& E);
 int launch_add_counts(Ctx* ctx, int32_t* a, const int32_t* b, int64_t elems, cudaStream_t st, const Err& E);
