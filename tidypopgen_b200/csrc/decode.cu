@@ -411,7 +411,7 @@ scan_counts_kernel(const DecodeParams p, const ScanParams sp) {
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const uint32_t c = lut[(g[u] >> (8 * b)) & 0xFFu];
-        const bool ok = b < nv, miss = c == 0xFFu;
+        const bool ok = b < nv && l0 + u < p.lc, miss = c == 0xFFu;  // padding loci of the last round count nothing
         if (ok && miss) { ++na[b]; ++nal; }
         if (ok && !miss) { alt += c * wgt[b]; val += plo[b]; het[b] += (c == 1u); }
       }
