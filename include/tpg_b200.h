@@ -213,6 +213,13 @@ int tpg_filter_high_relatedness(int device, const double* matrix, int32_t on_dev
                                 double kings_threshold, int32_t* keep, int32_t* order, int64_t* n_removed,
                                 char* err, size_t errlen);
 
+/* qc_report_indiv(kings_threshold = ...) without shipping the matrix (R/qc_report_indiv.R:85-99):
+ * runs the KING job of `job` (stat is forced to TPG_STAT_KING), keeps the n x n matrix in HBM,
+ * filters it there and returns keep / order as tpg_filter_high_relatedness does.  king_host
+ * (n x n, may be NULL) receives the kinship matrix only if the caller wants it. */
+int tpg_king_filter(const tpg_job* job, double kings_threshold, int32_t* keep, int32_t* order,
+                    int64_t* n_removed, double* king_host, tpg_stats* stats, char* err, size_t errlen);
+
 /* Weir & Goudet (2017) statistics from an allele-sharing matrix:
  *   inbreeding (n, or NULL)       indiv_inbreeding — R/indiv_inbreeding.R:56-81
  *   fst  (npop + 1, or NULL)      pop_fst, last entry = global — R/pop_fst.R:31-76
@@ -239,6 +246,12 @@ int tpg_wg17(int device, const double* allele_sharing, int32_t on_device, int64_
 int tpg_scan(const tpg_job* job, const double* code256, const double* ploidy, int32_t as_counts,
              int32_t* het_n, int32_t* na_n, double* loc0, double* loc1, int32_t* loc_na, tpg_stats* stats,
              char* err, size_t errlen);
+
+/* The same statistics straight from the genotypes: runs the allele-sharing job of `job` (stat is
+ * forced to TPG_STAT_AS, block_size / pad_quirk honoured), keeps the n x n matrix in HBM and
+ * reduces it there.  as_host (n x n, may be NULL) receives the matrix only if wanted. */
+int tpg_as_wg17(const tpg_job* job, const int32_t* group, int64_t npop, double* inbreeding, double* fst,
+                double* fis, double* mb_out, double* as_host, tpg_stats* stats, char* err, size_t errlen);
 
 /* ------------------------------------------------------------------ staged interface
  * Used by the sharding layer (one process per GPU): accumulate integer counts for a

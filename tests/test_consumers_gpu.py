@@ -234,5 +234,9 @@ def test_qc_report_indiv_families(families):
     assert same(rep["het_obs"], het / (961 - na)) and same(rep["missingness"], na / 961)
     king = O.snp_king(families["raw"], 12, 961, block_size_=O.block_size(12))["king"]
     assert np.array_equal(rep["to_keep"], O.filter_high_relatedness(king, 0.2)["keep"]) and rep["to_keep"].sum() == 10
+    assert same(rep["king"], king)
+    rel, k2 = tpg.king_filter(gt, 0.2)            # matrix never leaves HBM
+    assert k2 is None and np.array_equal(rel[2], rep["to_keep"])
+    assert rel[0] == tpg.filter_high_relatedness(king, gt, kings_threshold=0.2)[0]
     assert "to_keep" not in tpg.qc_report_indiv(gt)
     assert tpg.qc_report_indiv(gt, kings_threshold="first")["to_keep"].sum() == 10

@@ -22,6 +22,7 @@ from .consumers import (  # noqa: F401
     indiv_het_obs,
     indiv_inbreeding,
     indiv_missingness,
+    king_filter,
     loci_alt_freq,
     loci_missingness,
     pop_fis,

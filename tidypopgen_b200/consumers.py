@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from .pairwise import GenTibble, pairwise_allele_sharing
+from .pairwise import GenTibble
 
 
 def _square(matrix):
@@ -52,18 +52,58 @@ def filter_high_relatedness(matrix, x: GenTibble | None = None, kings_threshold=
     return [passed, to_remove, np.array([nm in passed_set for nm in names])]
 
 
-def _wg17(as_mat, group, npop, want_inb=False, want_fst=False, want_fis=False, device: int = 0):
-    a = _square(as_mat)
-    n = a.shape[0]
+def king_filter(x: GenTibble, kings_threshold, return_king: bool = False, block_size: int | None = None, **kw):
+    """pairwise_king + filter_high_relatedness in one native call; the n x n matrix stays in HBM
+    (returned only when return_king=True).  Returns ([passed, to_remove, keep], king or None)."""
+    from . import snp
+
+    if block_size is None:
+        block_size = snp.block_size(len(x))
+    job, keepalive = snp.make_job(x.fbm, x.row_index, x.big_index, L.STAT_KING, block_size, **kw)
+    n = len(x)
+    keep, order = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    removed = C.c_int64(0)
+    king = np.zeros((n, n), np.float64, order="F") if return_king else None
+    st = L.Stats()
+    eb = L.errbuf()
+    rc = L.lib().tpg_king_filter(C.byref(job), float(kings_threshold), keep.ctypes.data, order.ctypes.data,
+                                 C.byref(removed), None if king is None else king.ctypes.data, C.byref(st), eb, len(eb))
+    del keepalive
+    L.check(rc, eb)
+    snp.last_stats = st.as_dict()
+    kept = keep.astype(bool)
+    names = list(x.id)
+    passed = [names[k] for k in order if kept[k]]
+    return [passed, [nm for k, nm in enumerate(names) if not kept[k]], kept], king
+
+
+def _wg17(as_mat, group, npop, want_inb=False, want_fst=False, want_fis=False, device: int = 0, x: GenTibble | None = None,
+          block_size: int | None = None, **kw):
+    """tpg_wg17 on a given allele-sharing matrix, or — as_mat None — tpg_as_wg17: the matrix is
+    computed from x's genotypes and reduced without leaving HBM."""
+    n = len(x) if as_mat is None else np.asarray(as_mat).shape[0]
     inb = np.zeros(n) if want_inb else None
     fst = np.zeros(npop + 1) if want_fst else None
     fis = np.zeros(npop + 1) if want_fis else None
     mb = np.zeros(2)
     g = None if group is None else np.ascontiguousarray(group, dtype=np.int32)
+    ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
     eb = L.errbuf()
-    rc = L.lib().tpg_wg17(device, a.ctypes.data, 0, n, None if g is None else g.ctypes.data, npop,
-                          None if inb is None else inb.ctypes.data, None if fst is None else fst.ctypes.data,
-                          None if fis is None else fis.ctypes.data, mb.ctypes.data, eb, len(eb))
+    if as_mat is None:
+        from . import snp
+
+        if block_size is None:
+            block_size = snp.block_size(len(x))
+        job, keepalive = snp.make_job(x.fbm, x.row_index, x.big_index, L.STAT_AS, block_size, device=device, **kw)
+        st = L.Stats()
+        rc = L.lib().tpg_as_wg17(C.byref(job), ptr(g), npop, ptr(inb), ptr(fst), ptr(fis), mb.ctypes.data, None,
+                                 C.byref(st), eb, len(eb))
+        del keepalive
+        snp.last_stats = st.as_dict()
+    else:
+        a = _square(as_mat)
+        rc = L.lib().tpg_wg17(device, a.ctypes.data, 0, n, ptr(g), npop, ptr(inb), ptr(fst), ptr(fis), mb.ctypes.data,
+                              eb, len(eb))
     L.check(rc, eb)
     return inb, fst, fis, mb
 
@@ -92,9 +132,7 @@ def indiv_inbreeding(x: GenTibble, method: str = "WG17", allele_sharing_mat=None
             sub.population = None
             out.append(indiv_inbreeding(sub, method=method, **kw))
         return out
-    if allele_sharing_mat is None:
-        allele_sharing_mat = pairwise_allele_sharing(x, as_matrix=True, **kw)
-    inb, _, _, _ = _wg17(allele_sharing_mat, None, 1, want_inb=True, device=kw.get("device", 0))
+    inb, _, _, _ = _wg17(allele_sharing_mat, None, 1, want_inb=True, x=x, **kw)
     return inb
 
 
@@ -102,9 +140,7 @@ def pop_fst(x: GenTibble, include_global: bool = False, allele_sharing_mat=None,
     """R/pop_fst.R:31-76: population-specific Fst of Weir & Goudet (2017); a dict keyed by
     population (plus "global" when asked)."""
     keys, code = _groups(x)
-    if allele_sharing_mat is None:
-        allele_sharing_mat = pairwise_allele_sharing(x, as_matrix=True, **kw)
-    _, fst, _, _ = _wg17(allele_sharing_mat, code, len(keys), want_fst=True, device=kw.get("device", 0))
+    _, fst, _, _ = _wg17(allele_sharing_mat, code, len(keys), want_fst=True, x=x, **kw)
     out = {k: fst[i] for i, k in enumerate(keys)}
     if include_global:
         out["global"] = fst[len(keys)]
@@ -117,9 +153,7 @@ def pop_fis(x: GenTibble, method: str = "WG17", include_global: bool = False, al
     if method != "WG17":
         raise NotImplementedError("only method = 'WG17' is built on the pairwise path")
     keys, code = _groups(x)
-    if allele_sharing_mat is None:
-        allele_sharing_mat = pairwise_allele_sharing(x, as_matrix=True, **kw)
-    _, _, fis, _ = _wg17(allele_sharing_mat, code, len(keys), want_fis=True, device=kw.get("device", 0))
+    _, _, fis, _ = _wg17(allele_sharing_mat, code, len(keys), want_fis=True, x=x, **kw)
     out = {k: fis[i] for i, k in enumerate(keys)}
     if include_global:
         out["global"] = fis[len(keys)]
@@ -197,8 +231,6 @@ def qc_report_indiv(x: GenTibble, kings_threshold=None, **kw):
     het_obs, missingness and — with kings_threshold (a number, "first" = 0.177 or "second" =
     0.088) — to_keep from filter_high_relatedness on the KING matrix, which is attached as
     "king"."""
-    from .pairwise import pairwise_king
-
     if kings_threshold is not None and not isinstance(kings_threshold, (int, float)):
         if kings_threshold not in ("first", "second"):
             raise ValueError("kings_threshold must be a numeric or one of 'first' or 'second'")
@@ -207,8 +239,8 @@ def qc_report_indiv(x: GenTibble, kings_threshold=None, **kw):
     r = scan_counts(x.fbm, x.row_index, x.big_index, code256=_code(x), **kw)
     rep = {"het_obs": r["het_n"] / (n_loci - r["na_n"]), "missingness": r["na_n"] / n_loci}
     if kings_threshold is not None:
-        king = pairwise_king(x, as_matrix=True, **kw)
-        rel = filter_high_relatedness(king, x, kings_threshold=kings_threshold, device=kw.get("device", 0))
+        # one native call: KING is computed, filtered in HBM and shipped once for attr(to_keep, "king")
+        rel, king = king_filter(x, kings_threshold, return_king=True, **kw)
         rep["to_keep"] = rel[2]
         rep["id"] = list(x.id)
         rep["king"] = king

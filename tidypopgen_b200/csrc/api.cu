@@ -678,6 +678,50 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   return TPG_OK;
 }
 
+// D2H of up to `count` result buffers of `bytes` each (null host pointers are skipped), enqueued
+// on the compute stream: through two pinned bounce buffers, the pieces copied into the caller's
+// (pageable, usually untouched) memory by the worker pool while the next piece is in flight — a
+// cudaMemcpy straight into pageable memory runs at ~3 GB/s, first-touch faults included.
+static int results_to_host(Ctx* ctx, const void* const* dev, void* const* host, int count, size_t bytes,
+                           int64_t* bytes_d2h, const Err& E) {
+  const size_t kPiece = size_t(32) << 20;
+  const size_t piece = std::min(bytes, kPiece);
+  int rc = TPG_OK;
+  for (int b = 0; b < 2 && rc == TPG_OK; ++b)
+    rc = ensure_slot(&ctx->h_out[b], piece, true, "pinned result staging", E);
+  if (rc) return rc;
+  struct Piece { uint8_t* dst; const uint8_t* from; size_t len; cudaEvent_t ev; };
+  Piece prev{nullptr, nullptr, 0, nullptr};
+  auto drain = [&](const Piece& q) {
+    if (!q.dst) return cudaSuccess;
+    cudaError_t e = cudaEventSynchronize(q.ev);
+    if (e != cudaSuccess) return e;
+    uint8_t* dst = q.dst;
+    const uint8_t* from = q.from;
+    parallel_for(int64_t(q.len), int64_t(256) << 10, [=](int64_t a, int64_t z) { memcpy(dst + a, from + a, size_t(z - a)); });
+    return cudaSuccess;
+  };
+  cudaEvent_t evp[2] = {pooled_event(ctx, false), pooled_event(ctx, false)};
+  int64_t idx = 0;
+  for (int o = 0; o < count && rc == TPG_OK; ++o) {
+    if (!host[o]) continue;
+    for (size_t off = 0; off < bytes && rc == TPG_OK; off += piece, ++idx) {
+      const int b = int(idx & 1);
+      const size_t len = std::min(piece, bytes - off);
+      uint8_t* bounce = static_cast<uint8_t*>(ctx->h_out[b].p);
+      cudaError_t e = cudaMemcpyAsync(bounce, static_cast<const uint8_t*>(dev[o]) + off, len,
+                                      cudaMemcpyDeviceToHost, ctx->s_compute);
+      if (e == cudaSuccess) e = cudaEventRecord(evp[b], ctx->s_compute);
+      if (e == cudaSuccess) e = drain(prev);  // the other bounce buffer is free again after this
+      if (e != cudaSuccess) rc = E.fail(TPG_ERR_CUDA, "D2H of result failed: %s", cudaGetErrorString(e));
+      prev = Piece{static_cast<uint8_t*>(host[o]) + off, bounce, len, evp[b]};
+      if (bytes_d2h) *bytes_d2h += int64_t(len);
+    }
+  }
+  if (rc == TPG_OK && drain(prev) != cudaSuccess) rc = E.fail(TPG_ERR_CUDA, "D2H of result failed");
+  return rc;
+}
+
 static int finish_impl(Ctx* ctx, const tpg_job* job, const int32_t* d_counts, tpg_result* res,
                        const Err& E) {
   if (!res || !res->out0) return E.fail(TPG_ERR_ARG, "result / out0 is NULL");
@@ -719,46 +763,10 @@ static int finish_impl(Ctx* ctx, const tpg_job* job, const int32_t* d_counts, tp
   cudaEventRecord(e0, ctx->s_compute);
   int rc = launch_finish(ctx, fa, ctx->s_compute, E);
   cudaEventRecord(e1, ctx->s_compute);
-  double ms_host_copy = 0;
   if (rc == TPG_OK && !res->out_on_device) {
-    // D2H through two pinned bounce buffers, the pieces copied into the caller's (pageable,
-    // usually untouched) memory by the worker pool while the next piece is in flight — a
-    // cudaMemcpy straight into pageable memory runs at ~3 GB/s, first-touch faults included.
-    const size_t kPiece = size_t(32) << 20;
-    const size_t piece = std::min(bytes, kPiece);
-    for (int b = 0; b < 2 && rc == TPG_OK; ++b)
-      rc = ensure_slot(&ctx->h_out[b], piece, true, "pinned result staging", E);
-    struct Piece { uint8_t* dst; const uint8_t* from; size_t len; cudaEvent_t ev; };
-    Piece prev{nullptr, nullptr, 0, nullptr};
-    auto drain = [&](const Piece& q) {
-      if (!q.dst) return cudaSuccess;
-      cudaError_t e = cudaEventSynchronize(q.ev);
-      if (e != cudaSuccess) return e;
-      const double t0 = now_ms();
-      uint8_t* dst = q.dst;
-      const uint8_t* from = q.from;
-      parallel_for(int64_t(q.len), int64_t(256) << 10, [=](int64_t a, int64_t z) { memcpy(dst + a, from + a, size_t(z - a)); });
-      ms_host_copy += now_ms() - t0;
-      return cudaSuccess;
-    };
-    cudaEvent_t evp[2] = {pooled_event(ctx, false), pooled_event(ctx, false)};
-    int64_t idx = 0;
-    for (int o = 0; o < 4 && rc == TPG_OK; ++o) {
-      if (!host[o]) continue;
-      for (size_t off = 0; off < bytes && rc == TPG_OK; off += piece, ++idx) {
-        const int b = int(idx & 1);
-        const size_t len = std::min(piece, bytes - off);
-        uint8_t* bounce = static_cast<uint8_t*>(ctx->h_out[b].p);
-        cudaError_t e = cudaMemcpyAsync(bounce, reinterpret_cast<const uint8_t*>(dev[o]) + off, len,
-                                        cudaMemcpyDeviceToHost, ctx->s_compute);
-        if (e == cudaSuccess) e = cudaEventRecord(evp[b], ctx->s_compute);
-        if (e == cudaSuccess) e = drain(prev);  // the other bounce buffer is free again after this
-        if (e != cudaSuccess) rc = E.fail(TPG_ERR_CUDA, "D2H of result failed: %s", cudaGetErrorString(e));
-        prev = Piece{reinterpret_cast<uint8_t*>(host[o]) + off, bounce, len, evp[b]};
-        res->stats.bytes_d2h += int64_t(len);
-      }
-    }
-    if (rc == TPG_OK && drain(prev) != cudaSuccess) rc = E.fail(TPG_ERR_CUDA, "D2H of result failed");
+    const void* dv[4] = {dev[0], dev[1], dev[2], dev[3]};
+    void* hv[4] = {host[0], host[1], host[2], host[3]};
+    rc = results_to_host(ctx, dv, hv, 4, bytes, &res->stats.bytes_d2h, E);
   }
   cudaEventRecord(e2, ctx->s_compute);
   if (ctx->pending) {  // the accumulate of the same job was enqueued without a sync
@@ -1093,6 +1101,72 @@ int tpg_filter_high_relatedness(int device, const double* matrix, int32_t on_dev
   Ctx* c = cached_ctx(device, E, &rc);
   if (!c) return rc;
   return run_filter_high_relatedness(c, matrix, on_device != 0, n, kings_threshold, keep, order, n_removed, E);
+}
+
+int tpg_king_filter(const tpg_job* job_in, double kings_threshold, int32_t* keep, int32_t* order,
+                    int64_t* n_removed, double* king_host, tpg_stats* stats, char* err, size_t errlen) {
+  Err E{err, errlen};
+  if (!job_in || !keep) return E.fail(TPG_ERR_ARG, "job / keep is NULL");
+  tpg_job job = *job_in;
+  job.stat = TPG_STAT_KING;
+  int rc = TPG_OK;
+  Ctx* c = cached_ctx(job.device, E, &rc);
+  if (!c) return rc;
+  const int64_t n = job.ind_row ? job.n : job.nrow_total;
+  if (n <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row");
+  TPG_CUDA_OK(cudaSetDevice(c->device), E);
+  const size_t bytes = sizeof(double) * size_t(n) * size_t(n);
+  rc = ensure_slot(&c->d_out[0], bytes, false, "KING matrix", E);
+  if (rc) return rc;
+  tpg_result res;
+  memset(&res, 0, sizeof res);
+  res.out0 = static_cast<double*>(c->d_out[0].p);
+  res.out_on_device = 1;
+  rc = pairwise_on(c, &job, &res, E);   // KING stays in HBM
+  if (rc) return rc;
+  const double t0 = now_ms();
+  rc = run_filter_high_relatedness(c, res.out0, true, n, kings_threshold, keep, order, n_removed, E);
+  res.stats.ms_finish += now_ms() - t0;  // the filter is accounted with the finishing stage
+  if (rc == TPG_OK && king_host) {
+    const void* dv[1] = {res.out0};
+    void* hv[1] = {king_host};
+    rc = results_to_host(c, dv, hv, 1, bytes, &res.stats.bytes_d2h, E);
+  }
+  if (stats) *stats = res.stats;
+  return rc;
+}
+
+int tpg_as_wg17(const tpg_job* job_in, const int32_t* group, int64_t npop, double* inbreeding, double* fst,
+                double* fis, double* mb_out, double* as_host, tpg_stats* stats, char* err, size_t errlen) {
+  Err E{err, errlen};
+  if (!job_in) return E.fail(TPG_ERR_ARG, "job is NULL");
+  tpg_job job = *job_in;
+  job.stat = TPG_STAT_AS;
+  int rc = TPG_OK;
+  Ctx* c = cached_ctx(job.device, E, &rc);
+  if (!c) return rc;
+  const int64_t n = job.ind_row ? job.n : job.nrow_total;
+  if (n <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row");
+  TPG_CUDA_OK(cudaSetDevice(c->device), E);
+  const size_t bytes = sizeof(double) * size_t(n) * size_t(n);
+  rc = ensure_slot(&c->d_out[0], bytes, false, "allele-sharing matrix", E);
+  if (rc) return rc;
+  tpg_result res;
+  memset(&res, 0, sizeof res);
+  res.out0 = static_cast<double*>(c->d_out[0].p);
+  res.out_on_device = 1;
+  rc = pairwise_on(c, &job, &res, E);   // allele sharing stays in HBM
+  if (rc) return rc;
+  const double t0 = now_ms();
+  rc = run_wg17(c, res.out0, true, n, group, npop, inbreeding, fst, fis, mb_out, E);
+  res.stats.ms_finish += now_ms() - t0;
+  if (rc == TPG_OK && as_host) {
+    const void* dv[1] = {res.out0};
+    void* hv[1] = {as_host};
+    rc = results_to_host(c, dv, hv, 1, bytes, &res.stats.bytes_d2h, E);
+  }
+  if (stats) *stats = res.stats;
+  return rc;
 }
 
 int tpg_wg17(int device, const double* allele_sharing, int32_t on_device, int64_t n, const int32_t* group,

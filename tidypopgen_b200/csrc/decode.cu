@@ -20,6 +20,8 @@
 // aligned (nrow is arbitrary), so loads are aligned 32-bit words re-assembled with a
 // funnel shift across neighbouring lanes.  The K-major variant transposes 4x4 byte blocks
 // in registers (PRMT) and writes plane[i * lc_pad + l].
+#include <algorithm>
+#include <cstdlib>
 #include "internal.h"
 
 namespace tpg {
@@ -358,7 +360,7 @@ decode_planes_pk2_kernel(const DecodeParams p) {
 // the 256 doubles into a byte table (0xFF = missing, else the integer dosage) and per-individual
 // weights (2 / (3 - ploidy): 2 for diploids, 1 for pseudohaploids), so every sum is an exact
 // integer — n_alt is kept in half-allele units.  One pass, 1 byte read per genotype.
-constexpr int kScanLoci = 256;  // loci per CTA (16 rounds of 16)
+constexpr int kScanLociDefault = 256;  // loci per CTA (rounds of 16)
 
 struct ScanParams {
   const uint8_t* lut;     // 256 entries
@@ -369,12 +371,31 @@ struct ScanParams {
   int32_t* alt2;          // this chunk's loci (atomic): sum dosage * weight
   int32_t* valid;         //                           sum ploidy over non-missing
   int32_t* na_l;          //                           missing count
+  int loci_per_cta;       // multiple of 16
+  int flags;              // debugging: bit 0 = skip the per-individual atomics
 };
+
+// Sums 16 per-lane values over the 32 lanes of a warp with 16 shuffles (instead of 16 x 5): at
+// every step a lane hands half of its values to its partner and keeps the other half.  On
+// return, lane L (L even) holds in v[0] the warp total of locus (L >> 1).
+__device__ __forceinline__ void warp_multi_reduce16(uint32_t (&v)[16], int lane) {
+#pragma unroll
+  for (int h = 8, o = 16; h >= 1; h >>= 1, o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int k = 0; k < h; ++k) {
+      const uint32_t send = up ? v[k] : v[k + h];
+      const uint32_t keep = up ? v[k + h] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, o);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xFFFFFFFFu, v[0], 1);
+}
 
 __global__ void __launch_bounds__(kDecThreads)
 scan_counts_kernel(const DecodeParams p, const ScanParams sp) {
   __shared__ uint8_t lut[256];
-  __shared__ unsigned long long part[kDecThreads / 32][16];
+  __shared__ uint32_t part[kDecThreads / 32][16];
   lut[threadIdx.x] = sp.lut[threadIdx.x];  // kDecThreads == 256
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nib = (p.n + kDecThreads * 4 - 1) / (kDecThreads * 4);
@@ -382,59 +403,98 @@ scan_counts_kernel(const DecodeParams p, const ScanParams sp) {
   const int i0 = (ib * kDecThreads + threadIdx.x) * 4;
   const RowSel rs = make_rowsel(p, i0);
   const int nv = min(max(p.n - i0, 0), 4);
-  uint32_t wgt[4], plo[4];
+  const int n_here = min(kDecThreads * 4, p.n - ib * kDecThreads * 4);  // individuals of this CTA
+  // per-thread byte vectors over its 4 individuals: weight 2 / (3 - ploidy), diploid flag, validity
+  uint32_t w4 = 0, dip4 = 0, keep01 = 0;
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    wgt[b] = b < nv ? sp.weight[i0 + b] : 0u;
-    plo[b] = b < nv ? sp.ploidy[i0 + b] : 0u;
-  }
+  for (int b = 0; b < 4; ++b)
+    if (b < nv) {
+      w4 |= uint32_t(sp.weight[i0 + b]) << (8 * b);
+      dip4 |= (sp.ploidy[i0 + b] == 2 ? 1u : 0u) << (8 * b);
+      keep01 |= 1u << (8 * b);
+    }
   __syncthreads();
   int het[4] = {0, 0, 0, 0}, na[4] = {0, 0, 0, 0};
-  const int lbase = lb * kScanLoci;
-  for (int round = 0; round < kScanLoci / 16; ++round) {
+  const int lbase = lb * sp.loci_per_cta;
+  for (int round = 0; round < sp.loci_per_cta / 16; ++round) {
     const int l0 = lbase + round * 16;
     if (l0 >= p.lc) break;  // uniform over the CTA
     const bool safe = block_is_safe(p, l0, 16, ib * kDecThreads * 4, (ib + 1) * kDecThreads * 4);
     uint32_t g[16];
+    if (safe && l0 + 16 <= p.lc && !p.row_idx) {
+      // straight line: no branch between the 16 loads, so all of them are in flight together
+      uint32_t w0[16], wx[16], sh[16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int l = l0 + u;
-      g[u] = 0x03030303u;
-      if (l < p.lc) {
-        const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
-        g[u] = safe ? load4<true>(p, rs, col, lane) : load4<false>(p, rs, col, lane);
+      for (int u = 0; u < 16; ++u) {
+        const int64_t col = p.col_idx ? int64_t(__ldg(p.col_idx + l0 + u)) : p.col0 + l0 + u;
+        const uint8_t* a = p.raw + col * p.raw_stride + rs.off;
+        sh[u] = uint32_t(reinterpret_cast<uintptr_t>(a) & 3u);
+        const uint32_t* al = reinterpret_cast<const uint32_t*>(a - sh[u]);
+        w0[u] = __ldg(al);
+        wx[u] = 0;
+        if (lane == 31) wx[u] = __ldg(al + 1);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        uint32_t w1 = __shfl_down_sync(0xFFFFFFFFu, w0[u], 1);
+        if (lane == 31) w1 = wx[u];
+        g[u] = __funnelshift_r(w0[u], w1, sh[u] * 8);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int l = l0 + u;
+        g[u] = 0x03030303u;
+        if (l < p.lc) {
+          const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
+          g[u] = safe ? load4<true>(p, rs, col, lane) : load4<false>(p, rs, col, lane);
+        }
       }
     }
+    // per locus and lane: alt [0,15) | typed [15,23) | typed diploids [23,31) — the warp totals
+    // (<= 32512, 128, 128) cannot carry into the next field.  Four individuals at a time (SWAR):
+    // table bytes are 0xFF (missing) or <= 127, so bit 7 is the missing flag and byte sums
+    // never carry; the weighted sums are 4-way byte dot products.
+    uint32_t v[16];
+    uint32_t het4 = 0, na4 = 0;  // byte counters, at most 16 per round
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
-      uint32_t alt = 0, val = 0, nal = 0;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const uint32_t c = lut[(g[u] >> (8 * b)) & 0xFFu];
-        const bool ok = b < nv && l0 + u < p.lc, miss = c == 0xFFu;  // padding loci of the last round count nothing
-        if (ok && miss) { ++na[b]; ++nal; }
-        if (ok && !miss) { alt += c * wgt[b]; val += plo[b]; het[b] += (c == 1u); }
-      }
-      // alt [0,32) | valid [32,48) | na [48,64): one 64-bit butterfly per locus and warp
-      unsigned long long v = (unsigned long long)alt | ((unsigned long long)val << 32) | ((unsigned long long)nal << 48);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-      if (lane == 0) part[warp][u] = v;
+      const uint32_t gw = g[u];
+      const uint32_t c4 = uint32_t(lut[gw & 0xFFu]) | (uint32_t(lut[(gw >> 8) & 0xFFu]) << 8) |
+                          (uint32_t(lut[(gw >> 16) & 0xFFu]) << 16) | (uint32_t(lut[gw >> 24]) << 24);
+      const uint32_t real01 = (l0 + u < p.lc) ? keep01 : 0u;  // padding loci / individuals count nothing
+      const uint32_t miss01 = (c4 >> 7) & 0x01010101u;
+      const uint32_t typed01 = (miss01 ^ 0x01010101u) & real01;
+      const uint32_t cm = c4 & (typed01 * 0x7Fu);              // dosage of the typed, 0 elsewhere
+      const uint32_t alt = __dp4a(cm, w4, 0u);
+      const uint32_t typed = __dp4a(typed01, 0x01010101u, 0u);
+      const uint32_t td = __dp4a(typed01, dip4, 0u);
+      v[u] = alt | (typed << 15) | (td << 23);
+      const uint32_t ne1 = ((cm ^ 0x01010101u) + 0x7F7F7F7Fu) >> 7;  // bit 0 of a byte: dosage != 1
+      het4 += (ne1 ^ 0x01010101u) & typed01;                   // (bytes of cm ^ 1 are <= 0x7F: no carries)
+      na4 += miss01 & real01;
     }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { het[b] += (het4 >> (8 * b)) & 0xFFu; na[b] += (na4 >> (8 * b)) & 0xFFu; }
+    warp_multi_reduce16(v, lane);
+    if ((lane & 1) == 0) part[warp][lane >> 1] = v[0];
     __syncthreads();
     if (threadIdx.x < 16 && l0 + int(threadIdx.x) < p.lc) {
-      unsigned long long alt = 0, val = 0, nal = 0;
+      uint32_t alt = 0, typed = 0, td = 0;
 #pragma unroll
       for (int w = 0; w < kDecThreads / 32; ++w) {
-        const unsigned long long v = part[w][threadIdx.x];
-        alt += v & 0xFFFFFFFFull; val += (v >> 32) & 0xFFFFull; nal += v >> 48;
+        const uint32_t x = part[w][threadIdx.x];
+        alt += x & 0x7FFFu; typed += (x >> 15) & 0xFFu; td += x >> 23;
       }
       const int l = l0 + threadIdx.x;
-      if (nib == 1) { sp.alt2[l] += int32_t(alt); sp.valid[l] += int32_t(val); sp.na_l[l] += int32_t(nal); }
-      else { atomicAdd(sp.alt2 + l, int32_t(alt)); atomicAdd(sp.valid + l, int32_t(val)); atomicAdd(sp.na_l + l, int32_t(nal)); }
+      const int32_t val = int32_t(typed + td);  // sum of ploidy over the typed: 1 each + 1 more per diploid
+      const int32_t nal = n_here - int32_t(typed);
+      if (nib == 1) { sp.alt2[l] += int32_t(alt); sp.valid[l] += val; sp.na_l[l] += nal; }
+      else { atomicAdd(sp.alt2 + l, int32_t(alt)); atomicAdd(sp.valid + l, val); atomicAdd(sp.na_l + l, nal); }
     }
     __syncthreads();
   }
+  if (!(sp.flags & 1))
 #pragma unroll
   for (int b = 0; b < 4; ++b)
     if (b < nv) {
@@ -464,7 +524,10 @@ int launch_scan(Ctx* ctx, const DecodeArgs& a, const ScanArgs& s, cudaStream_t s
   ScanParams sp;
   sp.lut = s.lut; sp.weight = s.weight; sp.ploidy = s.ploidy;
   sp.het_n = s.het_n; sp.na_n = s.na_n; sp.alt2 = s.alt2; sp.valid = s.valid; sp.na_l = s.na_l;
-  const int64_t blocks = ((a.n + kDecThreads * 4 - 1) / (kDecThreads * 4)) * ((a.lc + kScanLoci - 1) / kScanLoci);
+  sp.loci_per_cta = kScanLociDefault;
+  if (const char* ev = getenv("TPG_SCAN_LOCI")) sp.loci_per_cta = std::max(16, atoi(ev) / 16 * 16);
+  sp.flags = getenv("TPG_SCAN_NO_INDIV") ? 1 : 0;
+  const int64_t blocks = ((a.n + kDecThreads * 4 - 1) / (kDecThreads * 4)) * ((a.lc + sp.loci_per_cta - 1) / sp.loci_per_cta);
   if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "scan: chunk too large for one launch");
   scan_counts_kernel<<<unsigned(blocks), kDecThreads, 0, st>>>(p, sp);
   TPG_CUDA_OK(cudaGetLastError(), E);

@@ -145,45 +145,51 @@ struct WalkParams {
   double* rs_lo;
   int32_t* rcnt;
   int32_t* rinf;
+  int32_t* rgt;            // by original index: living partners above the threshold in this row
   uint8_t* dead;           // by rank (zeroed by the host)
-  long long live_pairs;    // ordered pairs above the threshold among the living
   int32_t* status;         // [0] = 0 ok / 1 NaN reached, [1] = number deleted
 };
 
-__device__ void walk_totals(const WalkParams& p, dd* S, long long* C, long long* I, double* sh_hi, double* sh_lo,
-                            long long* sh_c, long long* sh_i) {
+// Totals over the living rows: S = sum of row sums, C = count, I = infinities, G = ordered pairs
+// above the threshold (the `any` test of :90).  Fixed order: identical in every thread.
+__device__ void walk_totals(const WalkParams& p, dd* S, long long* C, long long* I, long long* G, double* sh_hi,
+                            double* sh_lo, long long* sh_c, long long* sh_i, long long* sh_g) {
   dd acc = dd_zero();
-  long long c = 0, ii = 0;
+  long long c = 0, ii = 0, g = 0;
   for (int r = threadIdx.x; r < p.n; r += kWalkThreads) {
     if (p.dead[r]) continue;
     const int i = p.P[r];
     acc = dd_add(acc, dd{p.rs_hi[i], p.rs_lo[i]});
     c += p.rcnt[i];
     ii += p.rinf[i];
+    g += p.rgt[i];
   }
   acc = dd_warp_sum(acc);
   c = i64_warp_sum(c);
   ii = i64_warp_sum(ii);
+  g = i64_warp_sum(g);
   const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { sh_hi[w] = acc.hi; sh_lo[w] = acc.lo; sh_c[w] = c; sh_i[w] = ii; }
+  if ((threadIdx.x & 31) == 0) { sh_hi[w] = acc.hi; sh_lo[w] = acc.lo; sh_c[w] = c; sh_i[w] = ii; sh_g[w] = g; }
   __syncthreads();
   dd t = dd_zero();
-  long long tc = 0, ti = 0;
-  for (int k = 0; k < kWalkThreads / 32; ++k) { t = dd_add(t, dd{sh_hi[k], sh_lo[k]}); tc += sh_c[k]; ti += sh_i[k]; }
-  *S = t; *C = tc; *I = ti;
+  long long tc = 0, ti = 0, tg = 0;
+  for (int k = 0; k < kWalkThreads / 32; ++k) {
+    t = dd_add(t, dd{sh_hi[k], sh_lo[k]});
+    tc += sh_c[k]; ti += sh_i[k]; tg += sh_g[k];
+  }
+  *S = t; *C = tc; *I = ti; *G = tg;
   __syncthreads();
 }
 
 __global__ void __launch_bounds__(kWalkThreads, 1)
 relate_walk_kernel(const WalkParams p) {
   __shared__ double sh_hi[32], sh_lo[32];
-  __shared__ long long sh_c[32], sh_i[32];
+  __shared__ long long sh_c[32], sh_i[32], sh_g[32];
   __shared__ uint32_t sh_ev[kWalkThreads];
-  __shared__ uint8_t sh_alive[kWalkThreads];
+  __shared__ uint32_t sh_mask[kWalkThreads / 32];
   dd S;
-  long long C, I;
-  walk_totals(p, &S, &C, &I, sh_hi, sh_lo, sh_c, sh_i);
-  long long live = p.live_pairs;
+  long long C, I, live;
+  walk_totals(p, &S, &C, &I, &live, sh_hi, sh_lo, sh_c, sh_i, sh_g);
   int deleted = 0;
   for (int e = 0; e < p.n_erows; ++e) {
     if (live == 0) break;                       // :90 — nothing above the threshold is left
@@ -196,53 +202,49 @@ relate_walk_kernel(const WalkParams p) {
       bool alive = false;
       if (k < p.eoff[a + 1]) { w = p.ev[k]; alive = !p.dead[w & 0x7FFFFFFFu]; }
       sh_ev[threadIdx.x] = w;
-      sh_alive[threadIdx.x] = alive;
+      // Partners alive NOW stay alive while this row is walked, except the one a decision removes
+      // (each partner occurs once per row), so the snapshot can be consumed bit by bit.
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, alive);
+      if ((threadIdx.x & 31) == 0) sh_mask[threadIdx.x >> 5] = m;
       __syncthreads();
-      const int64_t left = p.eoff[a + 1] - base;
-      const int nb = left < kWalkThreads ? int(left) : kWalkThreads;
-      for (int q = 0; q < nb && !a_dead; ++q) {
-        if (!sh_alive[q]) continue;             // :100 (a partner deleted earlier)
-        const uint32_t wq = sh_ev[q];
-        if (wq & 0x80000000u) {                 // if (NA > threshold): R stops here
-          if (threadIdx.x == 0) { p.status[0] = 1; p.status[1] = deleted; }
-          return;
-        }
-        const int b = int(wq);
-        const int ia = p.P[a], ib = p.P[b];
-        // mn1 = mean(matrix2[a, ]), mn2 = mean(matrix2[-b, ]), na.rm = TRUE (:102-103)
-        const double mn1 = (p.rinf[ia] && p.rcnt[ia]) ? double(INFINITY)
-                                                      : dd_mean(dd{p.rs_hi[ia], p.rs_lo[ia]}, double(p.rcnt[ia]));
-        const long long c2 = C - p.rcnt[ib], i2 = I - p.rinf[ib];
-        const double mn2 = (i2 && c2) ? double(INFINITY)
-                                      : dd_mean(dd_add(S, dd_neg(dd{p.rs_hi[ib], p.rs_lo[ib]})), double(c2));
-        const int kill = (mn1 > mn2) ? a : b;   // :117-131
-        const int ik = p.P[kill];
-        __syncthreads();                        // everyone has read the sums of the victim
-        long long drop = 0;
-        for (int r = threadIdx.x; r < p.n; r += kWalkThreads) {
-          if (r == kill || p.dead[r]) continue;
-          const int i = p.P[r];
-          const double v = fabs(p.m[i + int64_t(ik) * p.ld]);   // matrix2[r, kill] <- NA
-          if (v == v) {
-            p.rcnt[i] -= 1;
-            if (isinf(v)) p.rinf[i] -= 1;
-            else { const dd t = dd_add_d(dd{p.rs_hi[i], p.rs_lo[i]}, -v); p.rs_hi[i] = t.hi; p.rs_lo[i] = t.lo; }
-            if (v > p.thr) ++drop;
+      for (int wq = 0; wq < kWalkThreads / 32 && !a_dead; ++wq) {
+        uint32_t bits = sh_mask[wq];
+        while (bits && !a_dead) {
+          const int q = wq * 32 + __ffs(bits) - 1;
+          bits &= bits - 1;
+          const uint32_t evq = sh_ev[q];
+          if (evq & 0x80000000u) {              // if (NA > threshold): R stops here
+            if (threadIdx.x == 0) { p.status[0] = 1; p.status[1] = deleted; }
+            return;
           }
-          const double u = fabs(p.m[ik + int64_t(i) * p.ld]);   // matrix2[kill, r] <- NA
-          if (u == u && u > p.thr) ++drop;
+          const int b = int(evq);
+          const int ia = p.P[a], ib = p.P[b];
+          // mn1 = mean(matrix2[a, ]), mn2 = mean(matrix2[-b, ]), na.rm = TRUE (:102-103)
+          const double mn1 = (p.rinf[ia] && p.rcnt[ia]) ? double(INFINITY)
+                                                        : dd_mean(dd{p.rs_hi[ia], p.rs_lo[ia]}, double(p.rcnt[ia]));
+          const long long c2 = C - p.rcnt[ib], i2 = I - p.rinf[ib];
+          const double mn2 = (i2 && c2) ? double(INFINITY)
+                                        : dd_mean(dd_add(S, dd_neg(dd{p.rs_hi[ib], p.rs_lo[ib]})), double(c2));
+          const int kill = (mn1 > mn2) ? a : b; // :117-131
+          const int ik = p.P[kill];
+          __syncthreads();                      // everyone has read the sums of the victim
+          for (int r = threadIdx.x; r < p.n; r += kWalkThreads) {
+            if (r == kill || p.dead[r]) continue;
+            const int i = p.P[r];
+            const double v = fabs(p.m[i + int64_t(ik) * p.ld]);   // matrix2[r, kill] <- NA
+            if (v == v) {
+              p.rcnt[i] -= 1;
+              if (isinf(v)) p.rinf[i] -= 1;
+              else { const dd t = dd_add_d(dd{p.rs_hi[i], p.rs_lo[i]}, -v); p.rs_hi[i] = t.hi; p.rs_lo[i] = t.lo; }
+              if (v > p.thr) p.rgt[i] -= 1;
+            }
+          }
+          if (threadIdx.x == 0) p.dead[kill] = 1;                  // matrix2[kill, ] <- NA
+          ++deleted;
+          __syncthreads();
+          walk_totals(p, &S, &C, &I, &live, sh_hi, sh_lo, sh_c, sh_i, sh_g);
+          if (kill == a) a_dead = true;
         }
-        drop = i64_warp_sum(drop);
-        if ((threadIdx.x & 31) == 0) sh_c[threadIdx.x >> 5] = drop;
-        if (threadIdx.x == 0) p.dead[kill] = 1;
-        __syncthreads();
-        long long d = 0;
-        for (int k2 = 0; k2 < kWalkThreads / 32; ++k2) d += sh_c[k2];
-        live -= d;
-        ++deleted;
-        __syncthreads();
-        walk_totals(p, &S, &C, &I, sh_hi, sh_lo, sh_c, sh_i);
-        if (kill == a) a_dead = true;
       }
       __syncthreads();
     }
@@ -263,7 +265,7 @@ int run_filter_high_relatedness(Ctx* ctx, const double* mat, bool on_device, int
   }
   TPG_CUDA_OK(cudaSetDevice(ctx->device), E);
   cudaStream_t st = ctx->s_compute;
-  DevBuf d_m, d_cm, d_rs, d_ri, d_P, d_ec, d_eoff, d_ev, d_erows, d_dead, d_status;
+  DevBuf d_m, d_cm, d_rs, d_ri, d_rgt, d_P, d_ec, d_eoff, d_ev, d_erows, d_dead, d_status;
   const double* m = mat;
   int rc;
   const size_t nn = size_t(n) * size_t(n);
@@ -312,8 +314,12 @@ int run_filter_high_relatedness(Ctx* ctx, const double* mat, bool on_device, int
   std::vector<uint8_t> dead(n, 0);
   int32_t status[2] = {0, 0};
   if (!erows.empty() && live > 0) {
-    if ((rc = d_ev.alloc(sizeof(uint32_t) * size_t(eoff[n]), E)) || (rc = d_erows.alloc(sizeof(int32_t) * erows.size(), E)))
+    if ((rc = d_ev.alloc(sizeof(uint32_t) * size_t(eoff[n]), E)) || (rc = d_erows.alloc(sizeof(int32_t) * erows.size(), E)) ||
+        (rc = d_rgt.alloc(sizeof(int32_t) * n, E)))
       return rc;
+    std::vector<int32_t> rgt(n);  // pairs above the threshold per row, by original index
+    for (int64_t a = 0; a < n; ++a) rgt[P[a]] = ec[n + a];
+    TPG_CUDA_OK(cudaMemcpyAsync(d_rgt.p, rgt.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st), E);
     TPG_CUDA_OK(cudaMemcpyAsync(d_eoff.p, eoff.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st), E);
     TPG_CUDA_OK(cudaMemcpyAsync(d_erows.p, erows.data(), sizeof(int32_t) * erows.size(), cudaMemcpyHostToDevice, st), E);
     TPG_CUDA_OK(cudaMemsetAsync(d_dead.p, 0, size_t(n), st), E);
@@ -325,7 +331,8 @@ int run_filter_high_relatedness(Ctx* ctx, const double* mat, bool on_device, int
     w.eoff = d_eoff.as<int64_t>(); w.ev = d_ev.as<uint32_t>();
     w.rs_hi = d_rs.as<double>(); w.rs_lo = d_rs.as<double>() + n;
     w.rcnt = d_ri.as<int32_t>(); w.rinf = d_ri.as<int32_t>() + n;
-    w.dead = d_dead.as<uint8_t>(); w.live_pairs = live; w.status = d_status.as<int32_t>();
+    w.rgt = d_rgt.as<int32_t>();
+    w.dead = d_dead.as<uint8_t>(); w.status = d_status.as<int32_t>();
     relate_walk_kernel<<<1, kWalkThreads, 0, st>>>(w);
     TPG_CUDA_OK(cudaGetLastError(), E);
     ctx->launches += 2;
