@@ -40,7 +40,7 @@ het = (host.reshape(m, n) == 1).sum(0)
 assert np.array_equal(r["het_n"], het), "scan mismatch"
 
 # ---- KING + filter with the matrix kept in HBM
-for (n, m, thr) in [(5000, 20000, 0.01), (20000, 20000, 0.015)]:
+for (n, m, thr) in [(5000, 20000, 0.01), (20000, 20000, 0.015), (20000, 20000, 0.088)]:
     X, raw = synth(n, m, 7, 0.01)
     gt = tpg.gen_tibble(X)
     kw = dict(src=(L.SRC_DEVICE, raw.data_ptr(), raw))

@@ -141,35 +141,22 @@ struct WalkParams {
   int n_erows;
   const int64_t* eoff;     // per rank: start of its events (n + 1 entries)
   const uint32_t* ev;
-  double* rs_hi;           // by original index
+  double* rs_hi;           // row state, by rank
   double* rs_lo;
   int32_t* rcnt;
   int32_t* rinf;
-  int32_t* rgt;            // by original index: living partners above the threshold in this row
+  int32_t* rgt;            // living partners above the threshold in this row
   uint8_t* dead;           // by rank (zeroed by the host)
   int32_t* status;         // [0] = 0 ok / 1 NaN reached, [1] = number deleted
 };
 
-// Totals over the living rows: S = sum of row sums, C = count, I = infinities, G = ordered pairs
-// above the threshold (the `any` test of :90).  Fixed order: identical in every thread.
-__device__ void walk_totals(const WalkParams& p, dd* S, long long* C, long long* I, long long* G, double* sh_hi,
-                            double* sh_lo, long long* sh_c, long long* sh_i, long long* sh_g) {
-  dd acc = dd_zero();
-  long long c = 0, ii = 0, g = 0;
-  for (int r = threadIdx.x; r < p.n; r += kWalkThreads) {
-    if (p.dead[r]) continue;
-    const int i = p.P[r];
-    acc = dd_add(acc, dd{p.rs_hi[i], p.rs_lo[i]});
-    c += p.rcnt[i];
-    ii += p.rinf[i];
-    g += p.rgt[i];
-  }
-  acc = dd_warp_sum(acc);
-  c = i64_warp_sum(c);
-  ii = i64_warp_sum(ii);
-  g = i64_warp_sum(g);
+// Block-wide sums in a fixed order (identical in every thread): a double-double and three counts.
+__device__ void block_sums(dd* v, long long* c, long long* i, long long* g, double* sh_hi, double* sh_lo,
+                           long long* sh_c, long long* sh_i, long long* sh_g) {
+  dd acc = dd_warp_sum(*v);
+  const long long cc = i64_warp_sum(*c), ii = i64_warp_sum(*i), gg = i64_warp_sum(*g);
   const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { sh_hi[w] = acc.hi; sh_lo[w] = acc.lo; sh_c[w] = c; sh_i[w] = ii; sh_g[w] = g; }
+  if ((threadIdx.x & 31) == 0) { sh_hi[w] = acc.hi; sh_lo[w] = acc.lo; sh_c[w] = cc; sh_i[w] = ii; sh_g[w] = gg; }
   __syncthreads();
   dd t = dd_zero();
   long long tc = 0, ti = 0, tg = 0;
@@ -177,19 +164,29 @@ __device__ void walk_totals(const WalkParams& p, dd* S, long long* C, long long*
     t = dd_add(t, dd{sh_hi[k], sh_lo[k]});
     tc += sh_c[k]; ti += sh_i[k]; tg += sh_g[k];
   }
-  *S = t; *C = tc; *I = ti; *G = tg;
+  *v = t; *c = tc; *i = ti; *g = tg;
   __syncthreads();
 }
 
+// Row state is indexed by RANK here (the host permutes it once): rs = sum of the row's living
+// entries, rcnt = how many (Inf included), rinf = infinities, rgt = entries above the threshold.
 __global__ void __launch_bounds__(kWalkThreads, 1)
 relate_walk_kernel(const WalkParams p) {
   __shared__ double sh_hi[32], sh_lo[32];
   __shared__ long long sh_c[32], sh_i[32], sh_g[32];
   __shared__ uint32_t sh_ev[kWalkThreads];
   __shared__ uint32_t sh_mask[kWalkThreads / 32];
-  dd S;
-  long long C, I, live;
-  walk_totals(p, &S, &C, &I, &live, sh_hi, sh_lo, sh_c, sh_i, sh_g);
+  // totals over the living rows: S, C (count), I (infinities), live (ordered pairs above the
+  // threshold: the `any` test of :90) — summed once, then kept up to date per deletion
+  dd S = dd_zero();
+  long long C = 0, I = 0, live = 0;
+  for (int r = threadIdx.x; r < p.n; r += kWalkThreads) {
+    S = dd_add(S, dd{p.rs_hi[r], p.rs_lo[r]});
+    C += p.rcnt[r];
+    I += p.rinf[r];
+    live += p.rgt[r];
+  }
+  block_sums(&S, &C, &I, &live, sh_hi, sh_lo, sh_c, sh_i, sh_g);
   int deleted = 0;
   for (int e = 0; e < p.n_erows; ++e) {
     if (live == 0) break;                       // :90 — nothing above the threshold is left
@@ -218,31 +215,39 @@ relate_walk_kernel(const WalkParams p) {
             return;
           }
           const int b = int(evq);
-          const int ia = p.P[a], ib = p.P[b];
           // mn1 = mean(matrix2[a, ]), mn2 = mean(matrix2[-b, ]), na.rm = TRUE (:102-103)
-          const double mn1 = (p.rinf[ia] && p.rcnt[ia]) ? double(INFINITY)
-                                                        : dd_mean(dd{p.rs_hi[ia], p.rs_lo[ia]}, double(p.rcnt[ia]));
-          const long long c2 = C - p.rcnt[ib], i2 = I - p.rinf[ib];
+          const double mn1 = (p.rinf[a] && p.rcnt[a]) ? double(INFINITY)
+                                                      : dd_mean(dd{p.rs_hi[a], p.rs_lo[a]}, double(p.rcnt[a]));
+          const long long c2 = C - p.rcnt[b], i2 = I - p.rinf[b];
           const double mn2 = (i2 && c2) ? double(INFINITY)
-                                        : dd_mean(dd_add(S, dd_neg(dd{p.rs_hi[ib], p.rs_lo[ib]})), double(c2));
+                                        : dd_mean(dd_add(S, dd_neg(dd{p.rs_hi[b], p.rs_lo[b]})), double(c2));
           const int kill = (mn1 > mn2) ? a : b; // :117-131
-          const int ik = p.P[kill];
+          const int64_t colk = int64_t(p.P[kill]) * p.ld;
+          // the victim's own row leaves the totals ...
+          dd rem = dd{p.rs_hi[kill], p.rs_lo[kill]};
+          long long remc = p.rcnt[kill], remi = p.rinf[kill], remg = p.rgt[kill];
           __syncthreads();                      // everyone has read the sums of the victim
+          // ... and so does its column: matrix2[r, kill] <- NA for every living r
+          dd part = dd_zero();
+          long long pc = 0, pi = 0, pg = 0;
           for (int r = threadIdx.x; r < p.n; r += kWalkThreads) {
             if (r == kill || p.dead[r]) continue;
-            const int i = p.P[r];
-            const double v = fabs(p.m[i + int64_t(ik) * p.ld]);   // matrix2[r, kill] <- NA
-            if (v == v) {
-              p.rcnt[i] -= 1;
-              if (isinf(v)) p.rinf[i] -= 1;
-              else { const dd t = dd_add_d(dd{p.rs_hi[i], p.rs_lo[i]}, -v); p.rs_hi[i] = t.hi; p.rs_lo[i] = t.lo; }
-              if (v > p.thr) p.rgt[i] -= 1;
+            const double v = fabs(p.m[p.P[r] + colk]);
+            if (v != v) continue;
+            p.rcnt[r] -= 1; ++pc;
+            if (isinf(v)) { p.rinf[r] -= 1; ++pi; }
+            else {
+              const dd t = dd_add_d(dd{p.rs_hi[r], p.rs_lo[r]}, -v);
+              p.rs_hi[r] = t.hi; p.rs_lo[r] = t.lo;
+              part = dd_add_d(part, v);
             }
+            if (v > p.thr) { p.rgt[r] -= 1; ++pg; }
           }
           if (threadIdx.x == 0) p.dead[kill] = 1;                  // matrix2[kill, ] <- NA
+          block_sums(&part, &pc, &pi, &pg, sh_hi, sh_lo, sh_c, sh_i, sh_g);
+          S = dd_add(S, dd_neg(dd_add(rem, part)));
+          C -= remc + pc; I -= remi + pi; live -= remg + pg;
           ++deleted;
-          __syncthreads();
-          walk_totals(p, &S, &C, &I, &live, sh_hi, sh_lo, sh_c, sh_i, sh_g);
           if (kill == a) a_dead = true;
         }
       }
@@ -317,12 +322,24 @@ int run_filter_high_relatedness(Ctx* ctx, const double* mat, bool on_device, int
     if ((rc = d_ev.alloc(sizeof(uint32_t) * size_t(eoff[n]), E)) || (rc = d_erows.alloc(sizeof(int32_t) * erows.size(), E)) ||
         (rc = d_rgt.alloc(sizeof(int32_t) * n, E)))
       return rc;
-    std::vector<int32_t> rgt(n);  // pairs above the threshold per row, by original index
-    for (int64_t a = 0; a < n; ++a) rgt[P[a]] = ec[n + a];
+    // row state in visiting (rank) order
+    std::vector<double> rs(2 * n), rs_r(2 * n);
+    std::vector<int32_t> ri(2 * n), ri_r(2 * n), rgt(n);
+    TPG_CUDA_OK(cudaMemcpyAsync(rs.data(), d_rs.p, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, st), E);
+    TPG_CUDA_OK(cudaMemcpyAsync(ri.data(), d_ri.p, sizeof(int32_t) * 2 * n, cudaMemcpyDeviceToHost, st), E);
+    TPG_CUDA_OK(cudaStreamSynchronize(st), E);
+    for (int64_t a = 0; a < n; ++a) {
+      rs_r[a] = rs[P[a]]; rs_r[n + a] = rs[n + P[a]];
+      ri_r[a] = ri[P[a]]; ri_r[n + a] = ri[n + P[a]];
+      rgt[a] = ec[n + a];
+    }
+    TPG_CUDA_OK(cudaMemcpyAsync(d_rs.p, rs_r.data(), sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st), E);
+    TPG_CUDA_OK(cudaMemcpyAsync(d_ri.p, ri_r.data(), sizeof(int32_t) * 2 * n, cudaMemcpyHostToDevice, st), E);
     TPG_CUDA_OK(cudaMemcpyAsync(d_rgt.p, rgt.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st), E);
     TPG_CUDA_OK(cudaMemcpyAsync(d_eoff.p, eoff.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st), E);
     TPG_CUDA_OK(cudaMemcpyAsync(d_erows.p, erows.data(), sizeof(int32_t) * erows.size(), cudaMemcpyHostToDevice, st), E);
     TPG_CUDA_OK(cudaMemsetAsync(d_dead.p, 0, size_t(n), st), E);
+    TPG_CUDA_OK(cudaStreamSynchronize(st), E);  // the host vectors above go out of scope
     relate_events_kernel<true><<<wblocks, 32 * wpb, 0, st>>>(m, n, int(n), thr, d_P.as<int32_t>(), nullptr, nullptr,
                                                             d_eoff.as<int64_t>(), d_ev.as<uint32_t>());
     WalkParams w;
