@@ -283,9 +283,11 @@ def run_b200(args, rank, world, local):
     gram_ops = KING_INT8_OPS_PER_PAIRSNP * n * n * loci_per_launch
     int8_peak = 2.0 * pk["bf16_tflops"]
     tr = traffic_from_profile()
-    roof = {"kernel": "gram_i8_kernel", "bound": "tensor", "achieved": gram_ops / (gram_ms * 1e-3) / 1e12,
+    pair = os.environ.get("TPG_GRAM_CTAS", "2") != "1"
+    roof = {"kernel": "gram_i8_pair_kernel (tcgen05.mma.cta_group::2)" if pair else "gram_i8_kernel (cta_group::1)",
+            "bound": "tensor", "achieved": gram_ops / (gram_ms * 1e-3) / 1e12,
             "peak": int8_peak, "unit": "TFLOP/s", "frac": gram_ops / (gram_ms * 1e-3) / 1e12 / int8_peak,
-            "traffic": tr.get("gram_i8_dram_bytes_per_launch"),
+            "traffic": tr.get("gram_i8_pair_dram_bytes_per_launch" if pair else "gram_i8_dram_bytes_per_launch"),
             "note": ("int8 tensor ops (2 per MAC); algorithmic = 4 op per pair-SNP (DD+NN upper, HN full); "
                      f"peak = 2 x measured bf16 burst from {pk['source']} (nominal int8 dense 4500); "
                      f"issued incl. tile padding = {2 * agg['macs'] / steps / (agg['ms_gram'] / steps * 1e-3) / 1e12:.0f} TOP/s; "
