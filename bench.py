@@ -77,6 +77,30 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+def measure_int8_library_peak(local):
+    """Dense int8 x int8 -> s32 GEMM through torch._int_mm (cuBLASLt) at 8192^3, best of 10 with CUDA
+    events: a measured int8 tensor-core figure to read the gram kernel against, beside the
+    2 x bf16 peak of MEASURED_PEAKS.json (which has no int8 entry)."""
+    import torch
+    try:
+        dev = f"cuda:{local}"
+        a = torch.randint(-1, 2, (8192, 8192), dtype=torch.int8, device=dev)
+        b = torch.randint(-1, 2, (8192, 8192), dtype=torch.int8, device=dev)
+        for _ in range(3):
+            torch._int_mm(a, b)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return {"tops": 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12, "how": "torch._int_mm 8192^3 (cuBLASLt), best of 10"}
+    except Exception as ex:  # noqa: BLE001
+        return {"tops": None, "how": f"torch._int_mm unavailable: {ex}"} if False else None
+
+
 def traffic_from_profile():
     """dram bytes per gram_i8 launch from the committed ncu capture, if one exists."""
     try:
@@ -282,6 +306,7 @@ def run_b200(args, rank, world, local):
     loci_per_launch = m * steps / max(1, agg["chunks"])
     gram_ops = KING_INT8_OPS_PER_PAIRSNP * n * n * loci_per_launch
     int8_peak = 2.0 * pk["bf16_tflops"]
+    int8_lib = measure_int8_library_peak(local)  # cuBLASLt int8 GEMM on this GPU, outside the timed region
     tr = traffic_from_profile()
     pair = os.environ.get("TPG_GRAM_CTAS", "2") != "1"
     roof = {"kernel": "gram_i8_pair_kernel (tcgen05.mma.cta_group::2)" if pair else "gram_i8_kernel (cta_group::1)",
@@ -291,7 +316,9 @@ def run_b200(args, rank, world, local):
             "note": ("int8 tensor ops (2 per MAC); algorithmic = 4 op per pair-SNP (DD+NN upper, HN full); "
                      f"peak = 2 x measured bf16 burst from {pk['source']} (nominal int8 dense 4500); "
                      f"issued incl. tile padding = {2 * agg['macs'] / steps / (agg['ms_gram'] / steps * 1e-3) / 1e12:.0f} TOP/s; "
-                     f"avg launch {gram_ms:.3f} ms over {agg['chunks'] // steps} launch(es)/step")}
+                     f"avg launch {gram_ms:.3f} ms over {agg['chunks'] // steps} launch(es)/step"),
+            "int8_library_peak": int8_lib,
+            "frac_of_int8_library_peak": (gram_ops / (gram_ms * 1e-3) / 1e12 / int8_lib["tops"]) if int8_lib else None}
     dec_bytes = DECODE_BYTES_PER_GENOTYPE * n * loci_per_launch
     roof_dec = {"kernel": "decode_planes_mn_kernel", "bound": "hbm", "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9,
                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / pk["hbm_gbs"],

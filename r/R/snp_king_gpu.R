@@ -51,3 +51,38 @@ snp_allele_sharing <- function(
 }
 # pairwise_king / pairwise_ibs / pairwise_allele_sharing / pairwise_grm
 # (R/pairwise_*.R) are unchanged: they only call the three drivers above.
+
+# ---- consumers of the matrices (SURVEY.md section 8f) --------------------------------------------
+# filter_high_relatedness(): the names handling (:33-44), the single-individual branch (:46-53) and
+# the return value (:138-144) stay as in R/filter_high_relatedness.R; the O(n^2)-per-pair loop
+# (:56-135) becomes one call.
+filter_high_relatedness_core <- function(matrix, var_names, kings_threshold,
+                                         device = getOption("tidypopgen.gpu.device", 0L)) {
+  res <- gpu_filter_high_relatedness(matrix, kings_threshold, device)
+  passed_filter <- var_names[res$order][as.logical(res$keep[res$order])]
+  to_remove <- var_names[!var_names %in% passed_filter]
+  list(passed_filter, to_remove, var_names %in% passed_filter)
+}
+
+# indiv_het_obs.vctrs_bigSNP (R/indiv_het_obs.R:33-65): one scan instead of big_apply(gt_ind_hetero)
+indiv_het_obs_gpu <- function(.x, as_counts = FALSE) {
+  X <- attr(.x, "fbm") # nolint
+  res <- gpu_scan(X, vctrs::vec_data(.x), attr(.x, "loci")$big_index, indiv_ploidy(.x),
+                  device = getOption("tidypopgen.gpu.device", 0L))
+  if (!as_counts) {
+    return(res$het_n / (ncol(X) - res$na_n))
+  }
+  cbind(het_n = res$het_n, na_n = res$na_n)
+}
+
+# pop_fst (R/pop_fst.R:31-76) from a precomputed or freshly computed allele-sharing matrix
+pop_fst_gpu <- function(.x, include_global = FALSE, allele_sharing_mat = NULL) {
+  if (!inherits(.x, "grouped_df")) stop(".x should be a grouped gen_tibble")
+  if (is.null(allele_sharing_mat)) allele_sharing_mat <- pairwise_allele_sharing(.x, as_matrix = TRUE)
+  n_pop <- max(dplyr::group_indices(.x))
+  res <- gpu_wg17(allele_sharing_mat, dplyr::group_indices(.x) - 1L, n_pop,
+                  device = getOption("tidypopgen.gpu.device", 0L))
+  fst <- if (include_global) res$fst else res$fst[seq_len(n_pop)]
+  names(fst) <- c(dplyr::group_keys(.x) %>% dplyr::pull(1), if (include_global) "global")
+  fst
+}

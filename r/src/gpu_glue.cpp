@@ -115,3 +115,71 @@ NumericMatrix gpu_snp_allele_sharing(Environment BM, const IntegerVector& rowInd
   run(job, res);
   return out;
 }
+
+// ------------------------------------------------------------------ consumers of the matrices
+// (include/tpg_b200.h "consumers of the matrices")
+
+// filter_high_relatedness(): keep / order of R/filter_high_relatedness.R:26-145 for a matrix in R memory.
+// [[Rcpp::export]]
+List gpu_filter_high_relatedness(NumericMatrix matrix, double kings_threshold, int device = 0) {
+  const int n = matrix.nrow();
+  if (matrix.ncol() != n) stop("matrix should be square");
+  IntegerVector keep(n), order(n);
+  int64_t removed = 0;
+  char err[1024] = {0};
+  if (tpg_filter_high_relatedness(device, matrix.begin(), /*on_device=*/0, n, kings_threshold, keep.begin(),
+                                  order.begin(), &removed, err, sizeof err) != TPG_OK)
+    stop("%s", err);  // R's own message where the reference stops on a NaN comparison
+  return List::create(_["keep"] = keep, _["order"] = order + 1, _["n_removed"] = (double) removed);
+}
+
+// qc_report_indiv(kings_threshold = ...): KING + filter in one call; the matrix stays in HBM unless
+// want_king (R/qc_report_indiv.R:85-99 attaches it as attr(to_keep, "king")).
+// [[Rcpp::export]]
+List gpu_king_filter(Environment BM, const IntegerVector& rowInd, const IntegerVector& colInd, double block_size,
+                     double kings_threshold, bool want_king = true, int device = 0) {
+  const int n = rowInd.size();
+  tpg_job job; std::string path;
+  fill_job(job, BM, rowInd, colInd, TPG_STAT_KING, block_size, true, device, path);
+  IntegerVector keep(n), order(n);
+  NumericMatrix king(want_king ? n : 0, want_king ? n : 0);
+  int64_t removed = 0;
+  char err[1024] = {0};
+  if (tpg_king_filter(&job, kings_threshold, keep.begin(), order.begin(), &removed, want_king ? king.begin() : nullptr,
+                      nullptr, err, sizeof err) != TPG_OK)
+    stop("%s", err);
+  return List::create(_["keep"] = keep, _["order"] = order + 1, _["king"] = king);
+}
+
+// indiv_inbreeding / pop_fst / pop_fis(method = "WG17") from an allele-sharing matrix in R memory
+// (R/indiv_inbreeding.R:56-81, R/pop_fst.R:31-76, R/pop_fis.R:137-191).  group = group_indices(.x) - 1L.
+// [[Rcpp::export]]
+List gpu_wg17(NumericMatrix allele_sharing, const IntegerVector& group, int npop, int device = 0) {
+  const int n = allele_sharing.nrow();
+  NumericVector inb(n), fst(npop + 1), fis(npop + 1), mb(2);
+  char err[1024] = {0};
+  const bool grouped = npop >= 2;
+  if (tpg_wg17(device, allele_sharing.begin(), 0, n, grouped ? group.begin() : nullptr, grouped ? npop : 1, inb.begin(),
+               grouped ? fst.begin() : nullptr, grouped ? fis.begin() : nullptr, mb.begin(), err, sizeof err) != TPG_OK)
+    stop("%s", err);
+  return List::create(_["inbreeding"] = inb, _["fst"] = fst, _["fis"] = fis, _["mb"] = mb);
+}
+
+// gt_ind_hetero + alt_freq_dip_pseudo_cpp + the NA row of big_counts in one pass
+// (src/gt_ind_hetero.cpp:12-42, src/alt_freq_dip_pseudo_cpp.cpp:8-58, R/loci_missingness.R:49-60).
+// [[Rcpp::export]]
+List gpu_scan(Environment BM, const IntegerVector& rowInd, const IntegerVector& colInd, const NumericVector& ploidy,
+              bool as_counts = false, int device = 0) {
+  const int n = rowInd.size(), m = colInd.size();
+  tpg_job job; std::string path;
+  fill_job(job, BM, rowInd, colInd, TPG_STAT_AS, 1, true, device, path);
+  NumericVector code = BM["code256"];          // these callers DO decode through code256
+  IntegerVector het(n), na(n), loc_na(m);
+  NumericVector loc0(m), loc1(m);
+  char err[1024] = {0};
+  if (tpg_scan(&job, code.begin(), ploidy.begin(), as_counts ? 1 : 0, het.begin(), na.begin(), loc0.begin(), loc1.begin(),
+               loc_na.begin(), nullptr, err, sizeof err) != TPG_OK)
+    stop("tidypopgen GPU backend: %s", err);
+  return List::create(_["het_n"] = het, _["na_n"] = na, _[as_counts ? "n_alt" : "freq"] = loc0, _["n_valid"] = loc1,
+                      _["n_na"] = loc_na);
+}

@@ -473,7 +473,10 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   // caller's zeroing of the counts, a previous job's finish) — cheap, and keeps jobs ordered.
   cudaEvent_t ev_start = B.ev(false);
   TPG_CUDA_OK(cudaEventRecord(ev_start, ctx->s_compute), E);
-  TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_decode, ev_start, 0), E);
+  // one device-resident chunk: nothing to overlap, so decode runs on the compute stream itself and
+  // the step pays no cross-stream event hops
+  cudaStream_t s_dec = (n_chunks == 1 && on_device) ? ctx->s_compute : ctx->s_decode;
+  TPG_CUDA_OK(cudaStreamWaitEvent(s_dec, ev_start, 0), E);
   std::vector<Ctx::ChunkEv>& tm = ctx->pend_ev;
   tm.assign(n_chunks, Ctx::ChunkEv{});
   int64_t macs = 0;
@@ -605,7 +608,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       TPG_CUDA_OK(cudaEventRecord(tm[c].c1, ctx->s_copy), E);
       TPG_CUDA_OK(cudaEventRecord(ev_h2d_done[b], ctx->s_copy), E);
       if (!use_direct) TPG_CUDA_OK(cudaEventRecord(ev_pin_free[n_staged++ & 1], ctx->s_copy), E);
-      TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_decode, ev_h2d_done[b], 0), E);
+      TPG_CUDA_OK(cudaStreamWaitEvent(s_dec, ev_h2d_done[b], 0), E);
       {
         const double t1 = now_ms();
         link_free_at = std::max(link_free_at, t1) + double(h2d_bytes) / (link_gbps * 1e6);
@@ -624,23 +627,23 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     if (scan) {  // one pass over the chunk's bytes; no planes, no products
       ScanArgs sa = *scan;
       sa.alt2 += k0; sa.valid += k0; sa.na_l += k0;
-      TPG_CUDA_OK(cudaEventRecord(tm[c].d0, ctx->s_decode), E);
-      rc = launch_scan(ctx, da, sa, ctx->s_decode, E);
+      TPG_CUDA_OK(cudaEventRecord(tm[c].d0, s_dec), E);
+      rc = launch_scan(ctx, da, sa, s_dec, E);
       if (rc) return rc;
-      TPG_CUDA_OK(cudaEventRecord(tm[c].d1, ctx->s_decode), E);
-      TPG_CUDA_OK(cudaEventRecord(ev_dec_done[b], ctx->s_decode), E);
+      TPG_CUDA_OK(cudaEventRecord(tm[c].d1, s_dec), E);
+      TPG_CUDA_OK(cudaEventRecord(ev_dec_done[b], s_dec), E);
       TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ev_dec_done[b], 0), E);
       TPG_CUDA_OK(cudaEventRecord(tm[c].g0, ctx->s_compute), E);
       TPG_CUDA_OK(cudaEventRecord(tm[c].g1, ctx->s_compute), E);
       continue;
     }
     // planes[b] were last read by the gram of chunk c-2
-    if (c >= 2) TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_decode, ev_gram_done[b], 0), E);
-    TPG_CUDA_OK(cudaEventRecord(tm[c].d0, ctx->s_decode), E);
-    rc = launch_decode(ctx, da, ctx->s_decode, E);
+    if (c >= 2) TPG_CUDA_OK(cudaStreamWaitEvent(s_dec, ev_gram_done[b], 0), E);
+    TPG_CUDA_OK(cudaEventRecord(tm[c].d0, s_dec), E);
+    rc = launch_decode(ctx, da, s_dec, E);
     if (rc) return rc;
-    TPG_CUDA_OK(cudaEventRecord(tm[c].d1, ctx->s_decode), E);
-    TPG_CUDA_OK(cudaEventRecord(ev_dec_done[b], ctx->s_decode), E);
+    TPG_CUDA_OK(cudaEventRecord(tm[c].d1, s_dec), E);
+    TPG_CUDA_OK(cudaEventRecord(ev_dec_done[b], s_dec), E);
     TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ev_dec_done[b], 0), E);
 
     GramArgs ga;
