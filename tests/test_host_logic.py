@@ -96,3 +96,21 @@ def test_pk2_packer_matches_numpy(shape):
     out = np.zeros((ncol, st), np.uint8)
     lib.tpg_pk2_pack_host(raw.ctypes.data + r0, nrow, span, ncol, out.ctypes.data)
     assert np.array_equal(out, pk2_ref(raw, nrow, ncol, r0, span))
+
+
+def test_consumers_argument_checks():
+    """Host-side checks of the consumers' mirror (no device needed to fail them)."""
+    with pytest.raises(TypeError, match="kings_threshold"):
+        tpg.filter_high_relatedness(np.eye(3))
+    with pytest.raises(ValueError, match="square"):
+        tpg.filter_high_relatedness(np.zeros((2, 3)), kings_threshold=0.1)
+    gt = tpg.gen_tibble(TOY_3x6)
+    with pytest.raises(ValueError, match="grouped gen_tibble"):
+        tpg.pop_fst(gt)
+    with pytest.raises(ValueError, match="should be 'WG17'"):
+        tpg.indiv_inbreeding(gt, method="x")
+    with pytest.raises(ValueError, match="kings_threshold must be a numeric"):
+        tpg.qc_report_indiv(gt, kings_threshold="third")
+    gt.population = ["a", "a", "b"]
+    with pytest.raises(ValueError, match="can not be provided for grouped_df"):
+        tpg.indiv_inbreeding(gt, allele_sharing_mat=np.eye(3))

@@ -272,13 +272,15 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_const
       uint32_t phase = 0;
       for (int it = cluster; it < p.n_items; it += n_clusters) {
         const WorkItem w = p.items[it];
-        const int prod = w.prod_ti & 15, ti = w.prod_ti >> 4, tj = w.tj;
+        const int prod = w.prod_ti & 15, ti = w.prod_ti >> 8, tj = w.tj;
+        const int ncols = (((w.prod_ti >> 4) & 15) + 1) * 16;  // N of this tile's MMAs (trimmed last tile column)
         int pa, pb;
         prod_planes(prod, pa, pb);
         const CUtensorMap* ma = pa == 0 ? &tm_d : pa == 1 ? &tm_nm : &tm_h1;
         const CUtensorMap* mb = pb == 0 ? &tm_d : pb == 1 ? &tm_nm : &tm_h1;
         const int row_a = ti * kPairTileM + int(rank) * 128;
-        const int row_b = tj * kTileN + int(rank) * 128;
+        // CTA r supplies B rows [r N/2, (r+1) N/2) of the tile; the box is 128 rows, the MMA reads N/2
+        const int row_b = tj * kTileN + int(rank) * (ncols / 2);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
           uint8_t* sa = smem + stage * kPairStageBytes;
@@ -301,7 +303,7 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_const
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA only)
     if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_i8(kPairTileM, kTileN, !kMajorK);
+      constexpr uint32_t idesc0 = make_idesc_i8(kPairTileM, 0, !kMajorK);
       constexpr uint32_t lbo = kMajorK ? 16u : uint32_t(kHalfBytes);  // one 128-row block: unused
       constexpr uint32_t sbo = 1024u;
       constexpr uint32_t kstep = kMajorK ? (32u >> 4) : (4096u >> 4);
@@ -311,6 +313,8 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_const
       uint32_t acc_phase = 0;
       for (int it = cluster; it < p.n_items; it += n_clusters) {
         const WorkItem w = p.items[it];
+        const uint32_t ncols = (((uint32_t(w.prod_ti) >> 4) & 15u) + 1u) * 16u;
+        const uint32_t idesc = idesc0 | ((ncols >> 3) << 17);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(acc * kTileN);
@@ -341,7 +345,8 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_const
     uint32_t acc_phase = 0;
     for (int it = cluster; it < p.n_items; it += n_clusters) {
       const WorkItem w = p.items[it];
-      const int prod = w.prod_ti & 15, ti = w.prod_ti >> 4, tj = w.tj;
+      const int prod = w.prod_ti & 15, ti = w.prod_ti >> 8, tj = w.tj;
+      const int ncols = (((w.prod_ti >> 4) & 15) + 1) * 16;   // multiple of 32 (host)
       const bool sym = prod != TPG_MAT_HN;
       mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
       tc_fence_after();
@@ -350,11 +355,11 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_const
       int32_t* cbase = p.counts + int64_t(prod) * p.mat_stride + i;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kTileN);
 #pragma unroll 1
-      for (int c = 0; c < kTileN; c += 32) {
+      for (int c = 0; c < ncols; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + uint32_t(c), v);
         tmem_ld_wait();
-        if (c + 32 == kTileN) {  // accumulator drained: hand it back (to the leader's barrier)
+        if (c + 32 == ncols) {   // accumulator drained: hand it back (to the leader's barrier)
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
@@ -499,12 +504,23 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   if (tiles.empty()) { if (macs_out) *macs_out = 0; return TPG_OK; }
 
   const int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units);
-  if (macs_out) *macs_out = int64_t(tiles.size()) * tile_m * kTileN * a.lc_pad;
 
   // The work list only depends on the geometry; chunks of equal size reuse the upload.
-  char key[160];
-  snprintf(key, sizeof key, "%lld/%lld/%d/%d/%d/%d/%d", (long long)a.n_pad, (long long)a.lc_pad,
-           a.prod_mask, a.shard_rank, a.shard_world, ks, tile_m);
+  const bool trim_n = pair && !getenv("TPG_GRAM_NO_TRIM");
+  // N of a tile's MMAs: the pair kernel trims the last tile column to its valid columns (multiple of 32)
+  auto tile_ncols = [&](int tj) {
+    if (!trim_n) return int(kTileN);
+    const int64_t valid = std::min<int64_t>(kTileN, a.n - int64_t(tj) * kTileN);
+    return int(std::max<int64_t>(32, (valid + 31) / 32 * 32));
+  };
+  if (macs_out) {
+    int64_t cells = 0;
+    for (const T& t : tiles) cells += int64_t(tile_m) * tile_ncols(t.tj);
+    *macs_out = cells * a.lc_pad;
+  }
+  char key[200];
+  snprintf(key, sizeof key, "%lld/%lld/%lld/%d/%d/%d/%d/%d/%d", (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad,
+           a.prod_mask, a.shard_rank, a.shard_world, ks, tile_m, int(trim_n));
   if (ctx->items_key != key) {
     std::vector<WorkItem>& items = ctx->h_items;
     items.clear();
@@ -512,7 +528,12 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
     for (int s = 0; s < ks; ++s) {
       const int32_t kb0 = int32_t(kblocks * s / ks), kb1 = int32_t(kblocks * (s + 1) / ks);
       if (kb1 <= kb0) continue;
-      for (const T& t : tiles) items.push_back({int32_t(t.prod | (t.ti << 4)), t.tj, kb0, kb1});
+      for (const T& t : tiles) {
+        if (!pair) { items.push_back({int32_t(t.prod | (t.ti << 4)), t.tj, kb0, kb1}); continue; }
+        // pair kernel: N of the MMAs trimmed to the valid columns of the last tile column (multiple of 32)
+        const int ncols = tile_ncols(t.tj);
+        items.push_back({int32_t(t.prod | ((ncols / 16 - 1) << 4) | (t.ti << 8)), t.tj, kb0, kb1});
+      }
     }
     if (items.size() > ctx->d_items_cap) {
       TPG_CUDA_OK(cudaStreamSynchronize(st), E);
