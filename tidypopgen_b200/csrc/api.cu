@@ -1004,7 +1004,9 @@ int tpg_accumulate(tpg_ctx* h, const tpg_job* job, int32_t* d_counts, tpg_stats*
   tpg_stats* st = stats ? stats : &local;
   Ctx* c = reinterpret_cast<Ctx*>(h);
   const int64_t l0 = c->launches;
-  int rc = accumulate_impl(c, job, d_counts, st, E);
+  // TPG_FLAG_ASYNC: enqueue only — the device work is collected (and its stage times folded into
+  // the result's stats) by the tpg_finish that follows on the same context
+  int rc = accumulate_impl(c, job, d_counts, st, E, /*defer=*/job && (job->flags & TPG_FLAG_ASYNC));
   st->n_launches += c->launches - l0;
   return rc;
 }

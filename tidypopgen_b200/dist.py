@@ -138,12 +138,19 @@ def pairwise_sharded(engine, X, ind_row=None, ind_col=None, stat: int = L.STAT_K
                              pad_quirk=pad_quirk, src=src, gpu_chunk_loci=gpu_chunk_loci, flags=flags,
                              shard_mode=shard, shard_rank=rank, shard_world=world)
     counts = engine.new_counts(n)
+    stream = getattr(engine, "stream", None)
+    if mode == "loci" and stream is not None:
+        job.flags |= L.FLAG_ASYNC  # accumulate -> all-reduce -> finish queue up on one stream, one wait at the end
+    if stream is not None:
+        stream.wait_stream(torch.cuda.current_stream(counts.device))  # the zero fill of `counts`
     engine.accumulate(job, counts)
     if mode == "loci":
         # the one exchange step of the path: integer sum of the count matrices
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
-        if counts.is_cuda:
-            torch.cuda.current_stream(counts.device).synchronize()
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
         job.shard_mode = L.SHARD_NONE  # finish sees the whole job (m = all loci, pad constant once)
         job.shard_world = 1
         job.shard_rank = 0
