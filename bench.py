@@ -29,6 +29,7 @@ N_IND, M_LOCI, MISSING, SEED = 929, 650_000, 0.02, 20260002
 WORKLOAD = "HGDP-shape synthetic 929 x 650000, 2% missing, pairwise_king (BASELINE.json configs[1])"
 METRIC = "pairwise_king pair-SNP ops/sec (n^2*m)"
 UNIT = "pair-SNP/s"
+SYNC_PATH = os.environ.get("TPG_BENCH_SYNC") == "1"
 KING_INT8_OPS_PER_PAIRSNP = 4.0   # 2.0 MAC: DD (upper) + NN (upper) + HN (full) — DESIGN.md "Algebra"
 DECODE_BYTES_PER_GENOTYPE = 4.0   # 1 read + 3 plane bytes written
 
@@ -47,7 +48,10 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clocks + throttle reasons DURING the timed region (B200_PROFILING.md), read through NVML
+    in-process (the library nvidia-smi itself uses): a `nvidia-smi` subprocess every few ms from
+    each of 8 ranks serialises on the driver and stalls everybody's launches.  Falls back to the
+    nvidia-smi query when pynvml is missing."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -56,17 +60,43 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:  # noqa: BLE001
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flag = lambda name: "Active" if r & getattr(n, name, 0) else "Not Active"  # noqa: E731
+        self.rows.append([str(self.index), str(sm), str(mx), "0",
+                          flag("nvmlClocksThrottleReasonHwSlowdown"), flag("nvmlClocksThrottleReasonHwThermalSlowdown"),
+                          flag("nvmlClocksThrottleReasonSwThermalSlowdown"), flag("nvmlClocksThrottleReasonSwPowerCap")])
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                for ln in out.strip().splitlines():
-                    self.rows.append([x.strip() for x in ln.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                    for ln in out.strip().splitlines():
+                        self.rows.append([x.strip() for x in ln.split(",")])
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02 if self.nvml is not None else 0.2)
 
     def summary(self):
         sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
@@ -74,7 +104,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({nm for r in self.rows if len(r) >= 8 for nm, v in zip(names, r[4:8]) if v == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "NVML" if self.nvml is not None else "nvidia-smi"}
 
 
 def measure_int8_library_peak(local):
@@ -206,8 +236,13 @@ def run_b200(args, rank, world, local):
             st = L.Stats()
             res.stats = L.Stats()  # tpg_finish adds the collected stage times to what it finds
             L.check(lib.tpg_accumulate(eng.ctx.handle, C.byref(job), counts.data_ptr(), C.byref(st), eb, len(eb)), eb)
-            with torch.cuda.stream(eng.stream):
+            if SYNC_PATH:   # A/B switch: host waits around the all-reduce (the round's first scheme)
+                eng.stream.synchronize()
                 dist.all_reduce(counts)
+                torch.cuda.current_stream().synchronize()
+            else:
+                with torch.cuda.stream(eng.stream):
+                    dist.all_reduce(counts)
             L.check(lib.tpg_finish(eng.ctx.handle, C.byref(job), counts.data_ptr(), C.byref(res), eb, len(eb)), eb)
             st.ms_decode, st.ms_gram, st.ms_finish = res.stats.ms_decode, res.stats.ms_gram, res.stats.ms_finish
             n_l = st.n_launches + res.stats.n_launches + 1  # + the counts fill
@@ -236,6 +271,8 @@ def run_b200(args, rank, world, local):
     e1.record(eng.stream)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
+    if os.environ.get("TPG_BENCH_DEBUG"):
+        print(f"[rank {rank}] {float(ms.item()) / args.steps:.3f} ms/step (device events)", file=sys.stderr, flush=True)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms.item()) / args.steps
