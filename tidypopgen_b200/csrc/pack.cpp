@@ -71,6 +71,11 @@ int HostPool::max_threads() {
     const int v = atoi(e);
     if (v >= 1) return v;
   }
+  // one process per GPU under torchrun: the ranks of a node share its cores
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
+    const int w = atoi(e);
+    if (w > 1) hw = std::max(2u, hw / unsigned(w));
+  }
   return int(hw > 32 ? 32 : hw);
 }
 
