@@ -141,6 +141,10 @@ def test_partitions_cover_exactly():
         tot = sum(tdist.owned_mask(n, r, w).astype(int) for r in range(w))
         assert (tot == 1).all()
         nb = (n + 255) // 256
-        cnt = np.bincount([tdist.block_owner(i, j, nb, w) for i in range(nb) for j in range(i, nb)], minlength=w)
-        assert cnt.max() - cnt.min() <= 1  # round-robin balance
+        r = tdist.shard_region_blocks(nb, w)          # ownership is dealt in r x r block regions
+        nr = (nb + r - 1) // r
+        cnt = np.bincount([tdist.block_owner(i * r, j * r, nb, w) for i in range(nr) for j in range(i, nr)], minlength=w)
+        assert cnt.max() - cnt.min() <= 1  # round-robin balance over the regions
+        assert nr * (nr + 1) // 2 >= 8 * w or r == 1
+    assert tdist.shard_region_blocks(196, 8) == 4 and tdist.shard_region_blocks(24, 8) == 2 and tdist.shard_region_blocks(4, 2) == 1
     assert tdist.choose_mode(929, 8) == "loci" and tdist.choose_mode(50000, 8) == "tiles"

@@ -120,14 +120,33 @@ struct GramArgs {
 };
 int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out, const Err& E);
 
-// Tile sharding: output blocks of 256x256 (bi <= bj, nblocks per side) are dealt round-robin
-// over the row-major order of the upper triangle; identical on every rank, host and device.
+// Tile sharding: the 256x256 output blocks (bi <= bj, nblocks per side) are grouped into square
+// REGIONS of R x R blocks and the regions of the upper triangle are dealt round-robin in row-major
+// order; identical on every rank, host and device.  A rank therefore owns whole 1024 x 1024
+// neighbourhoods (R = 4) — the unit whose operand panels the Gram scheduler keeps in L2; owning
+// scattered single blocks made every tile fetch its panels from HBM (C4 on 8 GPUs: 1752 TOP/s
+// per GPU against 2945 for one GPU on the whole matrix).  R shrinks for small matrices so that
+// there are still at least 8 regions per rank.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline int64_t shard_region_blocks(int64_t nblocks, int world) {
+  int64_t r = 4;
+  while (r > 1) {
+    const int64_t nr = (nblocks + r - 1) / r;
+    if (nr * (nr + 1) / 2 >= int64_t(8) * world) break;
+    r >>= 1;
+  }
+  return r;
+}
 #ifdef __CUDACC__
 __host__ __device__
 #endif
 inline bool block_owned(int64_t bi, int64_t bj, int64_t nblocks, int rank, int world) {
   if (world <= 1) return true;
-  const int64_t idx = bi * nblocks - bi * (bi - 1) / 2 + (bj - bi);
+  const int64_t r = shard_region_blocks(nblocks, world);
+  const int64_t ri = bi / r, rj = bj / r, nr = (nblocks + r - 1) / r;
+  const int64_t idx = ri * nr - ri * (ri - 1) / 2 + (rj - ri);
   return int(idx % world) == rank;
 }
 

@@ -52,19 +52,36 @@ def loci_slice(m: int, rank: int, world: int) -> tuple[int, int]:
     return m * rank // world, m * (rank + 1) // world
 
 
+def shard_region_blocks(nblocks: int, world: int) -> int:
+    """Side (in 256-blocks) of the square regions tile ownership is dealt in — identical to
+    shard_region_blocks() in csrc/internal.h: 4 (1024 x 1024 neighbourhoods, what the Gram
+    scheduler keeps in L2), smaller while a rank would get fewer than 8 regions."""
+    r = 4
+    while r > 1:
+        nr = (nblocks + r - 1) // r
+        if nr * (nr + 1) // 2 >= 8 * world:
+            break
+        r >>= 1
+    return r
+
+
 def block_owner(bi: int, bj: int, nblocks: int, world: int) -> int:
     """Owner rank of output block (bi <= bj) of the 256 x 256 block grid — identical to
     block_owned() in csrc/internal.h."""
-    idx = bi * nblocks - bi * (bi - 1) // 2 + (bj - bi)
+    r = shard_region_blocks(nblocks, world)
+    ri, rj, nr = bi // r, bj // r, (nblocks + r - 1) // r
+    idx = ri * nr - ri * (ri - 1) // 2 + (rj - ri)
     return idx % world
 
 
 def owned_mask(n: int, rank: int, world: int) -> np.ndarray:
     """Boolean n x n mask of the entries rank finishes in tiles mode (block + mirror)."""
     nb = (n + 255) // 256
-    b = np.arange(n) // 256
+    r = shard_region_blocks(nb, world)
+    nr = (nb + r - 1) // r
+    b = np.arange(n) // 256 // r
     bi, bj = np.minimum.outer(b, b), np.maximum.outer(b, b)
-    idx = bi * nb - bi * (bi - 1) // 2 + (bj - bi)
+    idx = bi * nr - bi * (bi - 1) // 2 + (bj - bi)
     return (idx % world) == rank
 
 
