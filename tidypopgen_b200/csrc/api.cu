@@ -546,39 +546,38 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
         const uint8_t* base = src.base;
         const Plan* plp = &pl;
         if (pack_ok) {
-         packed = true;
-         if (use_pread) {
-          // .bk file, contiguous columns: pread() blocks of whole columns into a per-thread buffer
-          // that stays in L2 and pack from there — a fresh mmap pays one page fault per 4 KiB.
           packed = true;
-          const int fd = src.fd;
-          const int64_t cpb = std::max<int64_t>(1, (int64_t(1) << 20) / nrow);  // columns per block
-          std::atomic<int>* bad = &io_err;
-          parallel_for(lcc, std::max<int64_t>(cpb, (int64_t(1) << 20) / span), [=](int64_t a, int64_t e) {
-            static thread_local std::vector<uint8_t> buf;
-            if (int64_t(buf.size()) < cpb * nrow) buf.resize(size_t(cpb * nrow));
-            for (int64_t k = k0 + a; k < k0 + e; k += cpb) {
-              const int64_t nc = std::min<int64_t>(cpb, k0 + e - k);
-              const int64_t off = (plp->col0 + k) * nrow;
-              int64_t got = 0;
-              while (got < nc * nrow) {
-                const ssize_t r = pread(fd, buf.data() + got, size_t(nc * nrow - got), off_t(off + got));
-                if (r <= 0) { bad->store(1); return; }
-                got += r;
+          if (use_pread) {
+            // .bk file, contiguous columns: pread() blocks of whole columns into a per-thread buffer
+            // that stays in L2 and pack from there — a fresh mmap pays one page fault per 4 KiB.
+            const int fd = src.fd;
+            const int64_t cpb = std::max<int64_t>(1, (int64_t(1) << 20) / nrow);  // columns per block
+            std::atomic<int>* bad = &io_err;
+            parallel_for(lcc, std::max<int64_t>(cpb, (int64_t(1) << 20) / span), [=](int64_t a, int64_t e) {
+              static thread_local std::vector<uint8_t> buf;
+              if (int64_t(buf.size()) < cpb * nrow) buf.resize(size_t(cpb * nrow));
+              for (int64_t k = k0 + a; k < k0 + e; k += cpb) {
+                const int64_t nc = std::min<int64_t>(cpb, k0 + e - k);
+                const int64_t off = (plp->col0 + k) * nrow;
+                int64_t got = 0;
+                while (got < nc * nrow) {
+                  const ssize_t r = pread(fd, buf.data() + got, size_t(nc * nrow - got), off_t(off + got));
+                  if (r <= 0) { bad->store(1); return; }
+                  got += r;
+                }
+                for (int64_t j = 0; j < nc; ++j)
+                  pk2_pack_column(buf.data() + j * nrow + rlo, span, stage + (k - k0 + j) * pk_stride, pk_stride);
               }
-              for (int64_t j = 0; j < nc; ++j)
-                pk2_pack_column(buf.data() + j * nrow + rlo, span, stage + (k - k0 + j) * pk_stride, pk_stride);
-            }
-          });
-          if (io_err.load()) return E.fail(TPG_ERR_IO, "reading '%s' failed: %s", job->bk_path, strerror(errno));
-         } else {
-          parallel_for(lcc, std::max<int64_t>(1, (int64_t(1) << 20) / span), [=](int64_t a, int64_t e) {
-            for (int64_t k = k0 + a; k < k0 + e; ++k) {
-              const int64_t col = plp->cols_contig ? plp->col0 + k : plp->cols0[k];
-              pk2_pack_column(base + col * nrow + rlo, span, stage + (k - k0) * pk_stride, pk_stride);
-            }
-          });
-         }
+            });
+            if (io_err.load()) return E.fail(TPG_ERR_IO, "reading '%s' failed: %s", job->bk_path, strerror(errno));
+          } else {
+            parallel_for(lcc, std::max<int64_t>(1, (int64_t(1) << 20) / span), [=](int64_t a, int64_t e) {
+              for (int64_t k = k0 + a; k < k0 + e; ++k) {
+                const int64_t col = plp->cols_contig ? plp->col0 + k : plp->cols0[k];
+                pk2_pack_column(base + col * nrow + rlo, span, stage + (k - k0) * pk_stride, pk_stride);
+              }
+            });
+          }
           h2d_bytes = lcc * pk_stride;
           col_stride = pk_stride;
           const double dt = now_ms() - t0;
