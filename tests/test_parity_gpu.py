@@ -462,6 +462,70 @@ def test_loci_and_tile_sharding_emulated(world):
     assert same(merged, ref_king)
 
 
+def _king_pair(gi, gj):
+    """KING-robust of one pair from raw bytes, the reference's arithmetic (src/snp_king.cpp:45-72,
+    R/snp_king.R:82-91)."""
+    h0i, h1i, h2i, vi = gi == 0, gi == 1, gi == 2, gi <= 2
+    h0j, h1j, h2j, vj = gj == 0, gj == 1, gj == 2, gj <= 2
+    K = float((h1i & h1j).sum()) - 2.0 * float((h0i & h2j).sum() + (h2i & h0j).sum())
+    Ni, Nj = float((h1i & vj).sum()), float((vi & h1j).sum())
+    pm = min(Ni, Nj)
+    with np.errstate(all="ignore"):
+        return np.float64(K) / np.float64(2 * pm) + 0.5 - np.float64(0.25 * (Ni + Nj)) / np.float64(pm)
+
+
+def test_biobank_regime_sampled_pairs_and_region_sharding():
+    """The many-tiles regime of BASELINE configs[3] at a size the suite can afford (20,000 x 40,000:
+    79 x 79 blocks, 20 x 20 ownership regions): whole matrix on one GPU, and ranks 0 / 3 / 7 of an
+    8-way tile-sharded run emulated on the same GPU.  The oracle is out of reach, so sampled entries
+    are checked EXACTLY against the reference formula on the two genotype columns; owned regions must
+    equal the unsharded result bit for bit and everything else must stay untouched."""
+    import torch
+    from tidypopgen_b200 import dist as tdist
+    n, m, world = 20000, 40000, 8
+    eng = tdist.CudaEngine(0)
+    eb = L.errbuf()
+    raw = torch.empty(n * m + 64, dtype=torch.uint8, device="cuda")
+    L.check(L.lib().tpg_synth_fill(eng.ctx.handle, raw.data_ptr(), n, m, 0, 20260004, 0.01, 0, eb, len(eb)), eb)
+    X = tpg.FBMCode256.__new__(tpg.FBMCode256)
+    X.backingfile, X.nrow, X.ncol, X.code256 = "<device>", n, m, None
+    src = (L.SRC_DEVICE, raw.data_ptr(), raw)
+    from tidypopgen_b200 import snp
+    def run(shard, rank):
+        job, keep = snp.make_job(X, None, None, L.STAT_KING, snp.block_size(n), src=src,
+                                 shard_mode=L.SHARD_TILES if shard else L.SHARD_NONE, shard_rank=rank,
+                                 shard_world=world if shard else 1)
+        counts = eng.new_counts(n)
+        eng.accumulate(job, counts)
+        out, _, _ = eng.finish(job, counts, n, False, on_device=True)
+        del counts
+        return out                                   # torch [i, j] view of the column-major result
+    full = run(False, 0)
+    cols = raw[: n * m].view(m, n)
+    rng = np.random.default_rng(4)
+    for k in range(48):
+        i, j = (int(x) for x in rng.integers(0, n, 2))
+        if k % 6 == 0:
+            j = i
+        ref = _king_pair(cols[:, i].cpu().numpy(), cols[:, j].cpu().numpy())
+        got = full[i, j].item()
+        assert got == ref or (np.isnan(got) and np.isnan(ref)), (i, j)
+        assert full[j, i].item() == got or np.isnan(got)
+    nb = (n + 255) // 256
+    assert tdist.shard_region_blocks(nb, world) == 4
+    blk = torch.arange(n, device="cuda") // 256 // 4
+    bi, bj = torch.minimum(blk[:, None], blk[None, :]), torch.maximum(blk[:, None], blk[None, :])
+    nr = (nb + 3) // 4
+    owner = (bi * nr - bi * (bi - 1) // 2 + (bj - bi)) % world
+    del bi, bj
+    for rank in (0, 3, 7):
+        part = run(True, rank)
+        mine = owner == rank
+        assert torch.equal(part[mine].nan_to_num(-9.0), full[mine].nan_to_num(-9.0))
+        assert bool((part[~mine] == 0).all())
+        del part, mine
+
+
 def test_two_gpus_nccl_if_available():
     """Real NCCL run (torchrun, 2 ranks) when the box has >= 2 GPUs; skipped on the 1-GPU box."""
     import subprocess

@@ -102,7 +102,13 @@ class CudaEngine:
     def new_counts(self, n: int) -> torch.Tensor:
         return torch.zeros(int(L.lib().tpg_counts_elems(n)), dtype=torch.int32, device=f"cuda:{self.device}")
 
+    def _order_after_torch(self):
+        # buffers handed to the library are filled (zeroed) by torch on ITS current stream; the
+        # library's kernels run on the context's stream, so order that stream after torch's
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+
     def accumulate(self, job, counts: torch.Tensor):
+        self._order_after_torch()
         st = L.Stats()
         eb = L.errbuf()
         rc = L.lib().tpg_accumulate(self.ctx.handle, C.byref(job), counts.data_ptr(), C.byref(st), eb, len(eb))
@@ -123,6 +129,8 @@ class CudaEngine:
             res.out0 = out0.ctypes.data
             res.out1 = out1.ctypes.data if want_out1 else None
         res.out_on_device = 1 if on_device else 0
+        if on_device:
+            self._order_after_torch()
         eb = L.errbuf()
         rc = L.lib().tpg_finish(self.ctx.handle, C.byref(job), counts.data_ptr(), C.byref(res), eb, len(eb))
         L.check(rc, eb)
@@ -158,8 +166,6 @@ def pairwise_sharded(engine, X, ind_row=None, ind_col=None, stat: int = L.STAT_K
     stream = getattr(engine, "stream", None)
     if mode == "loci" and stream is not None:
         job.flags |= L.FLAG_ASYNC  # accumulate -> all-reduce -> finish queue up on one stream, one wait at the end
-    if stream is not None:
-        stream.wait_stream(torch.cuda.current_stream(counts.device))  # the zero fill of `counts`
     engine.accumulate(job, counts)
     if mode == "loci":
         # the one exchange step of the path: integer sum of the count matrices
