@@ -273,6 +273,7 @@ def test_decode_planes_kernel(k_major, gather):
     d_rows, d_cols = torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda()
     ps = n_pad * lc_pad
     d_planes = torch.full((3 * ps,), 77, dtype=torch.int8, device="cuda")
+    torch.cuda.synchronize()  # the library runs on its own non-blocking stream
     eb = L.errbuf()
     L.check(L.lib().tpg_decode_planes(ctx.handle, d_raw.data_ptr(), raw.size, nrow,
                                       d_rows.data_ptr() if gather else None, int(rows[0]), n, n_pad,
@@ -299,6 +300,7 @@ def test_gram_kernel(k_major, shape, ctas):
     host = np.stack([p if k_major else p.T for p in planes]).copy()
     d_planes = torch.from_numpy(host.reshape(-1)).cuda()
     d_counts = torch.zeros(4 * n_pad * n_pad, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()  # the library runs on its own non-blocking stream
     eb, ms = L.errbuf(), C.c_float(0)
     for rep in range(2):  # two launches accumulate
         L.check(L.lib().tpg_gram(ctx.handle, d_planes.data_ptr(), n_pad * lc_pad, n_pad, lc_pad,
@@ -328,6 +330,7 @@ def test_decode_planes_pk2_kernel(shape):
     d_raw = torch.from_numpy(packed.reshape(-1)).cuda()
     ps = n_pad * lc_pad
     d_planes = torch.full((3 * ps,), 77, dtype=torch.int8, device="cuda")
+    torch.cuda.synchronize()  # the library runs on its own non-blocking stream
     eb = L.errbuf()
     L.check(lib.tpg_decode_planes(ctx.handle, d_raw.data_ptr(), packed.size, st, None, 0, n, n_pad,
                                   None, 0, lc, lc_pad, d_planes.data_ptr(), ps, 4, eb, len(eb)), eb)
@@ -370,6 +373,7 @@ def test_synth_device_equals_host():
     ctx = L.Context(0)
     nrow, ncol = 301, 999
     d = torch.zeros(nrow * ncol, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()  # the library runs on its own non-blocking stream
     eb = L.errbuf()
     for mode in (0, 1, 2):
         L.check(L.lib().tpg_synth_fill(ctx.handle, d.data_ptr(), nrow, ncol, 17, 2026, 0.1, mode, eb, len(eb)), eb)
