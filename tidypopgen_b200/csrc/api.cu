@@ -707,6 +707,14 @@ static int results_to_host(Ctx* ctx, const void* const* dev, void* const* host, 
   int64_t idx = 0;
   for (int o = 0; o < count && rc == TPG_OK; ++o) {
     if (!host[o]) continue;
+    // A fresh result matrix is untouched memory: the copy below is bound by first-touch page
+    // faults (4 KiB each).  Ask for transparent huge pages on its 2 MiB-aligned interior; the
+    // call is advisory and fails harmlessly where THP is off.
+    if (bytes >= (size_t(8) << 20) && !getenv("TPG_NO_THP")) {
+      const uintptr_t lo = (reinterpret_cast<uintptr_t>(host[o]) + (size_t(2) << 20) - 1) & ~((uintptr_t(2) << 20) - 1);
+      const uintptr_t hi = (reinterpret_cast<uintptr_t>(host[o]) + bytes) & ~((uintptr_t(2) << 20) - 1);
+      if (hi > lo) madvise(reinterpret_cast<void*>(lo), size_t(hi - lo), MADV_HUGEPAGE);
+    }
     for (size_t off = 0; off < bytes && rc == TPG_OK; off += piece, ++idx) {
       const int b = int(idx & 1);
       const size_t len = std::min(piece, bytes - off);
