@@ -190,7 +190,8 @@ int tpg_pairwise(const tpg_job* job, tpg_result* res, char* err, size_t errlen);
 /* The same job spread over several GPUs of one box from ONE process (what an R session
  * needs): one host thread per device accumulates its shard — shard_mode TPG_SHARD_LOCI
  * (contiguous slices of ind_col) or TPG_SHARD_TILES (owned 256x256 output blocks, all loci);
- * TPG_SHARD_NONE picks by n — the int32 count matrices are summed onto devices[0] over
+ * TPG_SHARD_NONE picks loci while a device's count matrices stay within 64 GB — the int32 count
+ * matrices are summed onto devices[0] by a pairwise tree of peer-reading add kernels over
  * NVLink and finished there.  Results are identical to the single-GPU job. */
 int tpg_pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* devices, int32_t ndev,
                        int32_t shard_mode, char* err, size_t errlen);

@@ -853,7 +853,10 @@ static int pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* de
   const int64_t n = job->ind_row ? job->n : job->nrow_total;
   if (n <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row");
   if (shard_mode != TPG_SHARD_LOCI && shard_mode != TPG_SHARD_TILES)
-    shard_mode = n <= 30000 ? TPG_SHARD_LOCI : TPG_SHARD_TILES;
+    // Host bytes are the scarce resource of a one-process job: loci sharding reads (and packs) every
+    // byte once, tile sharding once per device.  So loci while the four int32 count matrices of a
+    // device stay within 64 GB (n <= ~63,000), tiles beyond.
+    shard_mode = tpg_counts_elems(n) * int64_t(sizeof(int32_t)) <= (int64_t(64) << 30) ? TPG_SHARD_LOCI : TPG_SHARD_TILES;
   const double t_begin = now_ms();
   memset(&res->stats, 0, sizeof res->stats);
   const size_t celems = size_t(tpg_counts_elems(n));
@@ -894,27 +897,58 @@ static int pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* de
   for (int r = 0; r < ndev; ++r)
     if (rcs[r]) return E.fail(rcs[r], "device %d (rank %d): %s", devices[r], r, msgs[r].c_str());
 
-  // ---- sum the count matrices onto rank 0's device
+  // ---- sum the count matrices onto rank 0's device: a pairwise tree over NVLink.  In step s the
+  // device of rank r (r % 2s == 0) adds the matrices of rank r + s, reading them straight out of the
+  // peer's HBM inside the add kernel (peer access; no staging copy) — the pairs of a step run side
+  // by side on their own devices, so 8 ranks need 3 steps instead of 7 serial copy + add rounds.
+  // Without peer access between a pair (e.g. the same device listed twice) the pair falls back to a
+  // copy through a staging buffer.
   Ctx* c0 = ctxs[0];
-  TPG_CUDA_OK(cudaSetDevice(c0->device), E);
   const int mask = prod_mask_for(job->stat);
   const int64_t ld = tpg_counts_ld(n), ms = ld * ld;
   const double t_red = now_ms();
-  if (ndev > 1) {
-    int rc = ensure_slot(&c0->d_out[3], sizeof(int32_t) * size_t(ms), false, "reduction staging", E);
-    if (rc) return rc;
-    int32_t* tmp = static_cast<int32_t*>(c0->d_out[3].p);
-    for (int r = 1; r < ndev; ++r)
+  for (int step = 1; step < ndev; step <<= 1) {
+    std::vector<int> receivers;
+    for (int r = 0; r + step < ndev; r += 2 * step) receivers.push_back(r);
+    for (int r : receivers) {
+      Ctx* cr = ctxs[r];
+      Ctx* cp = ctxs[r + step];
+      TPG_CUDA_OK(cudaSetDevice(cr->device), E);
+      bool direct = cr->device != cp->device;
+      if (direct) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, cr->device, cp->device) != cudaSuccess || !can) direct = false;
+        if (direct) {
+          cudaError_t e = cudaDeviceEnablePeerAccess(cp->device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) direct = false;
+          cudaGetLastError();
+        }
+      }
+      if (cr->device == cp->device) direct = true;  // same device: the "peer" pointer is local
+      int32_t* tmp = nullptr;
+      if (!direct) {
+        int rc = ensure_slot(&cr->d_out[3], sizeof(int32_t) * size_t(ms), false, "reduction staging", E);
+        if (rc) return rc;
+        tmp = static_cast<int32_t*>(cr->d_out[3].p);
+      }
       for (int k = 0; k < TPG_NUM_COUNT_MATS; ++k) {
         if (!(mask & (1 << k))) continue;
-        const int32_t* from = static_cast<const int32_t*>(ctxs[r]->d_counts.p) + k * ms;
-        TPG_CUDA_OK(cudaMemcpyPeerAsync(tmp, c0->device, from, ctxs[r]->device, sizeof(int32_t) * size_t(ms),
-                                        c0->s_compute), E);
-        rc = launch_add_counts(c0, static_cast<int32_t*>(c0->d_counts.p) + k * ms, tmp, ms, c0->s_compute, E);
+        int32_t* mine = static_cast<int32_t*>(cr->d_counts.p) + k * ms;
+        const int32_t* theirs = static_cast<const int32_t*>(cp->d_counts.p) + k * ms;
+        if (!direct) {
+          TPG_CUDA_OK(cudaMemcpyPeerAsync(tmp, cr->device, theirs, cp->device, sizeof(int32_t) * size_t(ms), cr->s_compute), E);
+          theirs = tmp;
+        }
+        int rc = launch_add_counts(cr, mine, theirs, ms, cr->s_compute, E);
         if (rc) return rc;
       }
-    TPG_CUDA_OK(cudaStreamSynchronize(c0->s_compute), E);
+    }
+    for (int r : receivers) {  // the step is done when every pair is
+      TPG_CUDA_OK(cudaSetDevice(ctxs[r]->device), E);
+      TPG_CUDA_OK(cudaStreamSynchronize(ctxs[r]->s_compute), E);
+    }
   }
+  TPG_CUDA_OK(cudaSetDevice(c0->device), E);
   const double ms_reduce = now_ms() - t_red;
   tpg_job j0 = *job;
   j0.device = c0->device;
