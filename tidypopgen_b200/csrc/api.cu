@@ -964,6 +964,7 @@ static int pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* de
     res->stats.ms_gram = std::max(res->stats.ms_gram, sts[r].ms_gram);
     res->stats.bytes_h2d += sts[r].bytes_h2d;
     res->stats.n_chunks += sts[r].n_chunks;
+    res->stats.n_packed_chunks += sts[r].n_packed_chunks;
     res->stats.mma_macs += sts[r].mma_macs;
     res->stats.n_launches += sts[r].n_launches;
   }
