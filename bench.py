@@ -160,6 +160,11 @@ def run_reference(args, rank):
     from oracle import blas_baseline as B
     from oracle import oracle as O
 
+    # every host thread the process may use (torchrun exports OMP_NUM_THREADS=1 for its ranks)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:  # noqa: BLE001
+        pass
     bs = O.block_size(N_IND)                   # pairwise_king passes block_size(nrow(x)): 144,475
     iv = O.split_len(M_LOCI, bs)               # 5 blocks of 130,000 loci
     sample = int(iv[0, 2])
