@@ -188,7 +188,7 @@ def test_scans_example(example_gt):
 
 @pytest.mark.parametrize("case", [(929, 3000, "all", "all"), (300, 2000, "shuffle", "shuffle"), (1500, 700, "window", "every3"),
                                   (64, 5000, "dup", "all"), (2500, 513, "subset", "subset")])
-@pytest.mark.parametrize("src_kind", ["file", "device"])
+@pytest.mark.parametrize("src_kind", ["file", "device", "pinned"])
 def test_scans_random_parity(case, src_kind):
     import torch
     from test_parity_gpu import pick
@@ -204,6 +204,9 @@ def test_scans_random_parity(case, src_kind):
     if src_kind == "device":
         dev = torch.from_numpy(raw).cuda()
         kw["src"] = (L.SRC_DEVICE, dev.data_ptr(), dev)
+    if src_kind == "pinned":                      # DMA'd raw from the caller's pinned memory
+        pin = torch.from_numpy(raw).pin_memory()
+        kw["src"] = (L.SRC_HOST, pin.data_ptr(), pin)
     kw["gpu_chunk_loci"] = 512
     for code in (O.CODE_012, O.CODE_IMPUTE_PRED):
         r = tpg.scan_counts(X, rows, cols, code256=code, ploidy=ploidy, **kw)

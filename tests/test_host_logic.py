@@ -114,3 +114,27 @@ def test_consumers_argument_checks():
     gt.population = ["a", "a", "b"]
     with pytest.raises(ValueError, match="can not be provided for grouped_df"):
         tpg.indiv_inbreeding(gt, allele_sharing_mat=np.eye(3))
+
+
+def test_host_pool_serves_concurrent_callers():
+    """The in-process multi-GPU driver has one streamer thread per device, all feeding the same
+    worker pool (csrc/pack.cpp): concurrent jobs must neither interleave nor deadlock."""
+    import threading
+    lib = L.lib()
+    rng = np.random.default_rng(5)
+    jobs = []
+    for k in range(6):
+        nrow, ncol = 300 + 37 * k, 4000 + 500 * k
+        raw = rng.integers(0, 5, nrow * ncol).astype(np.uint8)
+        out = np.zeros((ncol, int(lib.tpg_pk2_stride(nrow))), np.uint8)
+        jobs.append((raw, nrow, ncol, out))
+    def work(j):
+        raw, nrow, ncol, out = j
+        for _ in range(5):
+            lib.tpg_pk2_pack_host(raw.ctypes.data, nrow, nrow, ncol, out.ctypes.data)
+    th = [threading.Thread(target=work, args=(j,)) for j in jobs]
+    [t.start() for t in th]
+    [t.join(60) for t in th]
+    assert not any(t.is_alive() for t in th)
+    for raw, nrow, ncol, out in jobs:
+        assert np.array_equal(out, pk2_ref(raw, nrow, ncol, 0, nrow))
