@@ -488,8 +488,123 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   double pack_gbps = 4.0 * double(HostPool::max_threads());
   if (const char* ev = getenv("TPG_LINK_GBPS")) link_gbps = std::max(1.0, atof(ev));
   const bool hybrid = !getenv("TPG_NO_HYBRID");
+  double hybrid_factor = 0.9;
+  if (const char* ev = getenv("TPG_HYBRID_FACTOR")) hybrid_factor = atof(ev);
   const bool use_pread = job->src_kind == TPG_SRC_FILE && pl.cols_contig && !getenv("TPG_NO_PREAD");
   std::atomic<int> io_err{0};
+
+  // ---- host-source staging, software-pipelined: the workers stage (pack / copy) chunk c+1 while
+  // this thread enqueues the H2D, decode and Gram of chunk c.
+  struct Stage {
+    bool use_direct = false, packed = false, async = false;
+    const uint8_t* hp = nullptr;
+    int64_t h2d_bytes = 0, col_stride = 0;
+    int sb = 0;  // pinned staging buffer
+  };
+  Stage stg[2];
+  // Decides how chunk c crosses PCIe and starts its staging:
+  //   direct  raw bytes DMA'd from the caller's pinned memory (no host work, 1 B / genotype)
+  //   pk2     packed 4 genotypes / byte into pinned staging by the worker pool (0.25 B / genotype)
+  //   staged  raw row window copied into pinned staging (gathered rows, K-major planes)
+  // With both direct and pk2 available the link and the cores work side by side: a chunk goes
+  // raw when the copy queue would otherwise run dry before this chunk could be packed.
+  auto start_stage = [&](int64_t c) -> int {
+    Stage& S = stg[c & 1];
+    S = Stage{};
+    const int64_t k0 = c * lc, k1 = std::min(pl.m_shard, k0 + lc);
+    const int64_t lcc = k1 - k0;
+    const double t0 = now_ms();
+    S.use_direct = direct_only;
+    if (direct_ok && pack_ok) {
+      const double backlog = std::max(0.0, link_free_at - t0);
+      const double t_pack = double(lcc * span) / (pack_gbps * 1e6);
+      S.use_direct = hybrid && backlog < hybrid_factor * t_pack;
+    }
+    if (S.use_direct) {
+      S.hp = src.base + (pl.col0 + k0) * nrow;
+      S.h2d_bytes = lcc * nrow;
+      S.col_stride = nrow;
+      return TPG_OK;
+    }
+    S.sb = int(n_staged & 1);
+    if (n_staged >= 2) TPG_CUDA_OK(cudaEventSynchronize(ev_pin_free[S.sb]), E);
+    ++n_staged;
+    uint8_t* stage = B.h_pin[S.sb];
+    const uint8_t* base = src.base;
+    const Plan* plp = &pl;
+    S.hp = stage;
+    S.async = true;
+    if (pack_ok) {
+      S.packed = true;
+      S.h2d_bytes = lcc * pk_stride;
+      S.col_stride = pk_stride;
+      if (use_pread) {
+        // .bk file, contiguous columns: pread() blocks of whole columns into a per-thread buffer
+        // that stays in L2 and pack from there — a fresh mmap pays one page fault per 4 KiB.
+        const int fd = src.fd;
+        const int64_t cpb = std::max<int64_t>(1, (int64_t(1) << 20) / nrow);  // columns per block
+        std::atomic<int>* bad = &io_err;
+        HostPool::instance().begin(lcc, std::max<int64_t>(cpb, (int64_t(1) << 20) / span), [=](int64_t a, int64_t e) {
+          static thread_local std::vector<uint8_t> buf;
+          if (int64_t(buf.size()) < cpb * nrow) buf.resize(size_t(cpb * nrow));
+          for (int64_t k = k0 + a; k < k0 + e; k += cpb) {
+            const int64_t nc = std::min<int64_t>(cpb, k0 + e - k);
+            const int64_t off = (plp->col0 + k) * nrow;
+            int64_t got = 0;
+            while (got < nc * nrow) {
+              const ssize_t r = pread(fd, buf.data() + got, size_t(nc * nrow - got), off_t(off + got));
+              if (r <= 0) { bad->store(1); return; }
+              got += r;
+            }
+            for (int64_t j = 0; j < nc; ++j)
+              pk2_pack_column(buf.data() + j * nrow + rlo, span, stage + (k - k0 + j) * pk_stride, pk_stride);
+          }
+        });
+      } else {
+        HostPool::instance().begin(lcc, std::max<int64_t>(1, (int64_t(1) << 20) / span), [=](int64_t a, int64_t e) {
+          for (int64_t k = k0 + a; k < k0 + e; ++k) {
+            const int64_t col = plp->cols_contig ? plp->col0 + k : plp->cols0[k];
+            pk2_pack_column(base + col * nrow + rlo, span, stage + (k - k0) * pk_stride, pk_stride);
+          }
+        });
+      }
+    } else {
+      S.h2d_bytes = lcc * span;
+      S.col_stride = span;
+      if (pl.cols_contig && span == nrow) {
+        const uint8_t* from = base + (pl.col0 + k0) * nrow;
+        HostPool::instance().begin(lcc * nrow, int64_t(8) << 20, [=](int64_t a, int64_t e) { memcpy(stage + a, from + a, size_t(e - a)); });
+      } else {
+        HostPool::instance().begin(lcc, std::max<int64_t>(1, (int64_t(4) << 20) / span), [=](int64_t a, int64_t e) {
+          for (int64_t k = k0 + a; k < k0 + e; ++k) {
+            const int64_t col = plp->cols_contig ? plp->col0 + k : plp->cols0[k];
+            memcpy(stage + (k - k0) * span, base + col * nrow + rlo, size_t(span));
+          }
+        });
+      }
+    }
+    return TPG_OK;
+  };
+  // Waits for chunk c's staging, books its transfer in the link model.
+  auto finish_stage = [&](int64_t c) -> int {
+    Stage& S = stg[c & 1];
+    if (S.async) {
+      const double ms = HostPool::instance().end();
+      S.async = false;
+      ms_read += ms;
+      const int64_t lcc = std::min(pl.m_shard, (c + 1) * lc) - c * lc;
+      if (S.packed && ms > 0) pack_gbps = 0.5 * pack_gbps + 0.5 * double(lcc * span) / (ms * 1e6);
+      if (io_err.load()) return E.fail(TPG_ERR_IO, "reading '%s' failed: %s", job->bk_path, strerror(errno));
+    }
+    link_free_at = std::max(link_free_at, now_ms()) + double(S.h2d_bytes) / (link_gbps * 1e6);
+    return TPG_OK;
+  };
+  // (an early error return must not leave the pool's job open)
+  struct StageGuard {
+    Stage* s;
+    ~StageGuard() { for (int i = 0; i < 2; ++i) if (s[i].async) { HostPool::instance().end(); s[i].async = false; } }
+  } stage_guard{stg};
+  if (!on_device) { rc = start_stage(0); if (rc) return rc; }
 
   for (int64_t c = 0; c < n_chunks; ++c) {
     const int b = int(c & 1);
@@ -519,99 +634,21 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       TPG_CUDA_OK(cudaEventRecord(tm[c].c0, ctx->s_copy), E);
       TPG_CUDA_OK(cudaEventRecord(tm[c].c1, ctx->s_copy), E);
     } else {
-      // ---- pick how this chunk crosses PCIe:
-      //   direct  raw bytes DMA'd from the caller's pinned memory (no host work, 1 B / genotype)
-      //   pk2     packed 4 genotypes / byte into pinned staging by the worker pool (0.25 B / genotype)
-      //   staged  raw row window copied into pinned staging (gathered rows, K-major planes)
-      // With both direct and pk2 available the link and the cores work side by side: a chunk goes
-      // raw when the copy queue would otherwise run dry before this chunk could be packed.
-      const double t0 = now_ms();
-      bool use_direct = direct_only;
-      if (direct_ok && pack_ok) {
-        const double backlog = std::max(0.0, link_free_at - t0);
-        const double t_pack = double(lcc * span) / (pack_gbps * 1e6);
-        use_direct = hybrid && backlog < 0.9 * t_pack;
-      }
-      const uint8_t* hp;
-      int64_t h2d_bytes, col_stride;
-      bool packed = false;
-      if (use_direct) {
-        hp = src.base + (pl.col0 + k0) * nrow;
-        h2d_bytes = lcc * nrow;
-        col_stride = nrow;
-      } else {
-        const int sb = int(n_staged & 1);
-        if (n_staged >= 2) TPG_CUDA_OK(cudaEventSynchronize(ev_pin_free[sb]), E);
-        uint8_t* stage = B.h_pin[sb];
-        const uint8_t* base = src.base;
-        const Plan* plp = &pl;
-        if (pack_ok) {
-          packed = true;
-          if (use_pread) {
-            // .bk file, contiguous columns: pread() blocks of whole columns into a per-thread buffer
-            // that stays in L2 and pack from there — a fresh mmap pays one page fault per 4 KiB.
-            const int fd = src.fd;
-            const int64_t cpb = std::max<int64_t>(1, (int64_t(1) << 20) / nrow);  // columns per block
-            std::atomic<int>* bad = &io_err;
-            parallel_for(lcc, std::max<int64_t>(cpb, (int64_t(1) << 20) / span), [=](int64_t a, int64_t e) {
-              static thread_local std::vector<uint8_t> buf;
-              if (int64_t(buf.size()) < cpb * nrow) buf.resize(size_t(cpb * nrow));
-              for (int64_t k = k0 + a; k < k0 + e; k += cpb) {
-                const int64_t nc = std::min<int64_t>(cpb, k0 + e - k);
-                const int64_t off = (plp->col0 + k) * nrow;
-                int64_t got = 0;
-                while (got < nc * nrow) {
-                  const ssize_t r = pread(fd, buf.data() + got, size_t(nc * nrow - got), off_t(off + got));
-                  if (r <= 0) { bad->store(1); return; }
-                  got += r;
-                }
-                for (int64_t j = 0; j < nc; ++j)
-                  pk2_pack_column(buf.data() + j * nrow + rlo, span, stage + (k - k0 + j) * pk_stride, pk_stride);
-              }
-            });
-            if (io_err.load()) return E.fail(TPG_ERR_IO, "reading '%s' failed: %s", job->bk_path, strerror(errno));
-          } else {
-            parallel_for(lcc, std::max<int64_t>(1, (int64_t(1) << 20) / span), [=](int64_t a, int64_t e) {
-              for (int64_t k = k0 + a; k < k0 + e; ++k) {
-                const int64_t col = plp->cols_contig ? plp->col0 + k : plp->cols0[k];
-                pk2_pack_column(base + col * nrow + rlo, span, stage + (k - k0) * pk_stride, pk_stride);
-              }
-            });
-          }
-          h2d_bytes = lcc * pk_stride;
-          col_stride = pk_stride;
-          const double dt = now_ms() - t0;
-          if (dt > 0) pack_gbps = 0.5 * pack_gbps + 0.5 * double(lcc * span) / (dt * 1e6);
-        } else {
-          if (pl.cols_contig && span == nrow) {
-            const uint8_t* from = base + (pl.col0 + k0) * nrow;
-            parallel_for(lcc * nrow, int64_t(8) << 20, [=](int64_t a, int64_t e) { memcpy(stage + a, from + a, size_t(e - a)); });
-          } else {
-            parallel_for(lcc, std::max<int64_t>(1, (int64_t(4) << 20) / span), [=](int64_t a, int64_t e) {
-              for (int64_t k = k0 + a; k < k0 + e; ++k) {
-                const int64_t col = plp->cols_contig ? plp->col0 + k : plp->cols0[k];
-                memcpy(stage + (k - k0) * span, base + col * nrow + rlo, size_t(span));
-              }
-            });
-          }
-          h2d_bytes = lcc * span;
-          col_stride = span;
-        }
-        hp = stage;
-      }
-      ms_read += now_ms() - t0;
+      rc = finish_stage(c);
+      if (rc) return rc;
+      const Stage S = stg[c & 1];
+      if (c + 1 < n_chunks) { rc = start_stage(c + 1); if (rc) return rc; }  // the workers go on while we enqueue
+      const bool use_direct = S.use_direct, packed = S.packed;
+      const uint8_t* hp = S.hp;
+      const int64_t h2d_bytes = S.h2d_bytes, col_stride = S.col_stride;
       // ---- H2D on the copy stream, after the decode that last read this raw buffer
       if (c >= 2) TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_copy, ev_dec_done[b], 0), E);
       TPG_CUDA_OK(cudaEventRecord(tm[c].c0, ctx->s_copy), E);
       TPG_CUDA_OK(cudaMemcpyAsync(B.d_raw[b], hp, size_t(h2d_bytes), cudaMemcpyHostToDevice, ctx->s_copy), E);
       TPG_CUDA_OK(cudaEventRecord(tm[c].c1, ctx->s_copy), E);
       TPG_CUDA_OK(cudaEventRecord(ev_h2d_done[b], ctx->s_copy), E);
-      if (!use_direct) TPG_CUDA_OK(cudaEventRecord(ev_pin_free[n_staged++ & 1], ctx->s_copy), E);
+      if (!use_direct) TPG_CUDA_OK(cudaEventRecord(ev_pin_free[S.sb], ctx->s_copy), E);
       TPG_CUDA_OK(cudaStreamWaitEvent(s_dec, ev_h2d_done[b], 0), E);
-      {
-        const double t1 = now_ms();
-        link_free_at = std::max(link_free_at, t1) + double(h2d_bytes) / (link_gbps * 1e6);
-      }
       st->bytes_h2d += h2d_bytes;
       if (packed) n_packed++;
       da.raw = B.d_raw[b];

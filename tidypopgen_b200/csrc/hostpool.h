@@ -11,6 +11,11 @@ class HostPool {
   // Splits [0, n) into at most max_threads() contiguous parts of >= grain items and runs
   // body(begin, end) on the pool (the caller takes a share); returns when all parts are done.
   void run(int64_t n, int64_t grain, const std::function<void(int64_t, int64_t)>& body);
+  // The same split, but on the workers only: begin() returns at once (the caller goes on to
+  // enqueue GPU work), end() waits and returns the milliseconds from begin() to the last part.
+  // One job at a time, like run(); every begin() must be matched by an end().
+  void begin(int64_t n, int64_t grain, std::function<void(int64_t, int64_t)> body);
+  double end();
   static int max_threads();  // min(hardware threads, 32), or TPG_HOST_THREADS
 
  private:

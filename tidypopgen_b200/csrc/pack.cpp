@@ -11,6 +11,7 @@
 // k * pk_stride, pk_stride = round_up(ceil(span / 4), 16); byte b holds the individuals
 // 4b .. 4b+3 of the staged row window, individual 4b+j in bits [2j, 2j+2); code 3 = missing
 // (also used for the padding individuals of the last byte and the padding bytes).
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <algorithm>
@@ -25,12 +26,19 @@
 
 namespace tpg {
 
+static double now_ms_() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
 // ------------------------------------------------------------------ worker pool
 struct HostPool::Impl {
   std::mutex mu;
   std::condition_variable cv_work, cv_done;
   std::vector<std::thread> workers;
   const std::function<void(int64_t, int64_t)>* body = nullptr;
+  std::function<void(int64_t, int64_t)> owned;  // body of an asynchronous job (begin / end)
+  double t_begin = 0, t_done = 0;
   int64_t n = 0;
   int parts = 0;
   int next = 0, done = 0;
@@ -50,7 +58,7 @@ struct HostPool::Impl {
         lk.unlock();
         (*b)(a, e);
         lk.lock();
-        if (++done == parts) cv_done.notify_all();
+        if (++done == parts) { t_done = now_ms_(); cv_done.notify_all(); }
       }
       seen = epoch;
     }
@@ -107,6 +115,35 @@ void HostPool::run(int64_t n, int64_t grain, const std::function<void(int64_t, i
   s.cv_done.wait(lk, [&] { return s.done == s.parts; });
   s.body = nullptr;
   s.cv_done.notify_all();
+}
+
+void HostPool::begin(int64_t n, int64_t grain, std::function<void(int64_t, int64_t)> body) {
+  Impl& s = *impl_;
+  std::unique_lock<std::mutex> lk(s.mu);
+  s.cv_done.wait(lk, [&] { return s.body == nullptr; });
+  int parts = int(std::min<int64_t>(std::max(1, max_threads() - 1), std::max<int64_t>(1, n / std::max<int64_t>(grain, 1))));
+  if (n <= 0) parts = 0;
+  while (int(s.workers.size()) < std::max(parts, 1)) s.workers.emplace_back([&s] { s.worker(); });
+  s.owned = std::move(body);
+  s.body = &s.owned;
+  s.n = n;
+  s.parts = parts;
+  s.next = 0;
+  s.done = 0;
+  s.t_begin = s.t_done = now_ms_();
+  ++s.epoch;
+  s.cv_work.notify_all();
+}
+
+double HostPool::end() {
+  Impl& s = *impl_;
+  std::unique_lock<std::mutex> lk(s.mu);
+  s.cv_done.wait(lk, [&] { return s.done == s.parts; });
+  const double ms = s.t_done - s.t_begin;
+  s.body = nullptr;
+  s.owned = nullptr;
+  s.cv_done.notify_all();
+  return ms;
 }
 
 // ------------------------------------------------------------------ 2-bit packer
