@@ -161,8 +161,8 @@ def pick(kind, total, rng):
 
 @pytest.mark.parametrize("case", CASES, ids=[f"n{c[0]}_m{c[1]}_{c[4]}" for c in CASES])
 @pytest.mark.parametrize("variant", [0, L.FLAG_PLANES_K_MAJOR, L.FLAG_GRAM_1CTA, L.FLAG_PLANES_K_MAJOR | L.FLAG_GRAM_1CTA,
-                                     L.FLAG_NO_PACK],
-                         ids=["mn", "kmajor", "mn_1cta", "kmajor_1cta", "mn_nopack"])
+                                     L.FLAG_NO_PACK, L.FLAG_NO_PACK | L.FLAG_GRAM_I8],
+                         ids=["pk2_i8", "kmajor", "mn_1cta", "kmajor_1cta", "raw_mxf4", "raw_i8"])
 def test_random_parity_all_stats(case, variant):
     n_tot, m_tot, bs, chunk, rk, ck = case
     rng = np.random.default_rng(n_tot * 1000 + m_tot)
@@ -366,6 +366,74 @@ def test_hybrid_link_and_pack_chunks(monkeypatch):
     # file source: every chunk is packed
     tpg.snp_king(X, gpu_chunk_loci=4096)
     assert tpg.snp.last_stats["n_packed_chunks"] == tpg.snp.last_stats["n_chunks"] == 10
+
+
+def k4_pack(plane):
+    """numpy statement of the K-major 4-bit (E2M1) plane layout of decode_planes_k4: plane [rows, loci]
+    in {-1, 0, +1} -> [rows, loci / 2] bytes; byte k of a group of 8 loci holds locus k (low nibble)
+    and locus k + 4 (high nibble); +1 = 0x2, -1 = 0xA."""
+    code = np.where(plane > 0, 0x2, np.where(plane < 0, 0xA, 0)).astype(np.uint8)
+    r, lc = code.shape
+    g = code.reshape(r, lc // 8, 2, 4)              # [row, group, half, k]
+    return (g[:, :, 0, :] | (g[:, :, 1, :] << 4)).reshape(r, lc // 2)
+
+
+@pytest.mark.parametrize("gather", [False, True])
+def test_decode_planes_k4_kernel(gather):
+    import torch
+    ctx = L.Context(0)
+    rng = np.random.default_rng(3)
+    nrow, ncol = 929, 900
+    raw = rng.integers(0, 256, size=(ncol, nrow)).astype(np.uint8)
+    raw[rng.random(raw.shape) < 0.8] %= 4
+    if gather:
+        rows = rng.permutation(nrow)[:613].astype(np.int32)
+        cols = rng.permutation(ncol)[:391].astype(np.int32)
+    else:
+        rows = np.arange(5, 5 + 801, dtype=np.int32)
+        cols = np.arange(3, 3 + 700, dtype=np.int32)
+    n, lc = len(rows), len(cols)
+    n_pad, lc_pad = (n + 255) // 256 * 256, (lc + 255) // 256 * 256
+    d_raw = torch.from_numpy(raw.reshape(-1)).cuda()
+    d_rows, d_cols = torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda()
+    ps = n_pad * lc_pad // 2
+    d_planes = torch.full((3 * ps,), 0x77, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    eb = L.errbuf()
+    L.check(L.lib().tpg_decode_planes(ctx.handle, d_raw.data_ptr(), raw.size, nrow,
+                                      d_rows.data_ptr() if gather else None, int(rows[0]), n, n_pad,
+                                      d_cols.data_ptr() if gather else None, int(cols[0]), lc, lc_pad,
+                                      d_planes.data_ptr(), ps, 8, eb, len(eb)), eb)
+    got = d_planes.cpu().numpy().reshape(3, n_pad, lc_pad // 2)
+    for p, x in enumerate(planes_ref(raw[np.ix_(cols, rows)].T)):
+        full = np.zeros((n_pad, lc_pad), np.int8)
+        full[:n, :lc] = x
+        assert np.array_equal(got[p], k4_pack(full)), p
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (512, 1280), (1024, 4096), (2560, 2048)])
+def test_gram_mxf4_kernel(shape):
+    """kind::mxf4 Gram kernel on K-major 4-bit planes: integer counts, exact."""
+    import torch
+    n_pad, lc_pad = shape
+    ctx = L.Context(0)
+    rng = np.random.default_rng(2)
+    g = rng.choice(np.array([0, 1, 2, 3], np.uint8), size=(n_pad, lc_pad), p=[.4, .3, .25, .05])
+    planes = planes_ref(g)
+    host = np.stack([k4_pack(p) for p in planes]).copy()
+    d_planes = torch.from_numpy(host.reshape(-1)).cuda()
+    d_counts = torch.zeros(4 * n_pad * n_pad, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    eb, ms = L.errbuf(), C.c_float(0)
+    for rep in range(2):  # two launches accumulate
+        L.check(L.lib().tpg_gram(ctx.handle, d_planes.data_ptr(), n_pad * lc_pad // 2, n_pad, lc_pad, 8, 0b1111, 0, 1,
+                                 d_counts.data_ptr(), C.byref(ms), eb, len(eb)), eb)
+    got = d_counts.cpu().numpy().reshape(4, n_pad, n_pad).transpose(0, 2, 1)  # [mat][i][j]
+    d, nm, h1 = [p.astype(np.float64) for p in planes]
+    iu = np.triu_indices(n_pad)
+    for mat, ref in ((L.MAT_DD, d @ d.T), (L.MAT_NN, nm @ nm.T), (L.MAT_HH, h1 @ h1.T)):
+        assert np.array_equal(got[mat][iu], 2 * ref[iu].astype(np.int64)), mat
+    assert np.array_equal(got[L.MAT_HN], 2 * (h1 @ nm.T).astype(np.int64))
 
 
 def test_synth_device_equals_host():

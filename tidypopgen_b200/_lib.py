@@ -22,7 +22,7 @@ OK, ERR_ARG, ERR_IO, ERR_CUDA, ERR_NOMEM, ERR_KERNEL = range(6)
 STAT_KING, STAT_IBS_RAW, STAT_IBS_PROPORTION, STAT_IBS_ADJUSTED, STAT_AS, STAT_GRM = range(6)
 SRC_FILE, SRC_HOST, SRC_DEVICE = range(3)
 SHARD_NONE, SHARD_LOCI, SHARD_TILES = range(3)
-FLAG_PLANES_K_MAJOR, FLAG_NO_OVERLAP, FLAG_GRAM_1CTA, FLAG_NO_PACK, FLAG_ASYNC = 1, 2, 4, 8, 16
+FLAG_PLANES_K_MAJOR, FLAG_NO_OVERLAP, FLAG_GRAM_1CTA, FLAG_NO_PACK, FLAG_ASYNC, FLAG_GRAM_I8 = 1, 2, 4, 8, 16, 32
 MAT_DD, MAT_NN, MAT_HH, MAT_HN = range(4)
 NUM_COUNT_MATS = 4
 

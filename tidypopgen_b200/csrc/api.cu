@@ -385,6 +385,11 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   // (scans decode through code256 and need the whole byte)
   const bool pack_ok = !scan && !on_device && pl.rows_contig && !k_major && !(job->flags & TPG_FLAG_NO_PACK) &&
                        !getenv("TPG_NO_PACK");
+  // Chunks that reach the GPU as raw bytes can take the 4-bit route: decode_planes_k4 + the kind::mxf4
+  // Gram kernel (twice the int8 MAC rate, half the plane bytes, exact: gram.cu).  2-bit packed chunks
+  // and tile-sharded jobs use the int8 kernels; both kinds add into the same int32 counts.
+  const bool q4_forced_off = (job->flags & (TPG_FLAG_GRAM_I8 | TPG_FLAG_GRAM_1CTA)) || getenv("TPG_GRAM_I8");
+  const bool q4_ok = !scan && !k_major && !q4_forced_off && !(job->shard_mode == TPG_SHARD_TILES && job->shard_world > 1);
   const bool direct_only = direct_ok && !pack_ok;
   if (direct_only) { span = nrow; rlo = 0; }
   const int64_t pk_stride = pk2_stride(span);
@@ -660,6 +665,14 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       da.col_idx = nullptr;
       da.col0 = 0;
     }
+    const bool use_q4 = q4_ok && !da.packed;
+    const int64_t q4_lc_pad = round_up(lcc, 256);
+    const int64_t q4_stride = pl.n_pad * (round_up(lc, 256) / 2);  // <= plane_stride: fits the int8 plane buffer
+    if (use_q4) {
+      da.k4 = true;
+      da.lc_pad = q4_lc_pad;
+      da.plane_stride = q4_stride;
+    }
     if (scan) {  // one pass over the chunk's bytes; no planes, no products
       ScanArgs sa = *scan;
       sa.alt2 += k0; sa.valid += k0; sa.na_l += k0;
@@ -684,10 +697,11 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
 
     GramArgs ga;
     ga.planes = B.d_planes[b];
-    ga.plane_stride = plane_stride;
+    ga.plane_stride = use_q4 ? q4_stride : plane_stride;
     ga.n = pl.n;
     ga.n_pad = pl.n_pad;
-    ga.lc_pad = lc_pad;
+    ga.lc_pad = use_q4 ? q4_lc_pad : lc_pad;
+    ga.mxf4 = use_q4;
     ga.k_major = k_major;
     ga.ctas = (job->flags & TPG_FLAG_GRAM_1CTA) ? 1 : 0;
     ga.prod_mask = pl.prod_mask;
@@ -1359,6 +1373,7 @@ int tpg_decode_planes(tpg_ctx* h, const uint8_t* d_raw, int64_t raw_bytes, int64
   a.col_idx = d_col_idx; a.col0 = col0; a.lc = lc; a.lc_pad = lc_pad;
   a.planes = d_planes; a.plane_stride = plane_stride; a.nplanes = 3; a.k_major = (k_major & 1) != 0;
   a.packed = (k_major & 4) != 0;
+  a.k4 = (k_major & 8) != 0;
   int rc = launch_decode(c, a, c->s_compute, E);
   if (rc) return rc;
   TPG_CUDA_OK(cudaStreamSynchronize(c->s_compute), E);
@@ -1374,7 +1389,8 @@ int tpg_gram(tpg_ctx* h, const int8_t* d_planes, int64_t plane_stride, int64_t n
   TPG_CUDA_OK(cudaSetDevice(c->device), E);
   GramArgs a;
   a.planes = d_planes; a.plane_stride = plane_stride; a.n = n_pad; a.n_pad = n_pad;
-  a.lc_pad = lc_pad; a.k_major = (k_major & 1) != 0; a.ctas = (k_major & 2) ? 1 : 0; a.prod_mask = prod_mask;
+  a.lc_pad = lc_pad; a.k_major = (k_major & 1) != 0; a.ctas = (k_major & 2) ? 1 : 0; a.mxf4 = (k_major & 8) != 0;
+  a.prod_mask = prod_mask;
   a.shard_rank = shard_rank; a.shard_world = shard_world; a.counts = d_counts; a.ld = n_pad;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);

@@ -303,6 +303,108 @@ decode_planes_k_kernel(const DecodeParams p) {
   }
 }
 
+// ------------------------------------------------------------------ K-major 4-bit planes (E2M1)
+// Operand planes of the kind::mxf4 Gram kernel (gram.cu): every plane value is -1, 0 or +1, which
+// E2M1 holds exactly (+1 = 0x2, -1 = 0xA, 0 = 0x0), two per byte, K-major:
+//   plane[i * pitch + byte], pitch = lc_pad / 2, lc_pad a multiple of 256 (128-byte rows for TMA).
+// Within a group of 8 loci the byte k (0..3) holds locus k in its low and locus k + 4 in its high
+// nibble — a fixed permutation of K that is the same for every row and plane, which a dot product
+// over K does not see, and that makes packing two transposed words one shift and one OR.
+// Block = 128 individuals x 256 loci; warp w owns loci [32w, 32w + 32), a lane 4 individuals:
+// 32 loads in flight per lane, 4x4 byte transposes (PRMT), one 16-byte store per (individual, plane).
+// Traffic: 1 byte read + 0.5 P bytes written per genotype.
+__global__ void __launch_bounds__(256)
+decode_planes_k4_kernel(const DecodeParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nib = p.n_pad / 128;
+  const int i0 = int(blockIdx.x % nib) * 128 + lane * 4;
+  const int l0 = int(blockIdx.x / nib) * 256 + warp * 32;  // lc_pad is a multiple of 256: always in range
+  const RowSel rs = make_rowsel(p, i0);
+  const int ib0 = int(blockIdx.x % nib) * 128;
+  const bool safe = block_is_safe(p, l0, 32, ib0, ib0 + 128);
+  uint32_t g[32];
+  if (safe && l0 + 32 <= p.lc && !p.row_idx) {
+    uint32_t wx[32];
+    uint64_t shs = 0;  // 2 bits per locus
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      const int64_t col = p.col_idx ? int64_t(__ldg(p.col_idx + l0 + u)) : p.col0 + l0 + u;
+      const uint8_t* a = p.raw + col * p.raw_stride + rs.off;
+      const uint32_t sh = uint32_t(reinterpret_cast<uintptr_t>(a) & 3u);
+      shs |= uint64_t(sh) << (2 * u);
+      const uint32_t* al = reinterpret_cast<const uint32_t*>(a - sh);
+      g[u] = __ldg(al);
+      wx[u] = 0;
+      if (lane == 31) wx[u] = __ldg(al + 1);
+    }
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      uint32_t w1 = __shfl_down_sync(0xFFFFFFFFu, g[u], 1);
+      if (lane == 31) w1 = wx[u];
+      g[u] = __funnelshift_r(g[u], w1, uint32_t((shs >> (2 * u)) & 3u) * 8);
+      g[u] = (g[u] & rs.keep) | (0x03030303u & ~rs.keep);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int l = l0 + k;
+      g[k] = 0x03030303u;
+      if (l < p.lc) {
+        const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
+        g[k] = safe ? load4<true>(p, rs, col, lane) : load4<false>(p, rs, col, lane);
+      }
+    }
+  }
+  // out[plane][r][w]: 8 loci per word, 4 words = 32 loci per individual r
+  uint32_t od[4][4], on[4][4], oh[4][4];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {  // 4 loci at a time: t[r] = loci 4q..4q+3 of individual i0 + r
+    const uint32_t a0 = __byte_perm(g[4 * q], g[4 * q + 1], 0x5140);
+    const uint32_t a1 = __byte_perm(g[4 * q + 2], g[4 * q + 3], 0x5140);
+    const uint32_t b0 = __byte_perm(g[4 * q], g[4 * q + 1], 0x7362);
+    const uint32_t b1 = __byte_perm(g[4 * q + 2], g[4 * q + 3], 0x7362);
+    uint32_t t[4];
+    t[0] = __byte_perm(a0, a1, 0x5410);
+    t[1] = __byte_perm(a0, a1, 0x7632);
+    t[2] = __byte_perm(b0, b1, 0x5410);
+    t[3] = __byte_perm(b0, b1, 0x7632);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      uint32_t d, nm, h1;
+      decode4(t[r], d, nm, h1);
+      const uint32_t cd = ((d << 1) & 0x02020202u) | ((d >> 4) & 0x08080808u);  // +1 -> 0x2, -1 -> 0xA
+      const uint32_t cn = nm << 1, ch = h1 << 1;                                 // 1 -> 0x2
+      const int w = q >> 1;
+      if ((q & 1) == 0) { od[r][w] = cd; on[r][w] = cn; oh[r][w] = ch; }          // loci k     -> low nibbles
+      else { od[r][w] |= cd << 4; on[r][w] |= cn << 4; oh[r][w] |= ch << 4; }     // loci k + 4 -> high nibbles
+    }
+  }
+  // Stage the tile's output rows in shared memory (16-byte chunks XOR-swizzled by row so that neither
+  // side has bank conflicts) and write them out as whole 128-byte lines: a lane's own 16 bytes are
+  // 1/8 of a line, and eight warps writing eighths of the same lines is what DRAM likes least.
+  __shared__ uint4 tile[3][128][8];
+  const int rl = lane * 4;  // first local row of this lane
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = rl + r, ch = warp ^ ((row >> 2) & 7);
+    tile[0][row][ch] = make_uint4(od[r][0], od[r][1], od[r][2], od[r][3]);
+    tile[1][row][ch] = make_uint4(on[r][0], on[r][1], on[r][2], on[r][3]);
+    if (p.nplanes > 2) tile[2][row][ch] = make_uint4(oh[r][0], oh[r][1], oh[r][2], oh[r][3]);
+  }
+  __syncthreads();
+  const int64_t pitch = p.lc_pad >> 1;
+  const int ib0r = int(blockIdx.x % nib) * 128;
+  const int lbyte = (int(blockIdx.x / nib) * 256) >> 1;  // this tile's first byte within a plane row
+  for (int pln = 0; pln < p.nplanes; ++pln)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int row = warp * 16 + k * 4 + (lane >> 3), c = lane & 7;  // 4 rows x 8 chunks per warp store
+      const uint4 v = tile[pln][row][c ^ ((row >> 2) & 7)];
+      *reinterpret_cast<uint4*>(p.planes + int64_t(pln) * p.plane_stride + int64_t(ib0r + row) * pitch + lbyte + c * 16) = v;
+    }
+}
+
 // ------------------------------------------------------------------ pk2 input (2-bit packed)
 // Host-sourced chunks arrive packed four genotypes per byte (pack.cpp: column k at
 // k * raw_stride, individual i of the staged window in bits [2(i&3), 2(i&3)+2) of byte i>>2,
@@ -556,7 +658,13 @@ int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E) 
   p.planes = a.planes;
   p.plane_stride = a.plane_stride;
   p.nplanes = a.nplanes;
-  if (a.packed) {
+  if (a.k4) {
+    if (a.packed || a.lc_pad % 256 || a.plane_stride % 16 || (reinterpret_cast<uintptr_t>(a.planes) & 15))
+      return E.fail(TPG_ERR_ARG, "decode(k4): lc_pad must be a multiple of 256, planes 16-byte aligned, raw-byte input");
+    const int64_t blocks = (a.n_pad / 128) * (a.lc_pad / 256);
+    if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "decode: chunk too large for one launch");
+    decode_planes_k4_kernel<<<unsigned(blocks), 256, 0, st>>>(p);
+  } else if (a.packed) {
     if (a.k_major || a.row_idx || a.col_idx || a.row0 || a.col0 || a.raw_stride % 16 || a.plane_stride % 16 ||
         (reinterpret_cast<uintptr_t>(a.raw) & 15) || (reinterpret_cast<uintptr_t>(a.planes) & 15))
       return E.fail(TPG_ERR_ARG, "decode(pk2): packed chunks are MN-major, ungathered and 16-byte aligned");

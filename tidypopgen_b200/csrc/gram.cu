@@ -386,6 +386,181 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------ 4-bit variant (kind::mxf4)
+// Every plane value is -1, 0 or +1: exactly representable in E2M1, and the block-scaled 4-bit MMA
+// (scales = 1) issues twice the MACs per cycle of kind::i8 with half the operand bytes.  Its FP32
+// accumulator keeps integer sums exact below 2^24 (known-answer experiment: scripts/mxf4_probe.cu,
+// profiles/r01_mxf4_probe.json); one accumulation chain here is at most a chunk (<= 2^20 loci).
+// Same CTA-pair skeleton as gram_i8_pair_kernel with K-major 4-bit planes (decode_planes_k4): a
+// stage is 128 bytes = 256 loci of 128 A rows + 128 B rows per CTA, four K = 64 MMAs per stage.
+// TMEM also has to hold the scale factors, so a tile is 256 x 240 (two 240-column accumulators at
+// columns 0 and 256; columns [240, 256) of every lane are filled with UE8M0 1.0 and serve as SFA /
+// SFB whatever their layout).  The epilogue converts the (integer-valued) floats and adds them to
+// the same int32 count matrices as the int8 kernels, so chunks of both kinds can be mixed.
+constexpr int kQTileN = 240;
+constexpr int kQStageLoci = 256;
+
+template <int kDummy>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGramThreads, 1)
+gram_mxf4_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_nm,
+                      const __grid_constant__ CUtensorMap tm_h1, const GramParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kPairStages;
+  uint64_t* tfull_bar = bars + 2 * kPairStages;
+  uint64_t* tempty_bar = bars + 2 * kPairStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_d);
+    tma_prefetch_desc(&tm_nm);
+    tma_prefetch_desc(&tm_h1);
+    for (int s = 0; s < kPairStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 2) {  // scale factors: UE8M0 1.0 (0x7F) in columns [224, 256) of this warp's lanes;
+                    // [224, 240) belongs to accumulator 0 and is overwritten by its first MMA
+    tmem_fill_32x32(tmem_base + (uint32_t((warp & 3) * 32) << 16) + 224u, 0x7F7F7F7Fu);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = cluster; it < p.n_items; it += n_clusters) {
+        const WorkItem w = p.items[it];
+        const int prod = w.prod_ti & 15, ti = w.prod_ti >> 8, tj = w.tj;
+        int pa, pb;
+        prod_planes(prod, pa, pb);
+        const CUtensorMap* ma = pa == 0 ? &tm_d : pa == 1 ? &tm_nm : &tm_h1;
+        const CUtensorMap* mb = pb == 0 ? &tm_d : pb == 1 ? &tm_nm : &tm_h1;
+        const int row_a = ti * kPairTileM + int(rank) * 128;
+        const int row_b = tj * kQTileN + int(rank) * (kQTileN / 2);  // 120 of the 128 loaded rows are used
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+          uint8_t* sa = smem + stage * kPairStageBytes;
+          uint8_t* sb = sa + kHalfBytes;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
+          const uint32_t bar0 = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_pair(sa, ma, bar0, kb * 128, row_a);   // (byte along K, row)
+          tma_load_2d_pair(sb, mb, bar0, kb * 128, row_b);
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_mxf4(kPairTileM, kQTileN);
+      const uint32_t sfa = tmem_base + 240u, sfb = tmem_base + 244u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int it = cluster; it < p.n_items; it += n_clusters) {
+        const WorkItem w = p.items[it];
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(acc * 256);
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kPairStageBytes);
+          const uint64_t da = make_smem_desc_sw128(sa, 16u, 1024u);
+          const uint64_t db = make_smem_desc_sw128(sa + kHalfBytes, 16u, 1024u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 32 bytes = 64 loci per MMA
+            umma_mxf4_pair(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc,
+                           (kb > w.kb0 || k > 0) ? 1u : 0u, sfa, sfb);
+          }
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tfull_bar[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue (warps 2..5, both CTAs)
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int it = cluster; it < p.n_items; it += n_clusters) {
+      const WorkItem w = p.items[it];
+      const int prod = w.prod_ti & 15, ti = w.prod_ti >> 8, tj = w.tj;
+      const bool sym = prod != TPG_MAT_HN;
+      mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
+      tc_fence_after();
+      const int i = ti * kPairTileM + int(rank) * 128 + q * 32 + lane;
+      const int j0 = tj * kQTileN;
+      int32_t* cbase = p.counts + int64_t(prod) * p.mat_stride + i;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 256);
+#pragma unroll 1
+      for (int c = 0; c < kQTileN; c += 32) {
+        const bool last = c + 32 >= kQTileN;
+        const int cc = last ? kQTileN - 32 : c;     // the last 32-column load overlaps the previous one
+        const int first = last ? 32 - (kQTileN - c) : 0;
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + uint32_t(cc), v);
+        tmem_ld_wait();
+        if (last) {  // accumulator drained: hand it back (to the leader's barrier)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        }
+        if (j0 + cc < p.n && i < p.n) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = j0 + cc + jj;
+            if (jj >= first && j < p.n && (!sym || i <= j))
+              atomicAdd(cbase + int64_t(j) * p.ld, __float2int_rn(__uint_as_float(v[jj])));
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -433,6 +608,92 @@ static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms) {
   return std::max(best, std::min(ks_l2, max_ks));
 }
 
+// Host side of the 4-bit variant: 256 x 240 tiles over K-major 4-bit planes, k-blocks of 256 loci.
+static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out, const Err& E) {
+  if (a.n_pad % kRowPad || a.lc_pad % kQStageLoci || a.lc_pad <= 0)
+    return E.fail(TPG_ERR_ARG, "gram(mxf4): n_pad (%lld) / lc_pad (%lld) not multiples of 256",
+                  (long long)a.n_pad, (long long)a.lc_pad);
+  if (a.shard_world > 1) return E.fail(TPG_ERR_ARG, "gram(mxf4): tile sharding uses the int8 kernels");
+  if (!ctx->gram_attr_set) {
+    GramArgs probe = a;   // sets the attributes of every gram kernel and counts the resident CTA pairs
+    probe.mxf4 = false;
+    probe.prod_mask = 0;
+    int rc = launch_gram(ctx, probe, st, nullptr, E);
+    if (rc) return rc;
+  }
+  if (!ctx->mxf4_attr_set) {
+    TPG_CUDA_OK(cudaFuncSetAttribute(gram_mxf4_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes), E);
+    ctx->mxf4_attr_set = true;
+  }
+  if (ctx->pair_clusters <= 0) return E.fail(TPG_ERR_CUDA, "gram(mxf4): the device reports no resident CTA pairs");
+  const int units = ctx->pair_clusters;
+  const int64_t tiles_m = a.n_pad / kPairTileM, tiles_n = (a.n + kQTileN - 1) / kQTileN;
+  const int64_t kblocks = a.lc_pad / kQStageLoci;
+  struct T { int prod, ti, tj; };
+  std::vector<T> tiles;
+  const int64_t RI = 4, RJ = 4;
+  for (int64_t rj = 0; rj < tiles_n; rj += RJ)
+    for (int64_t ri = 0; ri < tiles_m; ri += RI)
+      for (int64_t tj = rj; tj < std::min(rj + RJ, tiles_n); ++tj)
+        for (int64_t ti = ri; ti < std::min(ri + RI, tiles_m); ++ti) {
+          if (kPairTileM * ti >= a.n) continue;  // rows of padding individuals only
+          const bool upper = kQTileN * tj + (kQTileN - 1) >= kPairTileM * ti;
+          for (int prod = 0; prod < TPG_NUM_COUNT_MATS; ++prod) {
+            if (!(a.prod_mask & (1 << prod))) continue;
+            if (prod != TPG_MAT_HN && !upper) continue;
+            tiles.push_back({prod, int(ti), int(tj)});
+          }
+        }
+  if (tiles.empty()) { if (macs_out) *macs_out = 0; return TPG_OK; }
+  const int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units);
+  if (macs_out) *macs_out = int64_t(tiles.size()) * kPairTileM * kQTileN * a.lc_pad;
+  char key[200];
+  snprintf(key, sizeof key, "q4/%lld/%lld/%lld/%d/%d", (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad, a.prod_mask, ks);
+  if (ctx->items_key != key) {
+    std::vector<WorkItem>& items = ctx->h_items;
+    items.clear();
+    items.reserve(tiles.size() * ks);
+    for (int s = 0; s < ks; ++s) {
+      const int32_t kb0 = int32_t(kblocks * s / ks), kb1 = int32_t(kblocks * (s + 1) / ks);
+      if (kb1 <= kb0) continue;
+      for (const T& t : tiles) items.push_back({int32_t(t.prod | (t.ti << 8)), t.tj, kb0, kb1});
+    }
+    if (items.size() > ctx->d_items_cap) {
+      TPG_CUDA_OK(cudaStreamSynchronize(st), E);
+      if (ctx->d_items) cudaFree(ctx->d_items);
+      ctx->d_items = nullptr;
+      ctx->d_items_cap = 0;
+      const size_t cap = items.size() + items.size() / 4 + 1024;
+      TPG_CUDA_OK(cudaMalloc(&ctx->d_items, cap * sizeof(WorkItem)), E);
+      ctx->d_items_cap = cap;
+    }
+    TPG_CUDA_OK(cudaMemcpyAsync(ctx->d_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st), E);
+    ctx->items_key = key;
+  }
+  const size_t n_items = ctx->h_items.size();
+  CUtensorMap maps[3];
+  for (int pl = 0; pl < 3; ++pl) {
+    const int8_t* base = a.planes + int64_t(pl) * a.plane_stride;
+    const bool present = pl < 2 || (a.prod_mask & ((1 << TPG_MAT_HH) | (1 << TPG_MAT_HN)));
+    // K-major 4-bit planes: inner = bytes along K (lc_pad / 2), outer = rows; rows past n_pad are zero fill
+    int rc = make_plane_map(ctx, &maps[pl], present ? base : a.planes, uint64_t(a.lc_pad / 2), uint64_t(a.n_pad), E);
+    if (rc) return rc;
+  }
+  GramParams p;
+  p.items = ctx->d_items;
+  p.n_items = int(n_items);
+  p.counts = a.counts;
+  p.mat_stride = a.ld * a.ld;
+  p.ld = a.ld;
+  p.n = int(a.n);
+  p.err_flag = ctx->d_err_flag;
+  const int grid = 2 * int(std::min<size_t>(n_items, size_t(units)));
+  gram_mxf4_pair_kernel<0><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
+  TPG_CUDA_OK(cudaGetLastError(), E);
+  ctx->launches++;
+  return TPG_OK;
+}
+
 static bool pair_mode(const GramArgs& a) {
   if (a.ctas == 1) return false;
   if (a.ctas == 2) return true;
@@ -444,6 +705,7 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   if (a.n_pad % kRowPad || a.lc_pad % kLociPad || a.lc_pad <= 0)
     return E.fail(TPG_ERR_ARG, "gram: n_pad (%lld) / lc_pad (%lld) not tile multiples",
                   (long long)a.n_pad, (long long)a.lc_pad);
+  if (a.mxf4) return launch_gram_mxf4(ctx, a, st, macs_out, E);
   const bool pair = pair_mode(a);
   const int tile_m = pair ? kPairTileM : kTileM;
   const int64_t tiles_m = a.n_pad / tile_m, tiles_n = a.n_pad / kTileN;

@@ -41,6 +41,7 @@ struct Ctx {
   void* encode_tiled = nullptr;    // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
   int64_t launches = 0;
   bool gram_attr_set = false;
+  bool mxf4_attr_set = false;
   int pair_clusters = 0;           // CTA pairs resident at once (cudaOccupancyMaxActiveClusters)
   // Grow-only buffer cache, reused across jobs (cudaMalloc / cudaMallocHost / cudaFree are
   // slow and synchronising; a job must not pay them every call).  tpg_ctx_trim() frees it.
@@ -88,6 +89,7 @@ struct DecodeArgs {
   int nplanes;  // 2 (d, NM) or 3 (d, NM, H1)
   bool k_major;
   bool packed = false;  // raw is a pk2 chunk (pack.cpp): raw_stride = packed bytes per column
+  bool k4 = false;      // write K-major 4-bit E2M1 planes (operands of the kind::mxf4 Gram kernel)
 };
 int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E);
 
@@ -113,6 +115,7 @@ struct GramArgs {
   int64_t lc_pad;  // loci in this chunk (padded)
   bool k_major;
   int ctas = 0;    // 1 = single-CTA kernel, 2 = CTA-pair kernel, 0 = default (pair)
+  bool mxf4 = false;  // planes are K-major 4-bit E2M1 (decode k4): kind::mxf4 pair kernel, 256 x 240 tiles
   int prod_mask;
   int shard_rank, shard_world;  // tile sharding (world <= 1: everything)
   int32_t* counts;

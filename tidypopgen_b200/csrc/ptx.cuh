@@ -201,6 +201,37 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
       : "memory");
 }
 
+// ---------------------------------------------------------------- block-scaled 4-bit MMA (kind::mxf4)
+// D[tmem, f32] (+)= A * B with E2M1 operands (two per byte, K-major) and one UE8M0 scale per 32
+// elements of K taken from TMEM; M = 256 over the CTA pair, K = 64 per instruction.
+__device__ __forceinline__ void umma_mxf4_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t tmem_sfa, uint32_t tmem_sfb) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+// Block-scaled instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptorBlockScaled):
+// a_format [7,10) = b_format [10,13) = 1 (E2M1), K-major, n_dim [17,23) = N>>3,
+// scale_format [23] = 1 (UE8M0), m_dim [24,29) = M>>4, scale-factor ids 0.
+__host__ __device__ constexpr uint32_t make_idesc_mxf4(int M, int N) {
+  return (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (1u << 23) | (uint32_t(M >> 4) << 24);
+}
+// registers -> TMEM: the same value into this warp's 32 lanes x 32 consecutive columns
+__device__ __forceinline__ void tmem_fill_32x32(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Instruction descriptor, kind::i8: signed 8-bit A and B, s32 accumulator.
 // Bit layout (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format [4,6) = 2 (S32),
