@@ -313,95 +313,119 @@ decode_planes_k_kernel(const DecodeParams p) {
 // Block = 128 individuals x 256 loci; warp w owns loci [32w, 32w + 32), a lane 4 individuals:
 // 32 loads in flight per lane, 4x4 byte transposes (PRMT), one 16-byte store per (individual, plane).
 // Traffic: 1 byte read + 0.5 P bytes written per genotype.
-__global__ void __launch_bounds__(256)
+// E2M1 nibble codes of 4 packed genotypes, straight from the raw bytes (one code per byte, in its
+// low nibble): cn = 0x2 where byte <= 2; ch = 0x2 where byte == 1; cd = 0x2 where byte == 2,
+// 0xA (-1) where byte == 0.
+__device__ __forceinline__ void codes4(uint32_t g, uint32_t& cd, uint32_t& cn, uint32_t& ch) {
+  const uint32_t t = (g & 0x7F7F7F7Fu) + 0x7D7D7D7Du;   // bit 7 set iff (byte & 127) >= 3
+  cn = (~(t | g) >> 6) & 0x02020202u;                   // bit 7 clear <=> byte <= 2 -> bit 1
+  ch = (g << 1) & cn;                                   // valid bytes are 0,1,2: bit 0 <=> het
+  const uint32_t c2 = g & cn;                           // bit 1 <=> hom-alt
+  const uint32_t c0 = cn ^ ch ^ c2;                     // the remaining valid ones: hom-ref
+  cd = c0 * 5u + c2;                                    // 0x02 * 5 = 0x0A (-1), no carries between bytes
+}
+
+__global__ void __launch_bounds__(256, 3)
 decode_planes_k4_kernel(const DecodeParams p) {
+  __shared__ uint4 tile[3][128][8];  // output rows, 16-byte chunks XOR-swizzled by row
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nib = p.n_pad / 128;
-  const int i0 = int(blockIdx.x % nib) * 128 + lane * 4;
-  const int l0 = int(blockIdx.x / nib) * 256 + warp * 32;  // lc_pad is a multiple of 256: always in range
-  const RowSel rs = make_rowsel(p, i0);
   const int ib0 = int(blockIdx.x % nib) * 128;
-  const bool safe = block_is_safe(p, l0, 32, ib0, ib0 + 128);
-  uint32_t g[32];
-  if (safe && l0 + 32 <= p.lc && !p.row_idx) {
-    uint32_t wx[32];
-    uint64_t shs = 0;  // 2 bits per locus
-#pragma unroll
-    for (int u = 0; u < 32; ++u) {
-      const int64_t col = p.col_idx ? int64_t(__ldg(p.col_idx + l0 + u)) : p.col0 + l0 + u;
-      const uint8_t* a = p.raw + col * p.raw_stride + rs.off;
-      const uint32_t sh = uint32_t(reinterpret_cast<uintptr_t>(a) & 3u);
-      shs |= uint64_t(sh) << (2 * u);
-      const uint32_t* al = reinterpret_cast<const uint32_t*>(a - sh);
-      g[u] = __ldg(al);
-      wx[u] = 0;
-      if (lane == 31) wx[u] = __ldg(al + 1);
+  const int i0 = ib0 + lane * 4;
+  const int lt = int(blockIdx.x / nib) * 256;               // lc_pad is a multiple of 256: always in range
+  const RowSel rs = make_rowsel(p, i0);
+  const bool full = rs.keep == 0xFFFFFFFFu;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {                     // 16 loci at a time keeps the registers down
+    const int l0 = lt + warp * 32 + half * 16;
+    uint32_t g[16];
+    // Contiguous rows and columns, all 16 loci real and every word load inside the buffer: the
+    // straight-line path.  Column u starts stride bytes after column u - 1, so addresses and the
+    // byte misalignment of a column are running sums, not 64-bit multiplies.
+    bool fast = !p.row_idx && !p.col_idx && l0 + 16 <= p.lc;
+    if (fast) {
+      const int64_t lo = (p.col0 + l0) * p.raw_stride + p.row0 + ib0 - 3;
+      const int64_t hi = (p.col0 + l0 + 15) * p.raw_stride + p.row0 + ib0 + 128 + 8;
+      fast = lo >= 0 && hi <= int64_t(p.raw_end - p.raw);
     }
+    const bool safe = fast || block_is_safe(p, l0, 16, ib0, ib0 + 128);
+    if (fast) {
+      const uint8_t* a = p.raw + (p.col0 + l0) * p.raw_stride + rs.off;
+      uint32_t wx[16];
+      uint32_t shs = 0;  // 2 bits per locus
 #pragma unroll
-    for (int u = 0; u < 32; ++u) {
-      uint32_t w1 = __shfl_down_sync(0xFFFFFFFFu, g[u], 1);
-      if (lane == 31) w1 = wx[u];
-      g[u] = __funnelshift_r(g[u], w1, uint32_t((shs >> (2 * u)) & 3u) * 8);
-      g[u] = (g[u] & rs.keep) | (0x03030303u & ~rs.keep);
-    }
-  } else {
+      for (int u = 0; u < 16; ++u) {
+        const uint32_t sh = uint32_t(reinterpret_cast<uintptr_t>(a) & 3u);
+        shs |= sh << (2 * u);
+        const uint32_t* al = reinterpret_cast<const uint32_t*>(a - sh);
+        g[u] = __ldg(al);
+        wx[u] = 0;
+        if (lane == 31) wx[u] = __ldg(al + 1);
+        a += p.raw_stride;
+      }
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const int l = l0 + k;
-      g[k] = 0x03030303u;
-      if (l < p.lc) {
-        const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
-        g[k] = safe ? load4<true>(p, rs, col, lane) : load4<false>(p, rs, col, lane);
+      for (int u = 0; u < 16; ++u) {
+        uint32_t w1 = __shfl_down_sync(0xFFFFFFFFu, g[u], 1);
+        if (lane == 31) w1 = wx[u];
+        g[u] = __funnelshift_r(g[u], w1, ((shs >> (2 * u)) & 3u) * 8);
+      }
+      if (!full) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) g[u] = (g[u] & rs.keep) | (0x03030303u & ~rs.keep);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int l = l0 + k;
+        g[k] = 0x03030303u;
+        if (l < p.lc) {
+          const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
+          g[k] = safe ? load4<true>(p, rs, col, lane) : load4<false>(p, rs, col, lane);
+        }
       }
     }
-  }
-  // out[plane][r][w]: 8 loci per word, 4 words = 32 loci per individual r
-  uint32_t od[4][4], on[4][4], oh[4][4];
+    // out[r][w]: 8 loci per word, 2 words = 16 loci per individual r
+    uint32_t od[4][2], on[4][2], oh[4][2];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {  // 4 loci at a time: t[r] = loci 4q..4q+3 of individual i0 + r
-    const uint32_t a0 = __byte_perm(g[4 * q], g[4 * q + 1], 0x5140);
-    const uint32_t a1 = __byte_perm(g[4 * q + 2], g[4 * q + 3], 0x5140);
-    const uint32_t b0 = __byte_perm(g[4 * q], g[4 * q + 1], 0x7362);
-    const uint32_t b1 = __byte_perm(g[4 * q + 2], g[4 * q + 3], 0x7362);
-    uint32_t t[4];
-    t[0] = __byte_perm(a0, a1, 0x5410);
-    t[1] = __byte_perm(a0, a1, 0x7632);
-    t[2] = __byte_perm(b0, b1, 0x5410);
-    t[3] = __byte_perm(b0, b1, 0x7632);
+    for (int q = 0; q < 4; ++q) {  // 4 loci at a time: t[r] = loci 4q..4q+3 of individual i0 + r
+      const uint32_t a0 = __byte_perm(g[4 * q], g[4 * q + 1], 0x5140);
+      const uint32_t a1 = __byte_perm(g[4 * q + 2], g[4 * q + 3], 0x5140);
+      const uint32_t b0 = __byte_perm(g[4 * q], g[4 * q + 1], 0x7362);
+      const uint32_t b1 = __byte_perm(g[4 * q + 2], g[4 * q + 3], 0x7362);
+      uint32_t t[4];
+      t[0] = __byte_perm(a0, a1, 0x5410);
+      t[1] = __byte_perm(a0, a1, 0x7632);
+      t[2] = __byte_perm(b0, b1, 0x5410);
+      t[3] = __byte_perm(b0, b1, 0x7632);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        uint32_t cd, cn, ch;
+        codes4(t[r], cd, cn, ch);
+        const int w = q >> 1;
+        if ((q & 1) == 0) { od[r][w] = cd; on[r][w] = cn; oh[r][w] = ch; }          // loci k     -> low nibbles
+        else { od[r][w] |= cd << 4; on[r][w] |= cn << 4; oh[r][w] |= ch << 4; }     // loci k + 4 -> high nibbles
+      }
+    }
+    // 8 bytes per (row, plane) into the row's chunk `warp`, half `half`; chunks swizzled by row
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      uint32_t d, nm, h1;
-      decode4(t[r], d, nm, h1);
-      const uint32_t cd = ((d << 1) & 0x02020202u) | ((d >> 4) & 0x08080808u);  // +1 -> 0x2, -1 -> 0xA
-      const uint32_t cn = nm << 1, ch = h1 << 1;                                 // 1 -> 0x2
-      const int w = q >> 1;
-      if ((q & 1) == 0) { od[r][w] = cd; on[r][w] = cn; oh[r][w] = ch; }          // loci k     -> low nibbles
-      else { od[r][w] |= cd << 4; on[r][w] |= cn << 4; oh[r][w] |= ch << 4; }     // loci k + 4 -> high nibbles
+      const int row = lane * 4 + r, ch = warp ^ ((row >> 2) & 7);
+      reinterpret_cast<uint2*>(&tile[0][row][ch])[half] = make_uint2(od[r][0], od[r][1]);
+      reinterpret_cast<uint2*>(&tile[1][row][ch])[half] = make_uint2(on[r][0], on[r][1]);
+      if (p.nplanes > 2) reinterpret_cast<uint2*>(&tile[2][row][ch])[half] = make_uint2(oh[r][0], oh[r][1]);
     }
   }
-  // Stage the tile's output rows in shared memory (16-byte chunks XOR-swizzled by row so that neither
-  // side has bank conflicts) and write them out as whole 128-byte lines: a lane's own 16 bytes are
-  // 1/8 of a line, and eight warps writing eighths of the same lines is what DRAM likes least.
-  __shared__ uint4 tile[3][128][8];
-  const int rl = lane * 4;  // first local row of this lane
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int row = rl + r, ch = warp ^ ((row >> 2) & 7);
-    tile[0][row][ch] = make_uint4(od[r][0], od[r][1], od[r][2], od[r][3]);
-    tile[1][row][ch] = make_uint4(on[r][0], on[r][1], on[r][2], on[r][3]);
-    if (p.nplanes > 2) tile[2][row][ch] = make_uint4(oh[r][0], oh[r][1], oh[r][2], oh[r][3]);
-  }
   __syncthreads();
+  // whole 128-byte lines out: a warp store covers 4 rows x 8 chunks
   const int64_t pitch = p.lc_pad >> 1;
-  const int ib0r = int(blockIdx.x % nib) * 128;
-  const int lbyte = (int(blockIdx.x / nib) * 256) >> 1;  // this tile's first byte within a plane row
+  const int lbyte = lt >> 1;  // this tile's first byte within a plane row
   for (int pln = 0; pln < p.nplanes; ++pln)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int row = warp * 16 + k * 4 + (lane >> 3), c = lane & 7;  // 4 rows x 8 chunks per warp store
+      const int row = warp * 16 + k * 4 + (lane >> 3), c = lane & 7;
       const uint4 v = tile[pln][row][c ^ ((row >> 2) & 7)];
-      *reinterpret_cast<uint4*>(p.planes + int64_t(pln) * p.plane_stride + int64_t(ib0r + row) * pitch + lbyte + c * 16) = v;
+      *reinterpret_cast<uint4*>(p.planes + int64_t(pln) * p.plane_stride + int64_t(ib0 + row) * pitch + lbyte + c * 16) = v;
     }
 }
 
