@@ -226,7 +226,7 @@ def run_b200(args, rank, world, local):
     counts = eng.new_counts(n)
     out_dev = torch.zeros((n, n), dtype=torch.float64, device=f"cuda:{local}")
     res = L.Result(out0=out_dev.data_ptr(), out1=None, aux0=None, aux1=None, out_on_device=1)
-    agg = {"ms_decode": 0.0, "ms_gram": 0.0, "ms_finish": 0.0, "launches": 0, "chunks": 0, "macs": 0}
+    agg = {"ms_decode": 0.0, "ms_gram": 0.0, "ms_finish": 0.0, "launches": 0, "chunks": 0, "macs": 0, "q4": 0}
 
     def step(record: bool):
         if world == 1:
@@ -258,6 +258,7 @@ def run_b200(args, rank, world, local):
             agg["launches"] += n_l
             agg["chunks"] += st.n_chunks
             agg["macs"] += st.mma_macs
+            agg["q4"] += st.n_mxf4_chunks
 
     def barrier():
         if world > 1:
@@ -359,22 +360,43 @@ def run_b200(args, rank, world, local):
     int8_peak = 2.0 * pk["bf16_tflops"]
     int8_lib = measure_int8_library_peak(local)  # cuBLASLt int8 GEMM on this GPU, outside the timed region
     tr = traffic_from_profile()
+    q4 = agg["q4"] > 0                         # the step's chunks ran the 4-bit route (tpg_stats.n_mxf4_chunks)
     pair = os.environ.get("TPG_GRAM_CTAS", "2") != "1"
-    roof = {"kernel": "gram_i8_pair_kernel (tcgen05.mma.cta_group::2)" if pair else "gram_i8_kernel (cta_group::1)",
-            "bound": "tensor", "achieved": gram_ops / (gram_ms * 1e-3) / 1e12,
-            "peak": int8_peak, "unit": "TFLOP/s", "frac": gram_ops / (gram_ms * 1e-3) / 1e12 / int8_peak,
-            "traffic": tr.get("gram_i8_pair_dram_bytes_per_launch" if pair else "gram_i8_dram_bytes_per_launch"),
-            "note": ("int8 tensor ops (2 per MAC); algorithmic = 4 op per pair-SNP (DD+NN upper, HN full); "
-                     f"peak = 2 x measured bf16 burst from {pk['source']} (nominal int8 dense 4500); "
-                     f"issued incl. tile padding = {2 * agg['macs'] / steps / (agg['ms_gram'] / steps * 1e-3) / 1e12:.0f} TOP/s; "
-                     f"avg launch {gram_ms:.3f} ms over {agg['chunks'] // steps} launch(es)/step"),
-            "int8_library_peak": int8_lib,
-            "frac_of_int8_library_peak": (gram_ops / (gram_ms * 1e-3) / 1e12 / int8_lib["tops"]) if int8_lib else None}
-    dec_bytes = DECODE_BYTES_PER_GENOTYPE * n * loci_per_launch
-    roof_dec = {"kernel": "decode_planes_mn_kernel", "bound": "hbm", "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9,
+    achieved = gram_ops / (gram_ms * 1e-3) / 1e12
+    issued = 2 * agg["macs"] / steps / (agg["ms_gram"] / steps * 1e-3) / 1e12
+    if q4:
+        # The contraction runs as E2M1 x E2M1 -> f32 (exact for these integer sums): the
+        # roofline is the dense 4-bit tensor peak.  MEASURED_PEAKS.json has bf16 only; the 4-bit MMA
+        # issues 4x the bf16 MACs per cycle (nominal 9 vs 2.25 PFLOP/s), so peak = 4 x measured bf16.
+        peak = 4.0 * pk["bf16_tflops"]
+        roof = {"kernel": "gram_mxf4_pair_kernel (tcgen05.mma.cta_group::2.kind::mxf4.block_scale)", "bound": "tensor",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": tr.get("gram_mxf4_pair_dram_bytes_per_launch"),
+                "note": ("4-bit tensor ops (2 per MAC); algorithmic = 4 op per pair-SNP (DD+NN upper, HN full); "
+                         f"peak = 4 x measured bf16 burst from {pk['source']} (nominal 4-bit dense 9000); "
+                         f"issued incl. tile padding = {issued:.0f} TOP/s; the same products on the int8 kernel "
+                         "(TPG_GRAM_I8=1) reach 0.84 of 2 x bf16; "
+                         f"avg launch {gram_ms:.3f} ms over {agg['chunks'] // steps} launch(es)/step"),
+                "int8_library_peak": int8_lib,
+                "frac_of_int8_library_peak": (achieved / int8_lib["tops"]) if int8_lib else None}
+    else:
+        roof = {"kernel": "gram_i8_pair_kernel (tcgen05.mma.cta_group::2)" if pair else "gram_i8_kernel (cta_group::1)",
+                "bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TFLOP/s", "frac": achieved / int8_peak,
+                "traffic": tr.get("gram_i8_pair_dram_bytes_per_launch" if pair else "gram_i8_dram_bytes_per_launch"),
+                "note": ("int8 tensor ops (2 per MAC); algorithmic = 4 op per pair-SNP (DD+NN upper, HN full); "
+                         f"peak = 2 x measured bf16 burst from {pk['source']} (nominal int8 dense 4500); "
+                         f"issued incl. tile padding = {issued:.0f} TOP/s; "
+                         f"avg launch {gram_ms:.3f} ms over {agg['chunks'] // steps} launch(es)/step"),
+                "int8_library_peak": int8_lib,
+                "frac_of_int8_library_peak": (achieved / int8_lib["tops"]) if int8_lib else None}
+    bytes_per_gt = 2.5 if q4 else DECODE_BYTES_PER_GENOTYPE
+    dec_bytes = bytes_per_gt * n * loci_per_launch
+    roof_dec = {"kernel": "decode_planes_k4_kernel" if q4 else "decode_planes_mn_kernel", "bound": "hbm",
+                "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9,
                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-                "traffic": tr.get("decode_planes_dram_bytes_per_launch"),
-                "note": f"1 B read + 3 B written per genotype; avg launch {dec_ms:.3f} ms; peak from {pk['source']}"}
+                "traffic": tr.get("decode_planes_k4_dram_bytes_per_launch" if q4 else "decode_planes_dram_bytes_per_launch"),
+                "note": (f"1 B read + {'1.5 (three 4-bit planes)' if q4 else '3'} B written per genotype; "
+                         f"avg launch {dec_ms:.3f} ms; peak from {pk['source']}")}
 
     # ---- CPU baseline on this host: the reference path restated (oracle/blas_baseline.py)
     cpu = None
@@ -392,12 +414,12 @@ def run_b200(args, rank, world, local):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "e2m1 x e2m1 -> f32 (exact integer sums) + int8 -> s32" if agg["q4"] else "int8",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "n": n, "m_per_gpu": m, "m_global": m_global,
                    "sharding": "none" if world == 1 else f"loci x{world}, one NCCL all-reduce of int32 counts",
                    "l2": "inputs larger than L2 (604 MB raw + 2 GB planes per step vs 126 MB), no flush needed",
-                   "int8_ops_per_pair_snp": KING_INT8_OPS_PER_PAIRSNP},
+                   "tensor_ops_per_pair_snp": KING_INT8_OPS_PER_PAIRSNP},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": e2e_h2d // e2e_steps, "d2h_bytes_per_step": 8 * n * n,

@@ -134,6 +134,7 @@ typedef struct tpg_stats {
   int64_t mma_macs;   /* int8 MACs issued to the tensor pipe (incl. padding)        */
   int64_t n_short;    /* allele-sharing padding-quirk constant that was applied     */
   int64_t n_packed_chunks; /* chunks that crossed PCIe 2-bit packed (4 genotypes / byte)  */
+  int64_t n_mxf4_chunks;   /* chunks whose products ran on the 4-bit kind::mxf4 kernel   */
 } tpg_stats;
 
 /*

@@ -41,8 +41,8 @@ def test_enums_match_header():
 def test_struct_layout_matches_c():
     # offsets the C compiler would produce for the declared field order (LP64)
     assert C.sizeof(L.Job) == 120 and L.Job.bk_path.offset == 16 and L.Job.flags.offset == 112
-    assert C.sizeof(L.Stats) == 112
-    assert C.sizeof(L.Result) == 40 + 112 and L.Result.stats.offset == 40
+    assert C.sizeof(L.Stats) == 120
+    assert C.sizeof(L.Result) == 40 + 120 and L.Result.stats.offset == 40
 
 
 def test_version_and_device_count_without_gpu():

@@ -75,6 +75,7 @@ class Stats(C.Structure):
         ("mma_macs", C.c_int64),
         ("n_short", C.c_int64),
         ("n_packed_chunks", C.c_int64),
+        ("n_mxf4_chunks", C.c_int64),
     ]
 
     def as_dict(self) -> dict:

@@ -488,7 +488,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   double ms_read = 0;
   // hybrid link/core scheduling state (see the chunk loop)
   cudaEvent_t ev_pin_free[2] = {B.ev(false), B.ev(false)};
-  int64_t n_staged = 0, n_packed = 0;
+  int64_t n_staged = 0, n_packed = 0, n_q4 = 0;
   double link_free_at = 0, link_gbps = 45.0;
   double pack_gbps = 4.0 * double(HostPool::max_threads());
   if (const char* ev = getenv("TPG_LINK_GBPS")) link_gbps = std::max(1.0, atof(ev));
@@ -702,6 +702,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     ga.n_pad = pl.n_pad;
     ga.lc_pad = use_q4 ? q4_lc_pad : lc_pad;
     ga.mxf4 = use_q4;
+    if (use_q4) n_q4++;
     ga.k_major = k_major;
     ga.ctas = (job->flags & TPG_FLAG_GRAM_1CTA) ? 1 : 0;
     ga.prod_mask = pl.prod_mask;
@@ -726,6 +727,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   st->ms_read += ms_read;
   st->n_chunks += n_chunks;
   st->n_packed_chunks += n_packed;
+  st->n_mxf4_chunks += n_q4;
   st->mma_macs += macs;
   st->ms_total += now_ms() - t_begin;
   return TPG_OK;
@@ -1016,6 +1018,7 @@ static int pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* de
     res->stats.bytes_h2d += sts[r].bytes_h2d;
     res->stats.n_chunks += sts[r].n_chunks;
     res->stats.n_packed_chunks += sts[r].n_packed_chunks;
+    res->stats.n_mxf4_chunks += sts[r].n_mxf4_chunks;
     res->stats.mma_macs += sts[r].mma_macs;
     res->stats.n_launches += sts[r].n_launches;
   }

@@ -585,6 +585,7 @@ static int make_plane_map(Ctx* ctx, CUtensorMap* out, const int8_t* base, uint64
 
 // Chooses how many k-splits a tile gets so that the persistent CTAs finish together.
 static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms) {
+  if (const char* ev = getenv("TPG_GRAM_KS")) return int(std::max<int64_t>(1, std::min<int64_t>(kblocks, atoi(ev))));
   // Large problems: every CTA runs many items, balance is not the issue — L2 is.  CTAs that
   // run side by side share operand panels only while they stream the same loci; over a long
   // k range they drift apart and every CTA ends up fetching its panels from HBM by itself
