@@ -389,7 +389,11 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   // Gram kernel (twice the int8 MAC rate, half the plane bytes, exact: gram.cu).  2-bit packed chunks
   // and tile-sharded jobs use the int8 kernels; both kinds add into the same int32 counts.
   const bool q4_forced_off = (job->flags & (TPG_FLAG_GRAM_I8 | TPG_FLAG_GRAM_1CTA)) || getenv("TPG_GRAM_I8");
-  const bool q4_ok = !scan && !k_major && !q4_forced_off && !(job->shard_mode == TPG_SHARD_TILES && job->shard_world > 1);
+  // (tile-sharded jobs: only while ownership is dealt in 1024-column regions, which the 4-bit kernel's
+  //  240 + 240 + 240 + 240 + 64 column tiles respect)
+  const bool q4_tiles_ok = !(job->shard_mode == TPG_SHARD_TILES && job->shard_world > 1) ||
+                           shard_region_blocks(pl.n_pad / 256, job->shard_world) == 4;
+  const bool q4_ok = !scan && !k_major && !q4_forced_off && q4_tiles_ok;
   const bool direct_only = direct_ok && !pack_ok;
   if (direct_only) { span = nrow; rlo = 0; }
   const int64_t pk_stride = pk2_stride(span);

@@ -457,13 +457,14 @@ gram_mxf4_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
       uint32_t phase = 0;
       for (int it = cluster; it < p.n_items; it += n_clusters) {
         const WorkItem w = p.items[it];
-        const int prod = w.prod_ti & 15, ti = w.prod_ti >> 8, tj = w.tj;
+        const int prod = w.prod_ti & 15, ti = w.prod_ti >> 8;
+        const int ncols = (((w.prod_ti >> 4) & 15) + 1) * 16;        // N of this tile (240, or 64 at a region's edge)
         int pa, pb;
         prod_planes(prod, pa, pb);
         const CUtensorMap* ma = pa == 0 ? &tm_d : pa == 1 ? &tm_nm : &tm_h1;
         const CUtensorMap* mb = pb == 0 ? &tm_d : pb == 1 ? &tm_nm : &tm_h1;
         const int row_a = ti * kPairTileM + int(rank) * 128;
-        const int row_b = tj * kQTileN + int(rank) * (kQTileN / 2);  // 120 of the 128 loaded rows are used
+        const int row_b = w.tj + int(rank) * (ncols / 2);            // w.tj = first column; N/2 of the 128 loaded rows are used
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
           uint8_t* sa = smem + stage * kPairStageBytes;
@@ -480,7 +481,7 @@ gram_mxf4_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA only)
     if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_mxf4(kPairTileM, kQTileN);
+      constexpr uint32_t idesc0 = make_idesc_mxf4(kPairTileM, 0);
       const uint32_t sfa = tmem_base + 240u, sfb = tmem_base + 244u;
       int stage = 0;
       uint32_t phase = 0;
@@ -488,6 +489,8 @@ gram_mxf4_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
       uint32_t acc_phase = 0;
       for (int it = cluster; it < p.n_items; it += n_clusters) {
         const WorkItem w = p.items[it];
+        const uint32_t ncols = (((uint32_t(w.prod_ti) >> 4) & 15u) + 1u) * 16u;
+        const uint32_t idesc = idesc0 | ((ncols >> 3) << 17);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(acc * 256);
@@ -518,19 +521,20 @@ gram_mxf4_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
     uint32_t acc_phase = 0;
     for (int it = cluster; it < p.n_items; it += n_clusters) {
       const WorkItem w = p.items[it];
-      const int prod = w.prod_ti & 15, ti = w.prod_ti >> 8, tj = w.tj;
+      const int prod = w.prod_ti & 15, ti = w.prod_ti >> 8;
+      const int ncols = (((w.prod_ti >> 4) & 15) + 1) * 16;   // >= 32
       const bool sym = prod != TPG_MAT_HN;
       mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
       tc_fence_after();
       const int i = ti * kPairTileM + int(rank) * 128 + q * 32 + lane;
-      const int j0 = tj * kQTileN;
+      const int j0 = w.tj;
       int32_t* cbase = p.counts + int64_t(prod) * p.mat_stride + i;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 256);
 #pragma unroll 1
-      for (int c = 0; c < kQTileN; c += 32) {
-        const bool last = c + 32 >= kQTileN;
-        const int cc = last ? kQTileN - 32 : c;     // the last 32-column load overlaps the previous one
-        const int first = last ? 32 - (kQTileN - c) : 0;
+      for (int c = 0; c < ncols; c += 32) {
+        const bool last = c + 32 >= ncols;
+        const int cc = last ? ncols - 32 : c;       // the last 32-column load overlaps the previous one
+        const int first = last ? 32 - (ncols - c) : 0;
         uint32_t v[32];
         tmem_ld_32x32(taddr + uint32_t(cc), v);
         tmem_ld_wait();
@@ -614,7 +618,9 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   if (a.n_pad % kRowPad || a.lc_pad % kQStageLoci || a.lc_pad <= 0)
     return E.fail(TPG_ERR_ARG, "gram(mxf4): n_pad (%lld) / lc_pad (%lld) not multiples of 256",
                   (long long)a.n_pad, (long long)a.lc_pad);
-  if (a.shard_world > 1) return E.fail(TPG_ERR_ARG, "gram(mxf4): tile sharding uses the int8 kernels");
+  const int64_t nblocks = a.n_pad / 256;
+  if (a.shard_world > 1 && shard_region_blocks(nblocks, a.shard_world) != 4)
+    return E.fail(TPG_ERR_ARG, "gram(mxf4): tile sharding needs 1024-column ownership regions (int8 kernels otherwise)");
   if (!ctx->gram_attr_set) {
     GramArgs probe = a;   // sets the attributes of every gram kernel and counts the resident CTA pairs
     probe.mxf4 = false;
@@ -628,28 +634,49 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   }
   if (ctx->pair_clusters <= 0) return E.fail(TPG_ERR_CUDA, "gram(mxf4): the device reports no resident CTA pairs");
   const int units = ctx->pair_clusters;
-  const int64_t tiles_m = a.n_pad / kPairTileM, tiles_n = (a.n + kQTileN - 1) / kQTileN;
+  const int64_t tiles_m = a.n_pad / kPairTileM;
   const int64_t kblocks = a.lc_pad / kQStageLoci;
-  struct T { int prod, ti, tj; };
+  // Column tiles: every 1024-column region (the ownership / L2 unit) is cut into 240 + 240 + 240 + 240 + 64,
+  // so tiles never straddle a region; unsharded jobs simply run 240-wide tiles across the whole width.
+  struct T { int prod, ti, col0, ncols; };
   std::vector<T> tiles;
-  const int64_t RI = 4, RJ = 4;
-  for (int64_t rj = 0; rj < tiles_n; rj += RJ)
+  std::vector<std::pair<int, int>> cols;  // (first column, N)
+  if (a.shard_world > 1) {
+    for (int64_t r0 = 0; r0 < a.n; r0 += 1024)
+      for (int s5 = 0; s5 < 5; ++s5) {
+        const int64_t c0 = r0 + 240 * s5;
+        if (c0 < a.n) cols.push_back({int(c0), s5 < 4 ? kQTileN : 64});
+      }
+  } else {
+    for (int64_t c0 = 0; c0 < a.n; c0 += kQTileN) cols.push_back({int(c0), kQTileN});
+  }
+  const int64_t RI = 4;
+  const size_t RJ = a.shard_world > 1 ? 5 : 4;
+  for (size_t rj = 0; rj < cols.size(); rj += RJ)
     for (int64_t ri = 0; ri < tiles_m; ri += RI)
-      for (int64_t tj = rj; tj < std::min(rj + RJ, tiles_n); ++tj)
+      for (size_t cj = rj; cj < std::min(rj + RJ, cols.size()); ++cj)
         for (int64_t ti = ri; ti < std::min(ri + RI, tiles_m); ++ti) {
           if (kPairTileM * ti >= a.n) continue;  // rows of padding individuals only
-          const bool upper = kQTileN * tj + (kQTileN - 1) >= kPairTileM * ti;
+          const int c0 = cols[cj].first, nc = cols[cj].second;
+          const bool upper = c0 + nc - 1 >= kPairTileM * ti;
+          const int64_t bi = ti, bj = c0 / 256;  // 256-blocks; ownership is per 1024 region, so any block of the tile will do
           for (int prod = 0; prod < TPG_NUM_COUNT_MATS; ++prod) {
             if (!(a.prod_mask & (1 << prod))) continue;
             if (prod != TPG_MAT_HN && !upper) continue;
-            tiles.push_back({prod, int(ti), int(tj)});
+            if (!block_owned(std::min(bi, bj), std::max(bi, bj), nblocks, a.shard_rank, a.shard_world)) continue;
+            tiles.push_back({prod, int(ti), c0, nc});
           }
         }
   if (tiles.empty()) { if (macs_out) *macs_out = 0; return TPG_OK; }
   const int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units);
-  if (macs_out) *macs_out = int64_t(tiles.size()) * kPairTileM * kQTileN * a.lc_pad;
+  if (macs_out) {
+    int64_t cells = 0;
+    for (const T& t : tiles) cells += int64_t(kPairTileM) * t.ncols;
+    *macs_out = cells * a.lc_pad;
+  }
   char key[200];
-  snprintf(key, sizeof key, "q4/%lld/%lld/%lld/%d/%d", (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad, a.prod_mask, ks);
+  snprintf(key, sizeof key, "q4/%lld/%lld/%lld/%d/%d/%d/%d", (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad, a.prod_mask, ks,
+           a.shard_rank, a.shard_world);
   if (ctx->items_key != key) {
     std::vector<WorkItem>& items = ctx->h_items;
     items.clear();
@@ -657,7 +684,7 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
     for (int s = 0; s < ks; ++s) {
       const int32_t kb0 = int32_t(kblocks * s / ks), kb1 = int32_t(kblocks * (s + 1) / ks);
       if (kb1 <= kb0) continue;
-      for (const T& t : tiles) items.push_back({int32_t(t.prod | (t.ti << 8)), t.tj, kb0, kb1});
+      for (const T& t : tiles) items.push_back({int32_t(t.prod | ((t.ncols / 16 - 1) << 4) | (t.ti << 8)), t.col0, kb0, kb1});
     }
     if (items.size() > ctx->d_items_cap) {
       TPG_CUDA_OK(cudaStreamSynchronize(st), E);
