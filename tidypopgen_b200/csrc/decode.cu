@@ -325,7 +325,7 @@ __device__ __forceinline__ void codes4(uint32_t g, uint32_t& cd, uint32_t& cn, u
   cd = c0 * 5u + c2;                                    // 0x02 * 5 = 0x0A (-1), no carries between bytes
 }
 
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 decode_planes_k4_kernel(const DecodeParams p) {
   __shared__ uint4 tile[3][128][8];  // output rows, 16-byte chunks XOR-swizzled by row
   const int lane = threadIdx.x & 31;
