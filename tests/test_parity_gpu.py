@@ -563,8 +563,8 @@ def test_biobank_regime_sampled_pairs_and_region_sharding():
     X.backingfile, X.nrow, X.ncol, X.code256 = "<device>", n, m, None
     src = (L.SRC_DEVICE, raw.data_ptr(), raw)
     from tidypopgen_b200 import snp
-    def run(shard, rank):
-        job, keep = snp.make_job(X, None, None, L.STAT_KING, snp.block_size(n), src=src,
+    def run(shard, rank, flags=0):
+        job, keep = snp.make_job(X, None, None, L.STAT_KING, snp.block_size(n), src=src, flags=flags,
                                  shard_mode=L.SHARD_TILES if shard else L.SHARD_NONE, shard_rank=rank,
                                  shard_world=world if shard else 1)
         counts = eng.new_counts(n)
@@ -573,6 +573,11 @@ def test_biobank_regime_sampled_pairs_and_region_sharding():
         del counts
         return out                                   # torch [i, j] view of the column-major result
     full = run(False, 0)
+    assert eng.last_stats["n_mxf4_chunks"] >= 1          # the default (4-bit) route ...
+    i8 = run(False, 0, L.FLAG_GRAM_I8)                   # ... and the int8 route give the same matrix, bit for bit
+    assert eng.last_stats["n_mxf4_chunks"] == 0
+    assert torch.equal(i8.nan_to_num(-9.0), full.nan_to_num(-9.0))
+    del i8
     cols = raw[: n * m].view(m, n)
     rng = np.random.default_rng(4)
     for k in range(48):
