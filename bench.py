@@ -418,7 +418,7 @@ def run_b200(args, rank, world, local):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "n": n, "m_per_gpu": m, "m_global": m_global,
                    "sharding": "none" if world == 1 else f"loci x{world}, one NCCL all-reduce of int32 counts",
-                   "l2": "inputs larger than L2 (604 MB raw + 2 GB planes per step vs 126 MB), no flush needed",
+                   "l2": "inputs larger than L2 (604 MB raw + 1 GB of 4-bit planes (2 GB int8) per step vs 126 MB), no flush needed",
                    "tensor_ops_per_pair_snp": KING_INT8_OPS_PER_PAIRSNP},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT,
