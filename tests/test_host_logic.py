@@ -138,3 +138,15 @@ def test_host_pool_serves_concurrent_callers():
     assert not any(t.is_alive() for t in th)
     for raw, nrow, ncol, out in jobs:
         assert np.array_equal(out, pk2_ref(raw, nrow, ncol, 0, nrow))
+
+
+def test_swar_decode_arithmetic(tmp_path):
+    """The word-parallel arithmetic of decode_planes_k4_kernel (csrc/swar.cuh) against the reference's
+    per-genotype rule, every byte value in every lane position — compiled for the host with g++."""
+    import subprocess
+    from pathlib import Path
+    src = Path(__file__).resolve().parent / "swar_check.cpp"
+    exe = tmp_path / "swar_check"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("ok ")

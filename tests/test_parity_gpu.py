@@ -378,12 +378,16 @@ def k4_pack(plane):
     return (g[:, :, 0, :] | (g[:, :, 1, :] << 4)).reshape(r, lc // 2)
 
 
+@pytest.mark.parametrize("first_build", [False, True], ids=["k4", "k4_v1"])
+@pytest.mark.parametrize("nrow", [929, 928, 1023], ids=["odd_stride", "aligned_stride", "stride_3mod4"])
 @pytest.mark.parametrize("gather", [False, True])
-def test_decode_planes_k4_kernel(gather):
+def test_decode_planes_k4_kernel(gather, nrow, first_build, monkeypatch):
     import torch
+    if first_build:
+        monkeypatch.setenv("TPG_DECODE_K4_V1", "1")  # the round's first kernel, kept as the cross-check
     ctx = L.Context(0)
     rng = np.random.default_rng(3)
-    nrow, ncol = 929, 900
+    ncol = 900
     raw = rng.integers(0, 256, size=(ncol, nrow)).astype(np.uint8)
     raw[rng.random(raw.shape) < 0.8] %= 4
     if gather:

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include "internal.h"
+#include "swar.cuh"
 
 namespace tpg {
 
@@ -325,8 +326,10 @@ __device__ __forceinline__ void codes4(uint32_t g, uint32_t& cd, uint32_t& cn, u
   cd = c0 * 5u + c2;                                    // 0x02 * 5 = 0x0A (-1), no carries between bytes
 }
 
+// First build of the kernel (byte-density codes4 after the transposes, shuffle-assembled loads):
+// kept selectable (TPG_DECODE_K4_V1=1) as the cross-check of decode_planes_k4_kernel below.
 __global__ void __launch_bounds__(256, 4)
-decode_planes_k4_kernel(const DecodeParams p) {
+decode_planes_k4_v1_kernel(const DecodeParams p) {
   __shared__ uint4 tile[3][128][8];  // output rows, 16-byte chunks XOR-swizzled by row
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -406,6 +409,101 @@ decode_planes_k4_kernel(const DecodeParams p) {
         if ((q & 1) == 0) { od[r][w] = cd; on[r][w] = cn; oh[r][w] = ch; }          // loci k     -> low nibbles
         else { od[r][w] |= cd << 4; on[r][w] |= cn << 4; oh[r][w] |= ch << 4; }     // loci k + 4 -> high nibbles
       }
+    }
+    // 8 bytes per (row, plane) into the row's chunk `warp`, half `half`; chunks swizzled by row
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = lane * 4 + r, ch = warp ^ ((row >> 2) & 7);
+      reinterpret_cast<uint2*>(&tile[0][row][ch])[half] = make_uint2(od[r][0], od[r][1]);
+      reinterpret_cast<uint2*>(&tile[1][row][ch])[half] = make_uint2(on[r][0], on[r][1]);
+      if (p.nplanes > 2) reinterpret_cast<uint2*>(&tile[2][row][ch])[half] = make_uint2(oh[r][0], oh[r][1]);
+    }
+  }
+  __syncthreads();
+  // whole 128-byte lines out: a warp store covers 4 rows x 8 chunks
+  const int64_t pitch = p.lc_pad >> 1;
+  const int lbyte = lt >> 1;  // this tile's first byte within a plane row
+  for (int pln = 0; pln < p.nplanes; ++pln)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int row = warp * 16 + k * 4 + (lane >> 3), c = lane & 7;
+      const uint4 v = tile[pln][row][c ^ ((row >> 2) & 7)];
+      *reinterpret_cast<uint4*>(p.planes + int64_t(pln) * p.plane_stride + int64_t(ib0 + row) * pitch + lbyte + c * 16) = v;
+    }
+}
+
+// The default build.  Same block shape, layout and staging as above; what changed is the
+// instruction count of the straight-line path (the first build was issue-bound: 648 instructions
+// per 64 genotypes and lane, ncu issue slots 63 % busy at 0.58 of the HBM figure):
+//   * loads: one IMAD.WIDE forms the address of column u (a0 + u * stride), both aligned words
+//     are loaded by the lane itself (the second one is an L1 hit) — no shuffle, no select, no
+//     packed shift table;
+//   * compute at nibble density (swar.cuh): bytes are clamped to 2-bit codes first (5 ops per
+//     4 genotypes), loci k and k + 4 are paired into nibbles BEFORE the 4x4 byte transposes
+//     (half the PRMTs), and the three E2M1 codes are derived on 8 genotypes per word (6 ops).
+__global__ void __launch_bounds__(256, 4)
+decode_planes_k4_kernel(const DecodeParams p) {
+  __shared__ uint4 tile[3][128][8];  // output rows, 16-byte chunks XOR-swizzled by row
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nib = p.n_pad / 128;
+  const int ib0 = int(blockIdx.x % nib) * 128;
+  const int i0 = ib0 + lane * 4;
+  const int lt = int(blockIdx.x / nib) * 256;               // lc_pad is a multiple of 256: always in range
+  const RowSel rs = make_rowsel(p, i0);
+  const bool full = rs.keep == 0xFFFFFFFFu;
+  const bool plain = !p.row_idx && !p.col_idx && p.raw_stride < (int64_t(1) << 27);
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {                     // 16 loci at a time keeps the registers down
+    const int l0 = lt + warp * 32 + half * 16;
+    uint32_t g[16];
+    bool fast = plain && l0 + 16 <= p.lc;
+    if (fast) {
+      const int64_t lo = (p.col0 + l0) * p.raw_stride + p.row0 + ib0 - 3;
+      const int64_t hi = (p.col0 + l0 + 15) * p.raw_stride + p.row0 + ib0 + 128 + 8;
+      fast = lo >= 0 && hi <= int64_t(p.raw_end - p.raw);
+    }
+    if (fast) {
+      const uint64_t a0 = uint64_t(reinterpret_cast<uintptr_t>(p.raw + (p.col0 + l0) * p.raw_stride + rs.off));
+      const uint32_t stride = uint32_t(p.raw_stride);        // < 2^27: 15 * stride fits 32 bits
+      uint32_t w1[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        uint64_t au;
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(au) : "r"(stride), "r"(uint32_t(u)), "l"(a0));
+        const uint32_t* al = reinterpret_cast<const uint32_t*>(uintptr_t(au & ~uint64_t(3)));
+        g[u] = __ldg(al);
+        w1[u] = __ldg(al + 1);
+      }
+      const uint32_t a8 = uint32_t(a0) << 3, s8 = stride << 3;  // the funnel shift takes its amount mod 32
+#pragma unroll
+      for (int u = 0; u < 16; ++u) g[u] = __funnelshift_r(g[u], w1[u], a8 + uint32_t(u) * s8);
+    } else {
+      const bool safe = block_is_safe(p, l0, 16, ib0, ib0 + 128);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int l = l0 + k;
+        g[k] = 0x03030303u;
+        if (l < p.lc) {
+          const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
+          g[k] = safe ? load4<true>(p, rs, col, lane) : load4<false>(p, rs, col, lane);
+        }
+      }
+    }
+    if (fast && !full) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) g[u] |= ~rs.keep;         // individuals >= n: any byte above 2 is missing
+    }
+    // 2-bit codes; loci k (low nibble) and k + 4 (high nibble) of each group of 8 share a byte
+    uint32_t od[4][2], on[4][2], oh[4][2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      uint32_t pr[4], t[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pr[k] = nibble_pair(clamp4(g[8 * w + k]), clamp4(g[8 * w + 4 + k]));
+      transpose4x4(pr, t);                                    // t[r]: byte k = loci (k, k + 4) of individual i0 + r
+#pragma unroll
+      for (int r = 0; r < 4; ++r) codes8(t[r], od[r][w], on[r][w], oh[r][w]);
     }
     // 8 bytes per (row, plane) into the row's chunk `warp`, half `half`; chunks swizzled by row
 #pragma unroll
@@ -687,7 +785,9 @@ int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E) 
       return E.fail(TPG_ERR_ARG, "decode(k4): lc_pad must be a multiple of 256, planes 16-byte aligned, raw-byte input");
     const int64_t blocks = (a.n_pad / 128) * (a.lc_pad / 256);
     if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "decode: chunk too large for one launch");
-    decode_planes_k4_kernel<<<unsigned(blocks), 256, 0, st>>>(p);
+    const bool v1 = getenv("TPG_DECODE_K4_V1") != nullptr;  // the first build, kept as a cross-check
+    if (v1) decode_planes_k4_v1_kernel<<<unsigned(blocks), 256, 0, st>>>(p);
+    else decode_planes_k4_kernel<<<unsigned(blocks), 256, 0, st>>>(p);
   } else if (a.packed) {
     if (a.k_major || a.row_idx || a.col_idx || a.row0 || a.col0 || a.raw_stride % 16 || a.plane_stride % 16 ||
         (reinterpret_cast<uintptr_t>(a.raw) & 15) || (reinterpret_cast<uintptr_t>(a.planes) & 15))
