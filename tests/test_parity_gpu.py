@@ -192,6 +192,29 @@ def test_random_parity_all_stats(case, variant):
     assert np.array_equal(np.isnan(g), ~ok) and np.allclose(g[ok], ref_g[ok], rtol=0, atol=GRM_ATOL)
 
 
+# builds of the 4-bit decode kernel: the default and the round's first one (decode.cu)
+K4_BUILDS = {"k4": {}, "k4_v1": {"TPG_DECODE_K4_V1": "1"}}
+
+
+@pytest.mark.parametrize("build", list(K4_BUILDS))
+def test_k4_builds_whole_job(build, monkeypatch):
+    """Every build of the 4-bit decode kernel through whole KING / allele-sharing jobs (3 and 2 planes)."""
+    for k, v in K4_BUILDS[build].items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(11)
+    n, m = 389, 3000
+    raw = random_bk(rng, n, m, 0.08, codes=(0, 1, 2, 3, 4, 5, 6, 255))
+    X = fbm_of(raw, n, m)
+    for rows, cols in ((None, None), (pick("shuffle", n, rng), pick("every3", m, rng))):
+        ref_k = O.snp_king(raw, n, m, rows, cols)
+        king, K, N = tpg.snp_king_counts(X, rows, cols, flags=L.FLAG_NO_PACK, gpu_chunk_loci=1024)
+        assert tpg.snp.last_stats["n_mxf4_chunks"] >= 1
+        assert np.array_equal(K, ref_k["K"]) and np.array_equal(N, ref_k["N_Aa_i"]) and same(king, ref_k["king"])
+        ref_a = O.snp_allele_sharing(raw, n, m, rows, cols)
+        a, num, den = tpg.snp_allele_sharing_counts(X, rows, cols, flags=L.FLAG_NO_PACK)
+        assert np.array_equal(num, ref_a["num"]) and np.array_equal(den, ref_a["denom"]) and same(a, ref_a["as"])
+
+
 def test_pad_quirk_switch():
     rng = np.random.default_rng(5)
     raw = random_bk(rng, 50, 1003)
@@ -378,13 +401,13 @@ def k4_pack(plane):
     return (g[:, :, 0, :] | (g[:, :, 1, :] << 4)).reshape(r, lc // 2)
 
 
-@pytest.mark.parametrize("first_build", [False, True], ids=["k4", "k4_v1"])
+@pytest.mark.parametrize("build", list(K4_BUILDS))
 @pytest.mark.parametrize("nrow", [929, 928, 1023], ids=["odd_stride", "aligned_stride", "stride_3mod4"])
 @pytest.mark.parametrize("gather", [False, True])
-def test_decode_planes_k4_kernel(gather, nrow, first_build, monkeypatch):
+def test_decode_planes_k4_kernel(gather, nrow, build, monkeypatch):
     import torch
-    if first_build:
-        monkeypatch.setenv("TPG_DECODE_K4_V1", "1")  # the round's first kernel, kept as the cross-check
+    for k, v in K4_BUILDS[build].items():  # the default kernel and the round's first one
+        monkeypatch.setenv(k, v)
     ctx = L.Context(0)
     rng = np.random.default_rng(3)
     ncol = 900

@@ -441,6 +441,12 @@ decode_planes_k4_v1_kernel(const DecodeParams p) {
 //   * compute at nibble density (swar.cuh): bytes are clamped to 2-bit codes first (5 ops per
 //     4 genotypes), loci k and k + 4 are paired into nibbles BEFORE the 4x4 byte transposes
 //     (half the PRMTs), and the three E2M1 codes are derived on 8 genotypes per word (6 ops).
+// 0.376 -> 0.329 ms on the 929 x 650,000 chunk (ncu: 154 M warp instructions instead of 278 M, issue
+// slots 43 % busy, DRAM 4.75 TB/s).  Measured beside it and rejected: writing 16 bytes per
+// (individual, plane) straight from registers, no shared memory and no barrier — 0.81 ms when the
+// two halves of a 32-byte sector come from different warps (partial-sector writes), 0.40 ms when
+// one store instruction completes the sector; issuing all 32 loci of loads before decoding
+// (80 registers, 3 CTAs per SM) changed nothing.
 __global__ void __launch_bounds__(256, 4)
 decode_planes_k4_kernel(const DecodeParams p) {
   __shared__ uint4 tile[3][128][8];  // output rows, 16-byte chunks XOR-swizzled by row
@@ -505,13 +511,16 @@ decode_planes_k4_kernel(const DecodeParams p) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) codes8(t[r], od[r][w], on[r][w], oh[r][w]);
     }
-    // 8 bytes per (row, plane) into the row's chunk `warp`, half `half`; chunks swizzled by row
+    // 8 bytes per (row, plane) into the row's chunk `warp`, half `half`; chunks swizzled by row, and
+    // the two halves of a chunk swapped for lanes 8-15 and 24-31, so that the 16 lanes of a half-warp
+    // hit 16 different 8-byte bank pairs (without the swap lanes L and L + 8 collide).
+    const int hs = half ^ ((lane >> 3) & 1);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int row = lane * 4 + r, ch = warp ^ ((row >> 2) & 7);
-      reinterpret_cast<uint2*>(&tile[0][row][ch])[half] = make_uint2(od[r][0], od[r][1]);
-      reinterpret_cast<uint2*>(&tile[1][row][ch])[half] = make_uint2(on[r][0], on[r][1]);
-      if (p.nplanes > 2) reinterpret_cast<uint2*>(&tile[2][row][ch])[half] = make_uint2(oh[r][0], oh[r][1]);
+      reinterpret_cast<uint2*>(&tile[0][row][ch])[hs] = make_uint2(od[r][0], od[r][1]);
+      reinterpret_cast<uint2*>(&tile[1][row][ch])[hs] = make_uint2(on[r][0], on[r][1]);
+      if (p.nplanes > 2) reinterpret_cast<uint2*>(&tile[2][row][ch])[hs] = make_uint2(oh[r][0], oh[r][1]);
     }
   }
   __syncthreads();
@@ -522,7 +531,8 @@ decode_planes_k4_kernel(const DecodeParams p) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int row = warp * 16 + k * 4 + (lane >> 3), c = lane & 7;
-      const uint4 v = tile[pln][row][c ^ ((row >> 2) & 7)];
+      uint4 v = tile[pln][row][c ^ ((row >> 2) & 7)];
+      if ((row >> 5) & 1) v = make_uint4(v.z, v.w, v.x, v.y);  // undo the half swap (row >> 2 = the writing lane)
       *reinterpret_cast<uint4*>(p.planes + int64_t(pln) * p.plane_stride + int64_t(ib0 + row) * pitch + lbyte + c * 16) = v;
     }
 }

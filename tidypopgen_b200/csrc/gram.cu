@@ -648,7 +648,12 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
         if (c0 < a.n) cols.push_back({int(c0), s5 < 4 ? kQTileN : 64});
       }
   } else {
-    for (int64_t c0 = 0; c0 < a.n; c0 += kQTileN) cols.push_back({int(c0), kQTileN});
+    // the last column tile is trimmed to the valid individuals (multiples of 16, at least 32 for the epilogue)
+    const bool trim = !getenv("TPG_GRAM_NO_TRIM");
+    for (int64_t c0 = 0; c0 < a.n; c0 += kQTileN) {
+      const int64_t need = std::max<int64_t>(32, (a.n - c0 + 15) / 16 * 16);
+      cols.push_back({int(c0), trim ? int(std::min<int64_t>(kQTileN, need)) : kQTileN});
+    }
   }
   const int64_t RI = 4;
   const size_t RJ = a.shard_world > 1 ? 5 : 4;
