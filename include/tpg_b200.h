@@ -112,8 +112,8 @@ typedef struct tpg_job {
 #define TPG_FLAG_NO_OVERLAP 2     /* serialise copy / decode / gram (debugging)                      */
 #define TPG_FLAG_GRAM_1CTA 4      /* single-CTA gram kernel (default: CTA pairs, cta_group::2)       */
 #define TPG_FLAG_NO_PACK 8        /* host sources: ship raw bytes, no 2-bit packing while staging     */
-#define TPG_FLAG_GRAM_I8 32        /* int8 Gram kernels only (default: raw-byte chunks take the 4-bit   *
-                                   * kind::mxf4 kernel — exact, twice the MAC rate)                     */
+#define TPG_FLAG_GRAM_I8 32        /* int8 Gram kernels only (default: chunks, raw or 2-bit packed, take *
+                                   * the 4-bit kind::mxf4 kernel — exact, twice the MAC rate)           */
 #define TPG_FLAG_ASYNC 16         /* tpg_accumulate: enqueue and return; tpg_finish on the same ctx   *
                                    * waits (source bytes must stay valid until then).  Work enqueued  *
                                    * on tpg_ctx_stream in between (an all-reduce) is ordered after it */

@@ -160,9 +160,9 @@ def pick(kind, total, rng):
 
 
 @pytest.mark.parametrize("case", CASES, ids=[f"n{c[0]}_m{c[1]}_{c[4]}" for c in CASES])
-@pytest.mark.parametrize("variant", [0, L.FLAG_PLANES_K_MAJOR, L.FLAG_GRAM_1CTA, L.FLAG_PLANES_K_MAJOR | L.FLAG_GRAM_1CTA,
+@pytest.mark.parametrize("variant", [0, L.FLAG_GRAM_I8, L.FLAG_PLANES_K_MAJOR, L.FLAG_GRAM_1CTA, L.FLAG_PLANES_K_MAJOR | L.FLAG_GRAM_1CTA,
                                      L.FLAG_NO_PACK, L.FLAG_NO_PACK | L.FLAG_GRAM_I8],
-                         ids=["pk2_i8", "kmajor", "mn_1cta", "kmajor_1cta", "raw_mxf4", "raw_i8"])
+                         ids=["pk2_mxf4", "pk2_i8", "kmajor", "mn_1cta", "kmajor_1cta", "raw_mxf4", "raw_i8"])
 def test_random_parity_all_stats(case, variant):
     n_tot, m_tot, bs, chunk, rk, ck = case
     rng = np.random.default_rng(n_tot * 1000 + m_tot)
@@ -362,6 +362,34 @@ def test_decode_planes_pk2_kernel(shape):
     for p, x in enumerate(planes_ref(raw.T)):
         ref[p, :n, :lc] = x
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("shape", [(929, 700), (100, 37), (513, 130), (2049, 64), (128, 256)])
+def test_decode_planes_pk2_k4_kernel(shape):
+    """a 2-bit packed chunk decoded straight to the K-major 4-bit planes of the kind::mxf4 Gram kernel."""
+    import torch
+    n, lc = shape
+    ctx = L.Context(0)
+    rng = np.random.default_rng(12)
+    raw = rng.integers(0, 256, size=(lc, n)).astype(np.uint8)
+    raw[rng.random(raw.shape) < 0.8] %= 4
+    lib = L.lib()
+    st = int(lib.tpg_pk2_stride(n))
+    packed = np.zeros((lc, st), np.uint8)
+    lib.tpg_pk2_pack_host(raw.ctypes.data, n, n, lc, packed.ctypes.data)
+    n_pad, lc_pad = (n + 255) // 256 * 256, (lc + 255) // 256 * 256
+    d_raw = torch.from_numpy(packed.reshape(-1)).cuda()
+    ps = n_pad * lc_pad // 2
+    d_planes = torch.full((3 * ps,), 0x77, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    eb = L.errbuf()
+    L.check(lib.tpg_decode_planes(ctx.handle, d_raw.data_ptr(), packed.size, st, None, 0, n, n_pad,
+                                  None, 0, lc, lc_pad, d_planes.data_ptr(), ps, 4 | 8, eb, len(eb)), eb)
+    got = d_planes.cpu().numpy().reshape(3, n_pad, lc_pad // 2)
+    for p, x in enumerate(planes_ref(raw.T)):
+        full = np.zeros((n_pad, lc_pad), np.int8)
+        full[:n, :lc] = x
+        assert np.array_equal(got[p], k4_pack(full)), p
 
 
 def test_hybrid_link_and_pack_chunks(monkeypatch):

@@ -385,15 +385,16 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   // (scans decode through code256 and need the whole byte)
   const bool pack_ok = !scan && !on_device && pl.rows_contig && !k_major && !(job->flags & TPG_FLAG_NO_PACK) &&
                        !getenv("TPG_NO_PACK");
-  // Chunks that reach the GPU as raw bytes can take the 4-bit route: decode_planes_k4 + the kind::mxf4
-  // Gram kernel (twice the int8 MAC rate, half the plane bytes, exact: gram.cu).  2-bit packed chunks
-  // and tile-sharded jobs use the int8 kernels; both kinds add into the same int32 counts.
+  // The 4-bit route: decode_planes_k4 (raw bytes or 2-bit packed chunks) + the kind::mxf4 Gram kernel
+  // (twice the int8 MAC rate, half the plane bytes, exact: gram.cu).  Tile-sharded jobs too small for
+  // 1024-column ownership regions use the int8 kernels; both kinds add into the same int32 counts.
   const bool q4_forced_off = (job->flags & (TPG_FLAG_GRAM_I8 | TPG_FLAG_GRAM_1CTA)) || getenv("TPG_GRAM_I8");
   // (tile-sharded jobs: only while ownership is dealt in 1024-column regions, which the 4-bit kernel's
   //  240 + 240 + 240 + 240 + 64 column tiles respect)
   const bool q4_tiles_ok = !(job->shard_mode == TPG_SHARD_TILES && job->shard_world > 1) ||
                            shard_region_blocks(pl.n_pad / 256, job->shard_world) == 4;
   const bool q4_ok = !scan && !k_major && !q4_forced_off && q4_tiles_ok;
+  const bool pk2_i8 = getenv("TPG_PK2_I8") != nullptr;
   const bool direct_only = direct_ok && !pack_ok;
   if (direct_only) { span = nrow; rlo = 0; }
   const int64_t pk_stride = pk2_stride(span);
@@ -669,7 +670,8 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       da.col_idx = nullptr;
       da.col0 = 0;
     }
-    const bool use_q4 = q4_ok && !da.packed;
+    // (2-bit packed chunks decode to 4-bit planes too; TPG_PK2_I8=1 keeps them on the int8 kernels)
+    const bool use_q4 = q4_ok && !(da.packed && pk2_i8);
     const int64_t q4_lc_pad = round_up(lcc, 256);
     const int64_t q4_stride = pl.n_pad * (round_up(lc, 256) / 2);  // <= plane_stride: fits the int8 plane buffer
     if (use_q4) {

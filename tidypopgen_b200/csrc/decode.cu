@@ -317,6 +317,10 @@ decode_planes_k_kernel(const DecodeParams p) {
 // E2M1 nibble codes of 4 packed genotypes, straight from the raw bytes (one code per byte, in its
 // low nibble): cn = 0x2 where byte <= 2; ch = 0x2 where byte == 1; cd = 0x2 where byte == 2,
 // 0xA (-1) where byte == 0.
+__device__ __forceinline__ uint32_t spread4(uint32_t t) {  // 4 codes in bits [0,8) -> 4 bytes
+  return (t | (t << 6) | (t << 12) | (t << 18)) & 0x03030303u;
+}
+
 __device__ __forceinline__ void codes4(uint32_t g, uint32_t& cd, uint32_t& cn, uint32_t& ch) {
   const uint32_t t = (g & 0x7F7F7F7Fu) + 0x7D7D7D7Du;   // bit 7 set iff (byte & 127) >= 3
   cn = (~(t | g) >> 6) & 0x02020202u;                   // bit 7 clear <=> byte <= 2 -> bit 1
@@ -447,6 +451,9 @@ decode_planes_k4_v1_kernel(const DecodeParams p) {
 // two halves of a 32-byte sector come from different warps (partial-sector writes), 0.40 ms when
 // one store instruction completes the sector; issuing all 32 loci of loads before decoding
 // (80 registers, 3 CTAs per SM) changed nothing.
+// kPacked: the chunk crossed PCIe 2-bit packed (pk2, below) — a lane's four individuals are ONE byte
+// per locus (a warp reads one 32-byte sector per locus) and already hold the clamped codes.
+template <bool kPacked>
 __global__ void __launch_bounds__(256, 4)
 decode_planes_k4_kernel(const DecodeParams p) {
   __shared__ uint4 tile[3][128][8];  // output rows, 16-byte chunks XOR-swizzled by row
@@ -462,43 +469,66 @@ decode_planes_k4_kernel(const DecodeParams p) {
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {                     // 16 loci at a time keeps the registers down
     const int l0 = lt + warp * 32 + half * 16;
-    uint32_t g[16];
-    bool fast = plain && l0 + 16 <= p.lc;
-    if (fast) {
-      const int64_t lo = (p.col0 + l0) * p.raw_stride + p.row0 + ib0 - 3;
-      const int64_t hi = (p.col0 + l0 + 15) * p.raw_stride + p.row0 + ib0 + 128 + 8;
-      fast = lo >= 0 && hi <= int64_t(p.raw_end - p.raw);
-    }
-    if (fast) {
-      const uint64_t a0 = uint64_t(reinterpret_cast<uintptr_t>(p.raw + (p.col0 + l0) * p.raw_stride + rs.off));
-      const uint32_t stride = uint32_t(p.raw_stride);        // < 2^27: 15 * stride fits 32 bits
-      uint32_t w1[16];
+    uint32_t q[16];                                          // clamped codes, one per byte: 0 / 1 / 2, 3 = missing
+    if (kPacked) {
+      // column l at l * raw_stride, individuals i0 .. i0 + 3 in byte i0 >> 2 (pack.cpp); bytes beyond the
+      // packed column and loci beyond the chunk read as missing
+      const int64_t boff = i0 >> 2;
+      const uint8_t* a = p.raw + int64_t(l0) * p.raw_stride + boff;
+      uint32_t pk[16];
+      if (boff < p.raw_stride && l0 + 16 <= p.lc) {
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        uint64_t au;
-        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(au) : "r"(stride), "r"(uint32_t(u)), "l"(a0));
-        const uint32_t* al = reinterpret_cast<const uint32_t*>(uintptr_t(au & ~uint64_t(3)));
-        g[u] = __ldg(al);
-        w1[u] = __ldg(al + 1);
-      }
-      const uint32_t a8 = uint32_t(a0) << 3, s8 = stride << 3;  // the funnel shift takes its amount mod 32
+        for (int u = 0; u < 16; ++u) pk[u] = __ldg(a + int64_t(u) * p.raw_stride);
+      } else {
 #pragma unroll
-      for (int u = 0; u < 16; ++u) g[u] = __funnelshift_r(g[u], w1[u], a8 + uint32_t(u) * s8);
-    } else {
-      const bool safe = block_is_safe(p, l0, 16, ib0, ib0 + 128);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int l = l0 + k;
-        g[k] = 0x03030303u;
-        if (l < p.lc) {
-          const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
-          g[k] = safe ? load4<true>(p, rs, col, lane) : load4<false>(p, rs, col, lane);
+        for (int u = 0; u < 16; ++u) {
+          pk[u] = 0xFFu;
+          if (boff < p.raw_stride && l0 + u < p.lc) pk[u] = __ldg(a + int64_t(u) * p.raw_stride);
         }
       }
-    }
-    if (fast && !full) {
 #pragma unroll
-      for (int u = 0; u < 16; ++u) g[u] |= ~rs.keep;         // individuals >= n: any byte above 2 is missing
+      for (int u = 0; u < 16; ++u) q[u] = spread4(pk[u]) | (0x03030303u & ~rs.keep);
+    } else {
+      uint32_t g[16];
+      bool fast = plain && l0 + 16 <= p.lc;
+      if (fast) {
+        const int64_t lo = (p.col0 + l0) * p.raw_stride + p.row0 + ib0 - 3;
+        const int64_t hi = (p.col0 + l0 + 15) * p.raw_stride + p.row0 + ib0 + 128 + 8;
+        fast = lo >= 0 && hi <= int64_t(p.raw_end - p.raw);
+      }
+      if (fast) {
+        const uint64_t a0 = uint64_t(reinterpret_cast<uintptr_t>(p.raw + (p.col0 + l0) * p.raw_stride + rs.off));
+        const uint32_t stride = uint32_t(p.raw_stride);        // < 2^27: 15 * stride fits 32 bits
+        uint32_t w1[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          uint64_t au;
+          asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(au) : "r"(stride), "r"(uint32_t(u)), "l"(a0));
+          const uint32_t* al = reinterpret_cast<const uint32_t*>(uintptr_t(au & ~uint64_t(3)));
+          g[u] = __ldg(al);
+          w1[u] = __ldg(al + 1);
+        }
+        const uint32_t a8 = uint32_t(a0) << 3, s8 = stride << 3;  // the funnel shift takes its amount mod 32
+#pragma unroll
+        for (int u = 0; u < 16; ++u) g[u] = __funnelshift_r(g[u], w1[u], a8 + uint32_t(u) * s8);
+      } else {
+        const bool safe = block_is_safe(p, l0, 16, ib0, ib0 + 128);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int l = l0 + k;
+          g[k] = 0x03030303u;
+          if (l < p.lc) {
+            const int64_t col = p.col_idx ? int64_t(p.col_idx[l]) : p.col0 + l;
+            g[k] = safe ? load4<true>(p, rs, col, lane) : load4<false>(p, rs, col, lane);
+          }
+        }
+      }
+      if (fast && !full) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) g[u] |= ~rs.keep;         // individuals >= n: any byte above 2 is missing
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) q[u] = clamp4(g[u]);
     }
     // 2-bit codes; loci k (low nibble) and k + 4 (high nibble) of each group of 8 share a byte
     uint32_t od[4][2], on[4][2], oh[4][2];
@@ -506,7 +536,7 @@ decode_planes_k4_kernel(const DecodeParams p) {
     for (int w = 0; w < 2; ++w) {
       uint32_t pr[4], t[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pr[k] = nibble_pair(clamp4(g[8 * w + k]), clamp4(g[8 * w + 4 + k]));
+      for (int k = 0; k < 4; ++k) pr[k] = nibble_pair(q[8 * w + k], q[8 * w + 4 + k]);
       transpose4x4(pr, t);                                    // t[r]: byte k = loci (k, k + 4) of individual i0 + r
 #pragma unroll
       for (int r = 0; r < 4; ++r) codes8(t[r], od[r][w], on[r][w], oh[r][w]);
@@ -546,9 +576,6 @@ decode_planes_k4_kernel(const DecodeParams p) {
 // Algorithmic traffic: 0.25 byte read + 3 bytes written per genotype.
 constexpr int kPkLociPerWarp = 8;
 
-__device__ __forceinline__ uint32_t spread4(uint32_t t) {  // 4 codes in bits [0,8) -> 4 bytes
-  return (t | (t << 6) | (t << 12) | (t << 18)) & 0x03030303u;
-}
 
 __global__ void __launch_bounds__(kDecThreads)
 decode_planes_pk2_kernel(const DecodeParams p) {
@@ -791,13 +818,16 @@ int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E) 
   p.plane_stride = a.plane_stride;
   p.nplanes = a.nplanes;
   if (a.k4) {
-    if (a.packed || a.lc_pad % 256 || a.plane_stride % 16 || (reinterpret_cast<uintptr_t>(a.planes) & 15))
-      return E.fail(TPG_ERR_ARG, "decode(k4): lc_pad must be a multiple of 256, planes 16-byte aligned, raw-byte input");
+    if (a.lc_pad % 256 || a.plane_stride % 16 || (reinterpret_cast<uintptr_t>(a.planes) & 15))
+      return E.fail(TPG_ERR_ARG, "decode(k4): lc_pad must be a multiple of 256, planes 16-byte aligned");
+    if (a.packed && (a.row_idx || a.col_idx || a.row0 || a.col0))
+      return E.fail(TPG_ERR_ARG, "decode(k4, pk2): packed chunks are ungathered");
     const int64_t blocks = (a.n_pad / 128) * (a.lc_pad / 256);
     if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "decode: chunk too large for one launch");
     const bool v1 = getenv("TPG_DECODE_K4_V1") != nullptr;  // the first build, kept as a cross-check
-    if (v1) decode_planes_k4_v1_kernel<<<unsigned(blocks), 256, 0, st>>>(p);
-    else decode_planes_k4_kernel<<<unsigned(blocks), 256, 0, st>>>(p);
+    if (a.packed) decode_planes_k4_kernel<true><<<unsigned(blocks), 256, 0, st>>>(p);
+    else if (v1) decode_planes_k4_v1_kernel<<<unsigned(blocks), 256, 0, st>>>(p);
+    else decode_planes_k4_kernel<false><<<unsigned(blocks), 256, 0, st>>>(p);
   } else if (a.packed) {
     if (a.k_major || a.row_idx || a.col_idx || a.row0 || a.col0 || a.raw_stride % 16 || a.plane_stride % 16 ||
         (reinterpret_cast<uintptr_t>(a.raw) & 15) || (reinterpret_cast<uintptr_t>(a.planes) & 15))
