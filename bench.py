@@ -5,7 +5,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-A step = one whole pairwise_king job: decode_planes + gram_i8 (tcgen05 int8) + finish_king.
+A step = one whole pairwise_king job: decode_planes_k4 + gram_mxf4_pair (tcgen05 kind::mxf4 on exact
+4-bit operands; TPG_GRAM_I8=1 = the int8 -> s32 kernels) + finish_king.
 `value` is measured with the .bk bytes resident in HBM; `e2e` goes through the public API
 with HOST (pinned) buffers, H2D and D2H inside the timed region.  N > 1 is loci-sharded
 (weak scaling: every rank owns its own 650,000 loci, global m = N * 650,000): staged C-ABI
@@ -414,7 +415,7 @@ def run_b200(args, rank, world, local):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "e2m1 x e2m1 -> f32 (exact integer sums) + int8 -> s32" if agg["q4"] else "int8",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "e2m1 x e2m1 -> f32 (exact integer sums)" if agg["q4"] else "int8 x int8 -> s32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "n": n, "m_per_gpu": m, "m_global": m_global,
                    "sharding": "none" if world == 1 else f"loci x{world}, one NCCL all-reduce of int32 counts",
@@ -425,8 +426,8 @@ def run_b200(args, rank, world, local):
                 "h2d_bytes_per_step": e2e_h2d // e2e_steps, "d2h_bytes_per_step": 8 * n * n,
                 "host_bytes_per_step": n * m,
                 "transport": (f"{e2e_packed[0]} of {e2e_packed[1]} chunks cross PCIe 2-bit packed by the host worker pool, "
-                              "the rest are DMA'd raw from the caller's pinned buffer (hybrid schedule); result through "
-                              "pinned bounce buffers") if world == 1 else
+                              "the rest are DMA'd raw from the caller's pinned buffer (hybrid schedule); both kinds decode "
+                              "to 4-bit planes; result through pinned bounce buffers") if world == 1 else
                              "per rank: hybrid packed / raw chunks, staged accumulate + all-reduce + finish on one stream",
                 "ms_per_step": float(e2e_ms.item()), "steps": e2e_steps, "matches_device_run": same},
         "gpu_launches": agg["launches"],
