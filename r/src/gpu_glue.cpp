@@ -13,8 +13,9 @@
 // exception crosses a CUDA frame: the C ABI returns a code + message, turned into
 // Rcpp::stop() exactly where myassert() used to throw (src/snp_king.cpp:11).
 //
-// NOT compiled in this repository (no R toolchain in the build image); kept in sync with
-// include/tpg_b200.h by review.  See INTEGRATION.md.
+// Not BUILT in this repository (no R toolchain in the image), but type-checked: tests/test_abi.py compiles
+// this file with -fsyntax-only against include/tpg_b200.h and a stand-in for <Rcpp.h> (tests/stubs), so
+// every tpg_* call below agrees with the ABI.  See INTEGRATION.md.
 #include <Rcpp.h>
 #include "tpg_b200.h"
 

@@ -106,3 +106,20 @@ def test_compute_fails_loudly_without_gpu():
     X = tpg.FBMCode256.from_matrix(np.array([[0.0, 1, 2], [2, 1, 0]]))
     with pytest.raises(L.TpgError):
         tpg.snp_king(X)
+
+
+def test_r_glue_type_checks_against_the_header():
+    """r/src/gpu_glue.cpp (the Rcpp binding INTEGRATION.md hands to a tidypopgen maintainer) is compiled with
+    -fsyntax-only against include/tpg_b200.h and a minimal stand-in for <Rcpp.h> (tests/stubs): argument
+    counts and pointer types of every tpg_* call it makes are checked, so the written-out binding cannot
+    drift away from the ABI unnoticed (R itself is not in this image)."""
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", f"-I{root / 'tests' / 'stubs'}",
+                        f"-I{root / 'include'}", str(root / "r" / "src" / "gpu_glue.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # the header itself is plain C: it must also compile as C
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", "-x", "c", str(root / "include" / "tpg_b200.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
