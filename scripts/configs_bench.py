@@ -27,7 +27,10 @@ def timed(name, fn, n, m, ops):
     print(json.dumps({"job": name, "n": n, "m": m, "wall_ms": wall * 1e3, "decode_ms": st["ms_decode"], "gram_ms": st["ms_gram"],
                       "finish_ms": st["ms_finish"], "d2h_ms": st["ms_d2h"], "chunks": st["n_chunks"],
                       "gram_alg_TOPS": ops * n * n * m / (st["ms_gram"] * 1e-3) / 1e12,
-                      "decode_GBps": (1 + (2 if ops == 2 else 3)) * n * m / (st["ms_decode"] * 1e-3) / 1e9}), flush=True)
+                      "route": "4-bit (kind::mxf4)" if st["n_mxf4_chunks"] else "int8",
+                      # 1 B read + one byte (int8 route) or half a byte (4-bit route) written per plane and genotype
+                      "decode_GBps": (1 + (2 if ops == 2 else 3) * (0.5 if st["n_mxf4_chunks"] else 1.0)) * n * m
+                                     / (st["ms_decode"] * 1e-3) / 1e9}), flush=True)
 
 
 # C3
