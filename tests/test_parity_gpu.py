@@ -215,6 +215,32 @@ def test_k4_builds_whole_job(build, monkeypatch):
         assert np.array_equal(num, ref_a["num"]) and np.array_equal(den, ref_a["denom"]) and same(a, ref_a["as"])
 
 
+@pytest.mark.parametrize("compact", [True, False], ids=["compacted", "gather_in_decode"])
+@pytest.mark.parametrize("rk,ck", [("shuffle", "every3"), ("dup", "all"), ("subset", "shuffle")])
+def test_device_source_gathered_rows(rk, ck, compact, monkeypatch):
+    """Device-resident bytes with gathered rows: the chunk is compacted (compact_rows_kernel) and then decoded on
+    the contiguous fast path; TPG_NO_COMPACT=1 gathers inside the decode kernel instead.  Both exact."""
+    import torch
+    if not compact:
+        monkeypatch.setenv("TPG_NO_COMPACT", "1")
+    n_tot, m_tot = 1500, 2100
+    rng = np.random.default_rng(77)
+    raw = random_bk(rng, n_tot, m_tot, 0.08, codes=(0, 1, 2, 3, 4, 5, 6, 255))
+    dev = torch.from_numpy(raw).cuda()
+    X = tpg.FBMCode256.__new__(tpg.FBMCode256)
+    X.backingfile, X.nrow, X.ncol, X.code256 = "<device>", n_tot, m_tot, None
+    src = (L.SRC_DEVICE, dev.data_ptr(), dev)
+    rows, cols = pick(rk, n_tot, rng), pick(ck, m_tot, rng)
+    for chunk in (0, 512):   # one chunk / several (the last one short)
+        ref_k = O.snp_king(raw, n_tot, m_tot, rows, cols)
+        king, K, N = tpg.snp_king_counts(X, rows, cols, src=src, gpu_chunk_loci=chunk)
+        assert tpg.snp.last_stats["n_mxf4_chunks"] >= 1
+        assert np.array_equal(K, ref_k["K"]) and np.array_equal(N, ref_k["N_Aa_i"]) and same(king, ref_k["king"])
+    ref_a = O.snp_allele_sharing(raw, n_tot, m_tot, rows, cols)
+    a, num, den = tpg.snp_allele_sharing_counts(X, rows, cols, src=src)
+    assert np.array_equal(num, ref_a["num"]) and np.array_equal(den, ref_a["denom"]) and same(a, ref_a["as"])
+
+
 def test_pad_quirk_switch():
     rng = np.random.default_rng(5)
     raw = random_bk(rng, 50, 1003)

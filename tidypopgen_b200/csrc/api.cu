@@ -395,6 +395,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
                            shard_region_blocks(pl.n_pad / 256, job->shard_world) == 4;
   const bool q4_ok = !scan && !k_major && !q4_forced_off && q4_tiles_ok;
   const bool pk2_i8 = getenv("TPG_PK2_I8") != nullptr;
+  const bool compact_gather = on_device && !pl.rows_contig && !scan && !getenv("TPG_NO_COMPACT");
   const bool direct_only = direct_ok && !pack_ok;
   if (direct_only) { span = nrow; rlo = 0; }
   const int64_t pk_stride = pk2_stride(span);
@@ -695,6 +696,23 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     // planes[b] were last read by the gram of chunk c-2
     if (c >= 2) TPG_CUDA_OK(cudaStreamWaitEvent(s_dec, ev_gram_done[b], 0), E);
     TPG_CUDA_OK(cudaEventRecord(tm[c].d0, s_dec), E);
+    if (compact_gather && use_q4) {
+      // device-resident chunk with gathered rows: compact it first (decode.cu, "row / locus gather"), then
+      // the 4-bit decode takes its contiguous fast path on the dense copy (raw buffer b is free: device
+      // sources stage nothing; s_dec orders compact(c + 2) after decode(c))
+      rc = ensure_slot(&ctx->d_raw[b], size_t(pl.n_pad) * size_t(lcc) + 64, false, "compacted chunk", E);
+      if (rc) return rc;
+      uint8_t* dense = static_cast<uint8_t*>(ctx->d_raw[b].p);
+      rc = launch_compact_rows(ctx, da, dense, s_dec, E);
+      if (rc) return rc;
+      da.raw = dense;
+      da.raw_bytes = pl.n_pad * lcc + 64;
+      da.raw_stride = pl.n_pad;
+      da.row_idx = nullptr;
+      da.row0 = 0;
+      da.col_idx = nullptr;
+      da.col0 = 0;
+    }
     rc = launch_decode(ctx, da, s_dec, E);
     if (rc) return rc;
     TPG_CUDA_OK(cudaEventRecord(tm[c].d1, s_dec), E);

@@ -253,6 +253,80 @@ decode_planes_mn_kernel(const DecodeParams p) {
   }
 }
 
+// ------------------------------------------------------------------ row / locus gather
+// Gathered rows (ind.row in arbitrary order) read one byte per genotype from anywhere in a raw column:
+// every byte is its own 32-byte sector request, and what makes that affordable is L1 reuse — many
+// individuals of the SAME column read by the same SM.  The 4-bit decode kernel works on 128
+// individuals x 256 loci and keeps 192 KiB of the SM as shared memory, the opposite of what a gather
+// wants (measured: 10,000-row columns, 7,000 shuffled rows: 0.7 TB/s algorithmic).  So device-resident
+// gathered jobs first COMPACT the chunk — this kernel: 1024 individuals x 16 loci per CTA, no shared
+// memory, 32 byte loads in flight per lane, one coalesced 4-byte store per lane and locus — into a dense
+// column-major chunk (stride n_pad, padding individuals = 0x03), and the decode kernel then takes its
+// contiguous fast path.  Costs one extra byte written and read per genotype.
+template <bool kColIdx>
+__global__ void __launch_bounds__(kDecThreads)
+compact_rows_kernel(const DecodeParams p, uint8_t* __restrict__ out) {
+  const int nib = (p.n_pad + kDecThreads * 4 - 1) / (kDecThreads * 4);
+  const int ib = blockIdx.x % nib, lb = blockIdx.x / nib;   // individual blocks fastest: CTAs resident together share columns
+  const int i0 = (ib * kDecThreads + threadIdx.x) * 4;
+  if (i0 >= p.n_pad) return;
+  const RowSel rs = make_rowsel(p, i0);                      // rows of padding individuals are 0 (a valid address)
+  const int l0 = lb * kDecLociPerBlock;
+#pragma unroll
+  for (int half = 0; half < kDecLociPerBlock / 8; ++half) {
+    const uint8_t* cb[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int l = min(l0 + half * 8 + u, p.lc - 1);        // loci past the chunk re-read the last one (not stored)
+      const int64_t col = kColIdx ? int64_t(__ldg(p.col_idx + l)) : p.col0 + l;
+      cb[u] = p.raw + col * p.raw_stride;
+    }
+    uint32_t b0[8], b1[8], b2[8], b3[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      b0[u] = __ldg(cb[u] + rs.r[0]);
+      b1[u] = __ldg(cb[u] + rs.r[1]);
+      b2[u] = __ldg(cb[u] + rs.r[2]);
+      b3[u] = __ldg(cb[u] + rs.r[3]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int l = l0 + half * 8 + u;
+      if (l >= p.lc) break;
+      const uint32_t g = b0[u] | (b1[u] << 8) | (b2[u] << 16) | (b3[u] << 24);
+      *reinterpret_cast<uint32_t*>(out + int64_t(l) * p.n_pad + i0) = (g & rs.keep) | (0x03030303u & ~rs.keep);
+    }
+  }
+}
+
+int launch_compact_rows(Ctx* ctx, const DecodeArgs& a, uint8_t* out, cudaStream_t st, const Err& E) {
+  if (!a.row_idx || a.n_pad % 128 || a.n > a.n_pad || a.n <= 0 || a.lc <= 0 || a.n_pad > INT32_MAX || a.lc > INT32_MAX ||
+      (reinterpret_cast<uintptr_t>(out) & 3))
+    return E.fail(TPG_ERR_ARG, "compact_rows: needs a row index, n_pad a multiple of 128, a 4-byte aligned target");
+  DecodeParams p;
+  p.raw = a.raw;
+  p.raw_end = a.raw + a.raw_bytes;
+  p.raw_stride = a.raw_stride;
+  p.row_idx = a.row_idx;
+  p.row0 = a.row0;
+  p.col_idx = a.col_idx;
+  p.col0 = a.col0;
+  p.n = int(a.n);
+  p.n_pad = int(a.n_pad);
+  p.lc = int(a.lc);
+  p.lc_pad = int(a.lc);
+  p.planes = nullptr;
+  p.plane_stride = 0;
+  p.nplanes = 0;
+  const int64_t blocks = ((a.n_pad + kDecThreads * 4 - 1) / (kDecThreads * 4)) * ((a.lc + kDecLociPerBlock - 1) / kDecLociPerBlock);
+  if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "compact_rows: chunk too large for one launch");
+  if (a.col_idx) compact_rows_kernel<true><<<unsigned(blocks), kDecThreads, 0, st>>>(p, out);
+  else compact_rows_kernel<false><<<unsigned(blocks), kDecThreads, 0, st>>>(p, out);
+  TPG_CUDA_OK(cudaGetLastError(), E);
+  ctx->launches++;
+  return TPG_OK;
+}
+
 // ------------------------------------------------------------------ K-major (transposing)
 // Block = 128 individuals x 128 loci; warp w owns loci [16w, 16w+16), lane owns 4 individuals.
 __global__ void __launch_bounds__(256)

@@ -92,6 +92,9 @@ struct DecodeArgs {
   bool k4 = false;      // write K-major 4-bit E2M1 planes (operands of the kind::mxf4 Gram kernel)
 };
 int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E);
+// Gathers the rows (and loci) of a raw chunk into a dense column-major chunk: out[l * n_pad + i], padding
+// individuals = 0x03 (decode.cu).  a.planes / layout fields are ignored.
+int launch_compact_rows(Ctx* ctx, const DecodeArgs& a, uint8_t* out, cudaStream_t st, const Err& E);
 
 // One-pass scan of a raw chunk through code256 (decode.cu): device pointers; the per-locus
 // arrays are already offset to the chunk's first locus.  Uses a.raw / row / col addressing only.
