@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define TPG_ABI_VERSION 1
+#define TPG_ABI_VERSION 2
 
 /* ---- error codes (0 = success).  The message goes to the caller's err buffer;
  * the R glue turns a non-zero code into Rcpp::stop(msg), mirroring myassert()
@@ -135,7 +135,19 @@ typedef struct tpg_stats {
   int64_t n_short;    /* allele-sharing padding-quirk constant that was applied     */
   int64_t n_packed_chunks; /* chunks that crossed PCIe 2-bit packed (4 genotypes / byte)  */
   int64_t n_mxf4_chunks;   /* chunks whose products ran on the 4-bit kind::mxf4 kernel   */
+  int64_t n_i8_chunks;     /* chunks whose products ran on the int8 kind::i8 kernels     */
+  int64_t max_chain_loci;  /* longest accumulation chain (loci) any 4-bit work item ran: the FP32 *
+                            * accumulator of kind::mxf4 is exact for integer sums below 2^24, so  *
+                            * the library keeps this <= TPG_MXF4_MAX_CHAIN_LOCI whatever the      *
+                            * chunk size or k-split override (longer chunks are split)            */
+  int64_t bytes_file;      /* bytes read from the backing file                             */
+  int64_t n_direct_io;     /* chunks read with O_DIRECT (page cache bypassed)              */
+  int64_t n_cached_jobs;   /* 1 if the count matrices came from the context's cache       */
+  double ms_reduce;        /* multi-GPU: summing the count matrices over NVLink            */
 } tpg_stats;
+
+/* Longest accumulation chain a 4-bit (kind::mxf4, FP32 accumulator) work item may run. */
+#define TPG_MXF4_MAX_CHAIN_LOCI 8388608 /* 2^23: every partial sum stays an exact integer */
 
 /*
  * Results.  All matrices are caller-allocated, n x n, column-major (an R REALSXP,
@@ -157,8 +169,55 @@ typedef struct tpg_result {
   double* aux1;
   int32_t out_on_device; /* 1 = the four pointers are device pointers (no D2H) */
   int32_t reserved;
+  /* File-backed outputs: when out0 (out1) is NULL and out0_path (out1_path) is not, the library
+   * maps that file read-write and writes the n x n column-major doubles into it — the .bk of a
+   * bigstatsr::FBM(n, n) (type double has no header), which is what snp_ibs(type = "raw_counts")
+   * returns (R/snp_ibs.R:54-56,84-85; the reference aliases the same mapping through
+   * FBM_RW2arma, src/snp_ibs.cpp:8-15).  The file must exist and hold >= 8 n^2 bytes. */
+  const char* out0_path;
+  const char* out1_path;
   tpg_stats stats;
 } tpg_result;
+
+/* ------------------------------------------------------------------ configuration
+ * One documented struct instead of environment switches.  The R glue fills it from
+ * options(tidypopgen.gpu.<field>) (r/R/snp_king_gpu.R: tpg_gpu_config()); the Python mirror
+ * from tidypopgen_b200.config(**fields).  Process-wide; read when a job starts.
+ * tpg_config_init() gives the built-in defaults and then applies the TPG_<FIELD> environment
+ * variables named below (read there and nowhere else — a debugging convenience). */
+typedef struct tpg_config {
+  int32_t abi_version;        /* TPG_ABI_VERSION */
+  int32_t gram_route;         /* TPG_GRAM_I8: 0 = 4-bit kind::mxf4 where it is exact (default), 1 = int8 kind::i8 only */
+  int32_t gram_ctas;          /* TPG_GRAM_CTAS: 0/2 = CTA pairs (default), 1 = single-CTA int8 kernel */
+  int32_t gram_ksplit;        /* TPG_GRAM_KS: k-splits per tile, 0 = auto */
+  int32_t gram_max_kblocks;   /* TPG_GRAM_MAXKB: k-blocks per work item in the many-tiles regime, 0 = 128 */
+  int32_t gram_clusters;      /* TPG_GRAM_CLUSTERS: CTA pairs to launch, 0 = all resident */
+  int32_t gram_no_trim;       /* TPG_GRAM_NO_TRIM: 1 = do not trim the last tile column to the valid individuals */
+  int32_t pack_mode;          /* TPG_PACK_MODE: 0 = hybrid (pack or raw DMA per chunk), 1 = never pack (TPG_NO_PACK), *
+                               * 2 = always pack (TPG_NO_HYBRID) */
+  int32_t pk2_i8;             /* TPG_PK2_I8: 1 = packed chunks take the int8 kernels */
+  int32_t no_compact;         /* TPG_NO_COMPACT: 1 = gathered rows are gathered inside the decode kernel */
+  int32_t io_mode;            /* TPG_IO_MODE: file sources. 0 = auto (pread through the page cache), 1 = O_DIRECT *
+                               * (cold files, bypasses the page cache), 2 = mmap (TPG_NO_PREAD) */
+  int32_t no_thp;             /* TPG_NO_THP: 1 = no MADV_HUGEPAGE on result matrices */
+  int32_t decode_k4_v1;       /* TPG_DECODE_K4_V1: 1 = first build of the 4-bit decode kernel (cross-check) */
+  int32_t host_threads;       /* TPG_HOST_THREADS: staging worker threads, 0 = cores / local ranks (max 32) */
+  int32_t scan_loci_per_cta;  /* TPG_SCAN_LOCI: 0 = 256 */
+  int32_t scan_no_indiv;      /* TPG_SCAN_NO_INDIV: debugging */
+  int32_t scan_table;         /* TPG_SCAN_TABLE: 1 = always the table-lookup scan kernel (cross-check) */
+  int32_t cache_counts;       /* TPG_CACHE_COUNTS: 1 = a file-sourced job computes all four count matrices and keeps *
+                               * them in the context; the next job on the same file (size, mtime), ind.row and     *
+                               * ind.col finishes from them without touching the genotypes (pairwise_king, then    *
+                               * pairwise_ibs, then pairwise_allele_sharing on one gen_tibble = one pass)           */
+  int64_t device_chunk_loci;  /* TPG_DEVICE_CHUNK_LOCI: loci per chunk of a device-resident source, 0 = 2^20 */
+  int64_t host_chunk_mb;      /* TPG_HOST_CHUNK_MB: raw MB per chunk of a host / file source, 0 = 48 */
+  double link_gbps;           /* TPG_LINK_GBPS: PCIe model of the hybrid schedule, 0 = 45 */
+  double hybrid_factor;       /* TPG_HYBRID_FACTOR: 0 = 0.9 */
+} tpg_config;
+
+void tpg_config_init(tpg_config* cfg);                             /* defaults + TPG_* environment   */
+int tpg_config_set(const tpg_config* cfg, char* err, size_t errlen); /* process-wide, validated       */
+void tpg_config_get(tpg_config* cfg);                              /* the configuration in force     */
 
 /* ------------------------------------------------------------------ host-only helpers */
 
@@ -198,6 +257,17 @@ int tpg_pairwise(const tpg_job* job, tpg_result* res, char* err, size_t errlen);
  * NVLink and finished there.  Results are identical to the single-GPU job. */
 int tpg_pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* devices, int32_t ndev,
                        int32_t shard_mode, char* err, size_t errlen);
+
+/* Several statistics of the SAME (X, ind.row, ind.col) in one pass over the genotypes: the
+ * four integer products DD, NN, HH, HN are computed once (2.5 MAC per pair-SNP, one decode)
+ * and each statistic is finished from them — instead of one decode and 2.0 + 1.5 + 1.0 MAC for
+ * snp_king (R/snp_king.R:32), snp_ibs (R/snp_ibs.R:42) and snp_allele_sharing
+ * (R/snp_allele_sharing.R:33) run one after the other.  job->stat is ignored; stats[k] is a
+ * TPG_STAT_* and results[k] its outputs (same conventions as tpg_pairwise).  devices / ndev as
+ * in tpg_pairwise_multi (NULL / <= 1: job->device only).  results[0].stats carries the
+ * stage times of the shared pass. */
+int tpg_pairwise_many(const tpg_job* job, const int32_t* stats, int32_t nstats, tpg_result* results,
+                      const int32_t* devices, int32_t ndev, int32_t shard_mode, char* err, size_t errlen);
 
 /* pairwise_grm(x, allele_sharing_mat = <precomputed>) — R/pairwise_grm.R:42-50.
  * as_in / grm_out: n x n column-major host doubles (may alias). */
@@ -329,8 +399,8 @@ int tpg_gram(tpg_ctx* ctx, const int8_t* d_planes, int64_t plane_stride, int64_t
              int64_t lc_pad, int32_t k_major, int32_t prod_mask, int32_t shard_rank,
              int32_t shard_world, int32_t* d_counts, float* ms_out, char* err, size_t errlen);
 
-/* Deterministic synthetic genotypes (counter-based hash RNG; oracle/synth.c is the
- * CPU twin, byte-identical): fills column-major nrow x ncol bytes on the device. */
+/* Deterministic synthetic genotypes (counter-based hash, include/tpg_synth.h; tpg_synth_fill_host
+ * below is the byte-identical host twin): fills column-major nrow x ncol bytes on the device. */
 int tpg_synth_fill(tpg_ctx* ctx, uint8_t* d_raw, int64_t nrow, int64_t ncol, int64_t col_offset,
                    uint64_t seed, double missing_rate, int32_t mode, char* err, size_t errlen);
 

@@ -4,6 +4,25 @@
 # are replaced by one .Call.  `block.size` stays in the signature: it no longer sizes any
 # buffer, but allele sharing still depends on it through the reference's padding quirk.
 
+# options(tidypopgen.gpu.*) -> the library's tpg_config (include/tpg_b200.h), applied before every job.
+#   tidypopgen.gpu.devices   0-based CUDA ordinals; several = one job spread over them (tpg_pairwise_multi),
+#                            e.g. options(tidypopgen.gpu.devices = 0:7) for pairwise_king on 8 x B200
+#   tidypopgen.gpu.<field>   any field of tpg_config: gram_route, pack_mode, io_mode, host_threads,
+#                            cache_counts, host_chunk_mb, ...
+#   tidypopgen.gpu.reference_pad_quirk  FALSE = block-size independent allele sharing
+tpg_gpu_devices <- function() {
+  as.integer(getOption("tidypopgen.gpu.devices", getOption("tidypopgen.gpu.device", 0L)))
+}
+tpg_gpu_config <- function() {
+  fields <- c("gram_route", "gram_ctas", "gram_ksplit", "gram_max_kblocks", "gram_clusters",
+              "gram_no_trim", "pack_mode", "pk2_i8", "no_compact", "io_mode", "no_thp", "decode_k4_v1",
+              "host_threads", "scan_loci_per_cta", "scan_no_indiv", "scan_table", "cache_counts",
+              "device_chunk_loci", "host_chunk_mb", "link_gbps", "hybrid_factor")
+  opts <- lapply(stats::setNames(fields, fields), function(f) getOption(paste0("tidypopgen.gpu.", f)))
+  gpu_set_config(opts[!vapply(opts, is.null, logical(1))])
+  invisible(NULL)
+}
+
 snp_king <- function(
   X, # nolint start
   ind.row = bigstatsr::rows_along(X),
@@ -14,8 +33,8 @@ snp_king <- function(
   if (!inherits(X, "FBM.code256")) {
     stop("X should be a FBM.code256 matrix")
   }
-  gpu_snp_king(X, ind.row, ind.col, block.size,
-               device = getOption("tidypopgen.gpu.device", 0L))
+  tpg_gpu_config()
+  gpu_snp_king(X, ind.row, ind.col, block.size, tpg_gpu_devices())
 }
 
 snp_ibs <- function(
@@ -27,15 +46,17 @@ snp_ibs <- function(
 ) {
   # nolint end
   type <- match.arg(type)
-  device <- getOption("tidypopgen.gpu.device", 0L)
+  tpg_gpu_config()
+  devices <- tpg_gpu_devices()
   if (type == "raw_counts") {
     n <- length(ind.row)
     IBS <- bigstatsr::FBM(n, n, init = 0) # nolint
     IBS_valid_loci <- bigstatsr::FBM(n, n, init = 0) # nolint
-    gpu_snp_ibs_counts(IBS, IBS_valid_loci, X, ind.row, ind.col, block.size, device)
+    # the library maps IBS$backingfile / IBS_valid_loci$backingfile and writes the counts there
+    gpu_snp_ibs_counts(IBS, IBS_valid_loci, X, ind.row, ind.col, block.size, devices)
     return(list(ibs = IBS, valid_n = IBS_valid_loci))
   }
-  gpu_snp_ibs(X, ind.row, ind.col, type == "adjusted_counts", block.size, device)
+  gpu_snp_ibs(X, ind.row, ind.col, type == "adjusted_counts", block.size, devices)
 }
 
 snp_allele_sharing <- function(
@@ -45,9 +66,22 @@ snp_allele_sharing <- function(
   block.size = bigstatsr::block_size(nrow(X))
 ) {
   # nolint end
+  tpg_gpu_config()
   gpu_snp_allele_sharing(X, ind.row, ind.col, block.size,
                          pad_quirk = getOption("tidypopgen.gpu.reference_pad_quirk", TRUE),
-                         device = getOption("tidypopgen.gpu.device", 0L))
+                         devices = tpg_gpu_devices())
+}
+
+# Not in the reference: KING, IBS proportion and allele sharing of one (X, ind.row, ind.col) from a single
+# pass over the genotypes.  options(tidypopgen.gpu.cache_counts = 1L) gives the same saving without a new
+# function: the second and third of pairwise_king / pairwise_ibs / pairwise_allele_sharing on the same
+# gen_tibble finish from the count matrices the first one left on the device.
+snp_pairwise_many <- function(X, ind.row = bigstatsr::rows_along(X), ind.col = bigstatsr::cols_along(X), # nolint
+                              block.size = bigstatsr::block_size(nrow(X))) {
+  if (!inherits(X, "FBM.code256")) stop("X should be a FBM.code256 matrix")
+  tpg_gpu_config()
+  gpu_snp_pairwise_many(X, ind.row, ind.col, block.size,
+                        getOption("tidypopgen.gpu.reference_pad_quirk", TRUE), tpg_gpu_devices())
 }
 # pairwise_king / pairwise_ibs / pairwise_allele_sharing / pairwise_grm
 # (R/pairwise_*.R) are unchanged: they only call the three drivers above.

@@ -16,6 +16,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+@pytest.fixture
+def tpg_cfg():
+    """tidypopgen_b200.config (the process-wide tpg_config), restored to its defaults after the test."""
+    from tidypopgen_b200 import _lib as L
+    yield L.config
+    L.config(reset=True)
+
+
 @pytest.fixture(scope="session")
 def families():
     """12 x 961 reference fixture (inst/extdata/related/families.bed) as FBM bytes + golden outputs."""

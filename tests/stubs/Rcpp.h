@@ -60,6 +60,8 @@ static const NamedPlaceholder _ = NamedPlaceholder();
 class List {
  public:
   template <typename... A> static List create(const A&...) { return List(); }
+  bool containsElementNamed(const char*) const { return false; }
+  FieldProxy operator[](const char*) const { return FieldProxy(); }
 };
 
 [[noreturn]] inline void stop(const char* fmt, ...) {

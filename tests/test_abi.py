@@ -38,11 +38,55 @@ def test_enums_match_header():
         assert getattr(L, py) == v, k
 
 
-def test_struct_layout_matches_c():
-    # offsets the C compiler would produce for the declared field order (LP64)
-    assert C.sizeof(L.Job) == 120 and L.Job.bk_path.offset == 16 and L.Job.flags.offset == 112
-    assert C.sizeof(L.Stats) == 120
-    assert C.sizeof(L.Result) == 40 + 120 and L.Result.stats.offset == 40
+def test_struct_layout_matches_c(tmp_path):
+    """Every struct of the header as the C compiler lays it out (a probe compiled from include/tpg_b200.h
+    prints sizeof / offsetof) against the ctypes mirrors in _lib.py, field by field."""
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    structs = {"tpg_job": L.Job, "tpg_stats": L.Stats, "tpg_result": L.Result, "tpg_config": L.Config}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tpg_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    r = subprocess.run(["gcc", "-std=c99", f"-I{root / 'include'}", str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == C.sizeof(cls), cname
+        for f, _ in cls._fields_:
+            assert int(out[f"{cname}.{f}"]) == getattr(cls, f).offset, f"{cname}.{f}"
+    assert L.Job.bk_path.offset == 16 and L.Result.stats.offset == 56
+
+
+def test_config_roundtrip_and_validation(tpg_cfg):
+    """tpg_config: defaults, set / get round trip, validation errors, reset — host only."""
+    base = tpg_cfg()
+    assert base["abi_version"] == L.ABI_VERSION and base["gram_route"] == 0 and base["cache_counts"] == 0
+    got = tpg_cfg(gram_route=1, io_mode=1, host_threads=3, link_gbps=12.5, device_chunk_loci=4096)
+    assert (got["gram_route"], got["io_mode"], got["host_threads"], got["link_gbps"], got["device_chunk_loci"]) == (1, 1, 3, 12.5, 4096)
+    assert tpg_cfg() == got
+    for bad in ({"gram_route": 7}, {"pack_mode": 3}, {"io_mode": -1}, {"host_threads": -2}, {"link_gbps": -1.0}):
+        with pytest.raises(L.TpgError) as ei:
+            tpg_cfg(**bad)
+        assert ei.value.code == L.ERR_ARG
+    assert tpg_cfg() == got, "a rejected configuration must not be applied"
+    with pytest.raises(KeyError):
+        tpg_cfg(no_such_field=1)
+    assert tpg_cfg(reset=True)["gram_route"] == 0
+
+
+def test_no_env_switches_outside_config():
+    """The TPG_* environment variables are read in ONE place (csrc/config.cpp, tpg_config_init)."""
+    csrc = Path(__file__).resolve().parent.parent / "tidypopgen_b200" / "csrc"
+    for f in list(csrc.glob("*.cu")) + list(csrc.glob("*.cpp")) + list(csrc.glob("*.h")) + list(csrc.glob("*.cuh")):
+        if f.name == "config.cpp":
+            continue
+        assert 'getenv("TPG_' not in f.read_text(), f.name
 
 
 def test_version_and_device_count_without_gpu():
@@ -123,3 +167,37 @@ def test_r_glue_type_checks_against_the_header():
     r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", "-x", "c", str(root / "include" / "tpg_b200.h")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_r_package_build_through_makevars(tmp_path):
+    """north_star: "the R wrappers .Call into a thin C-ABI shared library built from new src/*.cu files through
+    src/Makevars" (reference: src/Makevars:1-9).  r/install_into_tidypopgen.sh copies the backend into a
+    package tree; the nvcc rules of r/src/Makevars then build every object the way `R CMD INSTALL` would
+    (R's own variables stubbed, <Rcpp.h> from tests/stubs), and the linked shared object exports the ABI."""
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    root = Path(__file__).resolve().parent.parent
+    pkg = tmp_path / "tidypopgen"
+    (pkg / "src").mkdir(parents=True)
+    (pkg / "R").mkdir()
+    (pkg / "DESCRIPTION").write_text("Package: tidypopgen\nVersion: 0.0.0\n")
+    for f in ("snp_king.R", "snp_ibs.R", "snp_allele_sharing.R"):
+        (pkg / "R" / f).write_text("# reference driver\n")
+    r = subprocess.run(["bash", str(root / "r" / "install_into_tidypopgen.sh"), str(pkg)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert (pkg / "R" / "snp_gpu_drivers.R").exists() and not (pkg / "R" / "snp_king.R").exists()
+    objs = ["api.o", "decode.o", "gram.o", "finish.o", "relate.o", "wg17.o", "pack.o", "config.o", "gpu_glue.o"]
+    stubs = f"-I. -I{root / 'tests' / 'stubs'}"
+    r = subprocess.run(["make", "-j8", "-f", "Makevars", "CXX=g++", f"ALL_CPPFLAGS={stubs}", f"CPPFLAGS={stubs}",
+                        "CXXFLAGS=-std=c++17 -fPIC -O1"] + objs, cwd=pkg / "src", capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("arch=compute_100a,code=sm_100a") == 6 and "--fmad=false" in r.stdout
+    so = pkg / "src" / "tidypopgen.so"
+    r = subprocess.run(["g++", "-shared", "-o", str(so)] + objs + ["-L/usr/local/cuda/lib64", "-lcudart_static", "-ldl",
+                        "-lrt", "-lpthread"], cwd=pkg / "src", capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = C.CDLL(str(so))
+    for name in declared_functions():
+        assert hasattr(lib, name), name

@@ -193,14 +193,13 @@ def test_random_parity_all_stats(case, variant):
 
 
 # builds of the 4-bit decode kernel: the default and the round's first one (decode.cu)
-K4_BUILDS = {"k4": {}, "k4_v1": {"TPG_DECODE_K4_V1": "1"}}
+K4_BUILDS = {"k4": {}, "k4_v1": {"decode_k4_v1": 1}}
 
 
 @pytest.mark.parametrize("build", list(K4_BUILDS))
-def test_k4_builds_whole_job(build, monkeypatch):
+def test_k4_builds_whole_job(build, tpg_cfg):
     """Every build of the 4-bit decode kernel through whole KING / allele-sharing jobs (3 and 2 planes)."""
-    for k, v in K4_BUILDS[build].items():
-        monkeypatch.setenv(k, v)
+    tpg_cfg(**K4_BUILDS[build])
     rng = np.random.default_rng(11)
     n, m = 389, 3000
     raw = random_bk(rng, n, m, 0.08, codes=(0, 1, 2, 3, 4, 5, 6, 255))
@@ -215,14 +214,15 @@ def test_k4_builds_whole_job(build, monkeypatch):
         assert np.array_equal(num, ref_a["num"]) and np.array_equal(den, ref_a["denom"]) and same(a, ref_a["as"])
 
 
-@pytest.mark.parametrize("compact", [True, False], ids=["compacted", "gather_in_decode"])
+@pytest.mark.parametrize("compact", [True, False], ids=["gather_pack", "gather_in_decode"])
 @pytest.mark.parametrize("rk,ck", [("shuffle", "every3"), ("dup", "all"), ("subset", "shuffle")])
-def test_device_source_gathered_rows(rk, ck, compact, monkeypatch):
-    """Device-resident bytes with gathered rows: the chunk is compacted (compact_rows_kernel) and then decoded on
-    the contiguous fast path; TPG_NO_COMPACT=1 gathers inside the decode kernel instead.  Both exact."""
+def test_device_source_gathered_rows(rk, ck, compact, tpg_cfg):
+    """Device-resident bytes with gathered rows: the chunk is gathered through shared memory into a dense
+    2-bit packed chunk (gather_pack_kernel) and then decoded on the contiguous packed-input path;
+    tpg_config.no_compact gathers inside the decode kernel instead.  Both exact."""
     import torch
     if not compact:
-        monkeypatch.setenv("TPG_NO_COMPACT", "1")
+        tpg_cfg(no_compact=1)
     n_tot, m_tot = 1500, 2100
     rng = np.random.default_rng(77)
     raw = random_bk(rng, n_tot, m_tot, 0.08, codes=(0, 1, 2, 3, 4, 5, 6, 255))
@@ -418,7 +418,7 @@ def test_decode_planes_pk2_k4_kernel(shape):
         assert np.array_equal(got[p], k4_pack(full)), p
 
 
-def test_hybrid_link_and_pack_chunks(monkeypatch):
+def test_hybrid_link_and_pack_chunks(tpg_cfg):
     """Pinned host source, many small chunks: some chunks are DMA'd raw, the rest cross PCIe
     2-bit packed (the hybrid schedule); the result does not depend on which chunk went how."""
     import torch
@@ -432,7 +432,7 @@ def test_hybrid_link_and_pack_chunks(monkeypatch):
     win = np.arange(11, 611, dtype=np.int32)          # contiguous row window: still packable
     ref_w = tpg.snp_king(X, ind_row=win, flags=L.FLAG_NO_PACK)
     for link in ("45", "0.5"):                        # a slow modelled link makes later chunks pack
-        monkeypatch.setenv("TPG_LINK_GBPS", link)
+        tpg_cfg(link_gbps=float(link))
         king, K, N = tpg.snp_king_counts(X, src=src, gpu_chunk_loci=2048)
         st = dict(tpg.snp.last_stats)
         assert st["n_chunks"] == 20 and 0 <= st["n_packed_chunks"] <= 20
@@ -458,10 +458,9 @@ def k4_pack(plane):
 @pytest.mark.parametrize("build", list(K4_BUILDS))
 @pytest.mark.parametrize("nrow", [929, 928, 1023], ids=["odd_stride", "aligned_stride", "stride_3mod4"])
 @pytest.mark.parametrize("gather", [False, True])
-def test_decode_planes_k4_kernel(gather, nrow, build, monkeypatch):
+def test_decode_planes_k4_kernel(gather, nrow, build, tpg_cfg):
     import torch
-    for k, v in K4_BUILDS[build].items():  # the default kernel and the round's first one
-        monkeypatch.setenv(k, v)
+    tpg_cfg(**K4_BUILDS[build])  # the default kernel and the round's first one
     ctx = L.Context(0)
     rng = np.random.default_rng(3)
     ncol = 900

@@ -40,6 +40,8 @@ from .snp import (  # noqa: F401
     snp_ibs,
     snp_king,
     snp_king_counts,
+    snp_pairwise_many,
 )
+from ._lib import config  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -15,7 +15,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libtpg_b200.so"
 CSRC = _HERE / "csrc"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums (keep in sync with include/tpg_b200.h; tests/test_abi.py checks the header)
 OK, ERR_ARG, ERR_IO, ERR_CUDA, ERR_NOMEM, ERR_KERNEL = range(6)
@@ -25,6 +25,7 @@ SHARD_NONE, SHARD_LOCI, SHARD_TILES = range(3)
 FLAG_PLANES_K_MAJOR, FLAG_NO_OVERLAP, FLAG_GRAM_1CTA, FLAG_NO_PACK, FLAG_ASYNC, FLAG_GRAM_I8 = 1, 2, 4, 8, 16, 32
 MAT_DD, MAT_NN, MAT_HH, MAT_HN = range(4)
 NUM_COUNT_MATS = 4
+MXF4_MAX_CHAIN_LOCI = 8388608
 
 
 class TpgError(RuntimeError):
@@ -76,6 +77,12 @@ class Stats(C.Structure):
         ("n_short", C.c_int64),
         ("n_packed_chunks", C.c_int64),
         ("n_mxf4_chunks", C.c_int64),
+        ("n_i8_chunks", C.c_int64),
+        ("max_chain_loci", C.c_int64),
+        ("bytes_file", C.c_int64),
+        ("n_direct_io", C.c_int64),
+        ("n_cached_jobs", C.c_int64),
+        ("ms_reduce", C.c_double),
     ]
 
     def as_dict(self) -> dict:
@@ -90,7 +97,37 @@ class Result(C.Structure):
         ("aux1", C.c_void_p),
         ("out_on_device", C.c_int32),
         ("reserved", C.c_int32),
+        ("out0_path", C.c_char_p),
+        ("out1_path", C.c_char_p),
         ("stats", Stats),
+    ]
+
+
+class Config(C.Structure):
+    """tpg_config (include/tpg_b200.h): the library's tuning switches, one documented struct."""
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("gram_route", C.c_int32),
+        ("gram_ctas", C.c_int32),
+        ("gram_ksplit", C.c_int32),
+        ("gram_max_kblocks", C.c_int32),
+        ("gram_clusters", C.c_int32),
+        ("gram_no_trim", C.c_int32),
+        ("pack_mode", C.c_int32),
+        ("pk2_i8", C.c_int32),
+        ("no_compact", C.c_int32),
+        ("io_mode", C.c_int32),
+        ("no_thp", C.c_int32),
+        ("decode_k4_v1", C.c_int32),
+        ("host_threads", C.c_int32),
+        ("scan_loci_per_cta", C.c_int32),
+        ("scan_no_indiv", C.c_int32),
+        ("scan_table", C.c_int32),
+        ("cache_counts", C.c_int32),
+        ("device_chunk_loci", C.c_int64),
+        ("host_chunk_mb", C.c_int64),
+        ("link_gbps", C.c_double),
+        ("hybrid_factor", C.c_double),
     ]
 
 
@@ -104,7 +141,12 @@ SIGNATURES = {
     "tpg_as_pad_count": (C.c_int64, [C.c_int64, C.c_int64]),
     "tpg_pk2_stride": (C.c_int64, [C.c_int64]),
     "tpg_pk2_pack_host": (None, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    "tpg_config_init": (None, [C.POINTER(Config)]),
+    "tpg_config_set": (C.c_int, [C.POINTER(Config)] + _ERR),
+    "tpg_config_get": (None, [C.POINTER(Config)]),
     "tpg_pairwise": (C.c_int, [C.POINTER(Job), C.POINTER(Result)] + _ERR),
+    "tpg_pairwise_many": (C.c_int, [C.POINTER(Job), C.c_void_p, C.c_int32, C.POINTER(Result), C.c_void_p, C.c_int32,
+                                    C.c_int32] + _ERR),
     "tpg_pairwise_multi": (C.c_int, [C.POINTER(Job), C.POINTER(Result), C.c_void_p, C.c_int32, C.c_int32] + _ERR),
     "tpg_pairwise_ctx": (C.c_int, [C.c_void_p, C.POINTER(Job), C.POINTER(Result)] + _ERR),
     "tpg_grm_from_as": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_double)] + _ERR),
@@ -170,6 +212,26 @@ def lib() -> C.CDLL:
         fn.argtypes = args
     _lib = L
     return L
+
+
+def config(**fields) -> dict:
+    """Reads (no arguments) or updates the process-wide tpg_config — the counterpart of the R glue's
+    options(tidypopgen.gpu.<field>).  config(reset=True) restores the built-in defaults (+ TPG_* env).
+    Returns the configuration in force as a dict."""
+    L = lib()
+    c = Config()
+    if fields.pop("reset", False):
+        L.tpg_config_init(C.byref(c))
+    else:
+        L.tpg_config_get(C.byref(c))
+    names = {k for k, _ in Config._fields_}
+    for k, v in fields.items():
+        if k not in names or k == "abi_version":
+            raise KeyError(f"tpg_config has no field '{k}'")
+        setattr(c, k, v)
+    eb = errbuf()
+    check(L.tpg_config_set(C.byref(c), eb, len(eb)), eb)
+    return {k: getattr(c, k) for k, _ in Config._fields_}
 
 
 def check(rc: int, errbuf) -> None:

@@ -22,6 +22,7 @@
 #include <unistd.h>
 #include "internal.h"
 #include "hostpool.h"
+#include "config.h"
 #include "../../include/tpg_synth.h"
 
 namespace tpg {
@@ -153,7 +154,8 @@ int ensure_slot(Ctx::Slot* s, size_t bytes, bool host, const char* what, const E
 void trim_ctx(Ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  Ctx::Slot* dev[] = {&c->d_raw[0], &c->d_raw[1], &c->d_planes[0], &c->d_planes[1], &c->d_rows,
+  c->counts_key.clear();
+  Ctx::Slot* dev[] = {&c->d_raw[0], &c->d_raw[1], &c->d_gat[0], &c->d_gat[1], &c->d_planes[0], &c->d_planes[1], &c->d_rows,
                       &c->d_cols, &c->d_counts, &c->d_out[0], &c->d_out[1], &c->d_out[2],
                       &c->d_out[3], &c->d_red};
   for (Ctx::Slot* s : dev) { if (s->p) cudaFree(s->p); s->p = nullptr; s->cap = 0; }
@@ -214,6 +216,9 @@ static int make_plan(const tpg_job* job, Plan* pl, const Err& E) {
   const int64_t m = job->ind_col ? job->m : job->ncol_total;
   if (n <= 0 || m <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row or ind.col (n=%lld, m=%lld)", (long long)n, (long long)m);
   if (n > (int64_t(1) << 24)) return E.fail(TPG_ERR_ARG, "n=%lld exceeds the supported 2^24 individuals", (long long)n);
+  // every count (DD, NN, HH, HN <= m) lives in an int32 matrix; finish combines them in FP64
+  if (m >= (int64_t(1) << 31) - 1)
+    return E.fail(TPG_ERR_ARG, "m=%lld loci exceed what the int32 count matrices hold (2^31 - 2); split ind.col", (long long)m);
   pl->n = n;
   pl->n_pad = round_up(n, kRowPad);
   // rows: R semantics, 1-based, no negatives (R/snp_king.R:12-15); bounds as SubBMAcc checks them
@@ -279,14 +284,16 @@ struct Mapped {
   const uint8_t* base = nullptr;
   size_t bytes = 0;
   int fd = -1;
+  int fd_direct = -1;  // the same file opened O_DIRECT (io_mode 1), -1 where the filesystem refuses
   bool owned = false;
   ~Mapped() {
     if (owned && base) munmap(const_cast<uint8_t*>(base), bytes);
     if (fd >= 0) close(fd);
+    if (fd_direct >= 0) close(fd_direct);
   }
 };
 
-static int open_source(const tpg_job* job, Mapped* mp, const Err& E) {
+static int open_source(const tpg_job* job, Mapped* mp, int io_mode, const Err& E) {
   const int64_t need = job->nrow_total * job->ncol_total;
   if (job->src_kind == TPG_SRC_FILE) {
     if (!job->bk_path) return E.fail(TPG_ERR_ARG, "bk_path is NULL");
@@ -300,6 +307,9 @@ static int open_source(const tpg_job* job, Mapped* mp, const Err& E) {
     void* p = mmap(nullptr, size_t(need), PROT_READ, MAP_PRIVATE, mp->fd, 0);
     if (p == MAP_FAILED) return E.fail(TPG_ERR_IO, "mmap('%s') failed: %s", job->bk_path, strerror(errno));
     madvise(p, size_t(need), MADV_SEQUENTIAL);
+    // io_mode 1: reads bypass the page cache (a cold 25 GB .bk should not evict everything else and
+    // pays no copy through it); tmpfs and some network filesystems refuse O_DIRECT -> buffered reads
+    if (io_mode == 1) mp->fd_direct = open(job->bk_path, O_RDONLY | O_DIRECT);
     mp->base = static_cast<const uint8_t*>(p);
     mp->bytes = size_t(need);
     mp->owned = true;
@@ -354,67 +364,86 @@ static int collect_accumulate(Ctx* ctx, tpg_stats* st, const Err& E) {
 
 // scan != nullptr: the chunks feed scan_counts (through code256) instead of decode + gram; the
 // per-locus arrays of *scan are indexed by the job's locus position.
+// prod_mask_override != 0: compute these products instead of the ones job->stat needs (one pass
+// for several statistics: tpg_pairwise_many, the count-matrix cache).
 static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_stats* st,
-                           const Err& E, bool defer = false, const ScanArgs* scan = nullptr) {
+                           const Err& E, bool defer = false, const ScanArgs* scan = nullptr,
+                           int prod_mask_override = 0) {
   const double t_begin = now_ms();
+  const tpg_config C = cfg();
   Plan pl;
   int rc = make_plan(job, &pl, E);
   if (rc) return rc;
+  if (prod_mask_override) {
+    pl.prod_mask = prod_mask_override;
+    pl.nplanes = (pl.prod_mask & ((1 << TPG_MAT_HH) | (1 << TPG_MAT_HN))) ? 3 : 2;
+  }
   TPG_CUDA_OK(cudaSetDevice(ctx->device), E);
   if (pl.m_shard <= 0) return TPG_OK;  // more ranks than loci: nothing to add
   Mapped src;
-  rc = open_source(job, &src, E);
+  rc = open_source(job, &src, C.io_mode, E);
   if (rc) return rc;
 
   const bool on_device = job->src_kind == TPG_SRC_DEVICE;
   const bool k_major = !scan && (job->flags & TPG_FLAG_PLANES_K_MAJOR) != 0;
   const bool no_overlap = (job->flags & TPG_FLAG_NO_OVERLAP) != 0;
   const int64_t nrow = job->nrow_total;
+  const bool rows_g = !pl.rows_contig;
 
   // Rows actually needed from each raw column: [rlo, rhi).  Staging copies only that span.
   int64_t rlo = pl.row0, rhi = pl.row0 + pl.n;
-  if (!pl.rows_contig) {
+  if (rows_g) {
     rlo = nrow; rhi = 0;
     for (int32_t r : pl.rows0) { rlo = std::min<int64_t>(rlo, r); rhi = std::max<int64_t>(rhi, r + 1); }
   }
   int64_t span = on_device ? nrow : rhi - rlo;  // bytes per staged column
+  // Gathered rows (ind.row in arbitrary order): the chunk is first compacted by gather_pack_kernel
+  // (decode.cu: the row span staged in shared memory, gathered there, written 2-bit packed), then
+  // decoded on the contiguous packed-input path.  Needs the column span to fit shared memory —
+  // as raw bytes, or as 2-bit codes when the chunk crosses PCIe packed.
+  const bool gp_base = rows_g && !scan && !k_major && !C.no_compact;
+  const bool gp_raw_fits = gp_base && gather_pack_fits(rhi - rlo);
+  const bool gp_pk_fits = gp_base && gather_pack_fits((rhi - rlo + 3) / 4);
+  // 2-bit packing while staging (pack.cpp): 4x fewer bytes over PCIe.  Contiguous row window (or a
+  // gathered one that gather_pack can take), MN-major planes only; scans decode through code256
+  // and need the whole byte.
+  const bool pack_ok = !scan && !on_device && !k_major && !(job->flags & TPG_FLAG_NO_PACK) && C.pack_mode != 1 &&
+                       (!rows_g || gp_pk_fits);
   // Pinned (or cudaHostRegister'ed) source with whole contiguous columns: can be DMA'd straight from it.
-  const bool direct_ok = !on_device && job->src_kind == TPG_SRC_HOST && pl.cols_contig && is_pinned_host(src.base);
-  // 2-bit packing while staging (pack.cpp): 4x fewer bytes over PCIe.  Contiguous row window,
-  // MN-major planes only; everything else keeps the raw-byte paths.
-  // (scans decode through code256 and need the whole byte)
-  const bool pack_ok = !scan && !on_device && pl.rows_contig && !k_major && !(job->flags & TPG_FLAG_NO_PACK) &&
-                       !getenv("TPG_NO_PACK");
+  // (gathered rows that can be packed always are: one chunk form per job keeps the row index simple)
+  const bool direct_ok = !on_device && job->src_kind == TPG_SRC_HOST && pl.cols_contig && is_pinned_host(src.base) &&
+                         !(rows_g && pack_ok);
   // The 4-bit route: decode_planes_k4 (raw bytes or 2-bit packed chunks) + the kind::mxf4 Gram kernel
   // (twice the int8 MAC rate, half the plane bytes, exact: gram.cu).  Tile-sharded jobs too small for
   // 1024-column ownership regions use the int8 kernels; both kinds add into the same int32 counts.
-  const bool q4_forced_off = (job->flags & (TPG_FLAG_GRAM_I8 | TPG_FLAG_GRAM_1CTA)) || getenv("TPG_GRAM_I8");
-  // (tile-sharded jobs: only while ownership is dealt in 1024-column regions, which the 4-bit kernel's
-  //  240 + 240 + 240 + 240 + 64 column tiles respect)
+  const bool q4_forced_off = (job->flags & (TPG_FLAG_GRAM_I8 | TPG_FLAG_GRAM_1CTA)) || C.gram_route == 1 || C.gram_ctas == 1;
   const bool q4_tiles_ok = !(job->shard_mode == TPG_SHARD_TILES && job->shard_world > 1) ||
                            shard_region_blocks(pl.n_pad / 256, job->shard_world) == 4;
   const bool q4_ok = !scan && !k_major && !q4_forced_off && q4_tiles_ok;
-  const bool pk2_i8 = getenv("TPG_PK2_I8") != nullptr;
-  const bool compact_gather = on_device && !pl.rows_contig && !scan && !getenv("TPG_NO_COMPACT");
   const bool direct_only = direct_ok && !pack_ok;
   if (direct_only) { span = nrow; rlo = 0; }
+  const int64_t g_span = rhi - rlo;            // rows a gather has to stage (relative row index 0 = raw row rlo)
+  const bool gp_staged = gp_base && !on_device && !pack_ok && gather_pack_fits(g_span);  // raw chunks of a host source
+  const bool gp_dev = on_device && gp_raw_fits;
+  const bool gp_any = gp_dev || gp_staged || (rows_g && pack_ok);
+  // device-resident gathered chunk whose span is too long for shared memory: compact through L2 instead
+  const bool compact_gather = on_device && rows_g && !gp_dev && !scan && !C.no_compact;
   const int64_t pk_stride = pk2_stride(span);
+  const int64_t g_stride = pk2_stride(pl.n);  // bytes per locus of a gathered (dense, packed) chunk
 
   // ---- chunk size (loci per GPU chunk), decoupled from R's block.size
   int64_t lc = job->gpu_chunk_loci;
-  // device bytes per locus: raw double buffer (largest form in use) + plane double buffer
+  // device bytes per locus: raw double buffer (largest form in use) + gathered copy + plane double buffer
   const int64_t raw_per_locus = on_device ? 0 : std::max(direct_ok ? nrow : 0, pack_ok ? pk_stride : span);
-  const int64_t per_locus = 2 * raw_per_locus + 2 * int64_t(pl.nplanes) * pl.n_pad;
+  const int64_t per_locus = 2 * raw_per_locus + (gp_any ? 2 * g_stride : 0) + 2 * int64_t(pl.nplanes) * pl.n_pad;
   if (lc <= 0) {
     // device-resident bytes: nothing to overlap with (decode and gram contend for HBM when run
     // side by side — measured), so one big chunk = fewest launches and atomics
     if (on_device) {
-      lc = int64_t(1) << 20;
-      if (const char* ev = getenv("TPG_DEVICE_CHUNK_LOCI")) lc = std::max<int64_t>(kLociPad, atoll(ev));
+      lc = C.device_chunk_loci > 0 ? std::max<int64_t>(kLociPad, C.device_chunk_loci) : (int64_t(1) << 20);
     } else {
       // host sources: the first chunk's staging is exposed, so chunks are small (tens of MB)
-      int64_t mb = 48;
-      if (const char* ev = getenv("TPG_HOST_CHUNK_MB")) mb = std::max<int64_t>(1, atoll(ev));
+      const int64_t mb = C.host_chunk_mb > 0 ? C.host_chunk_mb : 48;
       lc = std::min<int64_t>(262144, std::max<int64_t>(16384, (mb << 20) / std::max<int64_t>(span, 1)));
     }
   }
@@ -425,12 +454,16 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     // would have to grow for this chunk size.
     const size_t need_planes = size_t(pl.n_pad) * size_t(lc) * size_t(pl.nplanes);
     const size_t need_raw = on_device ? 0 : size_t(raw_per_locus) * size_t(lc) + 16;
-    const bool fits = ctx->d_planes[0].cap >= need_planes && (pl.m_shard <= lc || ctx->d_planes[1].cap >= need_planes) &&
-                      (on_device || (ctx->d_raw[0].cap >= need_raw && (pl.m_shard <= lc || ctx->d_raw[1].cap >= need_raw)));
+    const size_t need_gat = gp_any ? size_t(g_stride) * size_t(lc) + 16 : 0;
+    const bool two = pl.m_shard > lc;
+    const bool fits = ctx->d_planes[0].cap >= need_planes && (!two || ctx->d_planes[1].cap >= need_planes) &&
+                      (on_device || (ctx->d_raw[0].cap >= need_raw && (!two || ctx->d_raw[1].cap >= need_raw))) &&
+                      (ctx->d_gat[0].cap >= need_gat && (!two || ctx->d_gat[1].cap >= need_gat));
     if (!fits) {
       size_t free_b = 0, total_b = 0;
       TPG_CUDA_OK(cudaMemGetInfo(&free_b, &total_b), E);
-      const size_t held = ctx->d_planes[0].cap + ctx->d_planes[1].cap + ctx->d_raw[0].cap + ctx->d_raw[1].cap;
+      const size_t held = ctx->d_planes[0].cap + ctx->d_planes[1].cap + ctx->d_raw[0].cap + ctx->d_raw[1].cap +
+                          ctx->d_gat[0].cap + ctx->d_gat[1].cap;
       const int64_t mem_cap = std::max<int64_t>(kLociPad, int64_t(double(free_b + held) * 0.45 / double(per_locus)));
       lc = std::min(lc, mem_cap);
       lc = std::max<int64_t>(kLociPad, lc / kLociPad * kLociPad);
@@ -439,7 +472,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   const int64_t n_chunks = (pl.m_shard + lc - 1) / lc;
   const int64_t plane_stride = pl.n_pad * lc;
 
-  struct { uint8_t* d_raw[2]; int8_t* d_planes[2]; uint8_t* h_pin[2]; int32_t* d_rows; int32_t* d_cols;
+  struct { uint8_t* d_raw[2]; uint8_t* d_gat[2]; int8_t* d_planes[2]; uint8_t* h_pin[2]; int32_t* d_rows; int32_t* d_cols;
            Ctx* c; cudaEvent_t ev(bool t) { return pooled_event(c, t); } } B{};
   B.c = ctx;
   ctx->ev_timing_used = ctx->ev_plain_used = 0;
@@ -449,6 +482,11 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       rc = ensure_slot(&ctx->d_planes[b], size_t(plane_stride) * pl.nplanes, false, "plane storage", E);
       if (rc) return rc;
       B.d_planes[b] = static_cast<int8_t*>(ctx->d_planes[b].p);
+    }
+    if (gp_any) {
+      rc = ensure_slot(&ctx->d_gat[b], size_t(g_stride * lc) + 16, false, "gathered chunk storage", E);
+      if (rc) return rc;
+      B.d_gat[b] = static_cast<uint8_t*>(ctx->d_gat[b].p);
     }
     if (!on_device) {
       rc = ensure_slot(&ctx->d_raw[b], size_t(raw_per_locus * lc) + 16, false, "raw chunk storage", E);
@@ -461,19 +499,25 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       }
     }
   }
-  if (!pl.rows_contig) {
-    // staged columns start at raw row rlo
+  if (rows_g) {
+    // row offsets as the kernels see them: relative to raw row rlo for staged / packed chunks and for
+    // every gather_pack input; absolute for device-resident chunks on the older paths
     std::vector<int32_t> rel(pl.rows0);
-    if (!on_device) for (auto& r : rel) r -= int32_t(rlo);  // (direct-only: rlo = 0)
-    rc = ensure_slot(&ctx->d_rows, sizeof(int32_t) * pl.n, false, "row index", E);
+    if (!on_device || gp_dev) for (auto& r : rel) r -= int32_t(rlo);  // (direct-only: rlo = 0)
+    rc = ensure_slot(&ctx->d_rows, sizeof(int32_t) * (pl.n + 16), false, "row index", E);
     if (rc) return rc;
     B.d_rows = static_cast<int32_t*>(ctx->d_rows.p);
+    // (stream-ordered after the previous job's kernels that read the old index)
+    TPG_CUDA_OK(cudaStreamSynchronize(ctx->s_decode), E);
+    TPG_CUDA_OK(cudaStreamSynchronize(ctx->s_compute), E);
     TPG_CUDA_OK(cudaMemcpy(B.d_rows, rel.data(), sizeof(int32_t) * pl.n, cudaMemcpyHostToDevice), E);
   }
   if (on_device && !pl.cols_contig) {
     rc = ensure_slot(&ctx->d_cols, sizeof(int32_t) * pl.m_shard, false, "column index", E);
     if (rc) return rc;
     B.d_cols = static_cast<int32_t*>(ctx->d_cols.p);
+    TPG_CUDA_OK(cudaStreamSynchronize(ctx->s_decode), E);
+    TPG_CUDA_OK(cudaStreamSynchronize(ctx->s_compute), E);
     TPG_CUDA_OK(cudaMemcpy(B.d_cols, pl.cols0.data(), sizeof(int32_t) * pl.m_shard, cudaMemcpyHostToDevice), E);
   }
 
@@ -490,19 +534,35 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   TPG_CUDA_OK(cudaStreamWaitEvent(s_dec, ev_start, 0), E);
   std::vector<Ctx::ChunkEv>& tm = ctx->pend_ev;
   tm.assign(n_chunks, Ctx::ChunkEv{});
-  int64_t macs = 0;
+  int64_t macs = 0, max_chain = 0;
   double ms_read = 0;
   // hybrid link/core scheduling state (see the chunk loop)
   cudaEvent_t ev_pin_free[2] = {B.ev(false), B.ev(false)};
-  int64_t n_staged = 0, n_packed = 0, n_q4 = 0;
-  double link_free_at = 0, link_gbps = 45.0;
+  int64_t n_staged = 0, n_packed = 0, n_q4 = 0, n_i8 = 0, n_dio = 0;
+  double link_free_at = 0;
+  const double link_gbps = C.link_gbps > 0 ? std::max(1.0, C.link_gbps) : 45.0;
   double pack_gbps = 4.0 * double(HostPool::max_threads());
-  if (const char* ev = getenv("TPG_LINK_GBPS")) link_gbps = std::max(1.0, atof(ev));
-  const bool hybrid = !getenv("TPG_NO_HYBRID");
-  double hybrid_factor = 0.9;
-  if (const char* ev = getenv("TPG_HYBRID_FACTOR")) hybrid_factor = atof(ev);
-  const bool use_pread = job->src_kind == TPG_SRC_FILE && pl.cols_contig && !getenv("TPG_NO_PREAD");
-  std::atomic<int> io_err{0};
+  const bool hybrid = C.pack_mode != 2;
+  const double hybrid_factor = C.hybrid_factor > 0 ? C.hybrid_factor : 0.9;
+  // .bk files are read with pread() — whole columns in ~1 MB blocks into per-thread buffers that stay
+  // in L2 — unless io_mode asks for the mmap; with io_mode = 1 the reads bypass the page cache (O_DIRECT)
+  const bool use_pread = job->src_kind == TPG_SRC_FILE && C.io_mode != 2;
+  const bool direct_io = use_pread && src.fd_direct >= 0;
+  std::atomic<int> io_err{0};        // errno of a failed read (captured in the worker), -1 = unexpected EOF
+  std::atomic<int64_t> file_bytes{0};
+
+  // From the first enqueue on, an early error return must not leave device work in flight on the
+  // three streams: the next job on the cached context would reuse the staging and raw buffers.
+  struct DrainGuard {
+    Ctx* c; bool armed;
+    ~DrainGuard() {
+      if (!armed) return;
+      cudaStreamSynchronize(c->s_copy);
+      cudaStreamSynchronize(c->s_decode);
+      cudaStreamSynchronize(c->s_compute);
+      c->pending = false;
+    }
+  } drain{ctx, true};
 
   // ---- host-source staging, software-pipelined: the workers stage (pack / copy) chunk c+1 while
   // this thread enqueues the H2D, decode and Gram of chunk c.
@@ -516,7 +576,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   // Decides how chunk c crosses PCIe and starts its staging:
   //   direct  raw bytes DMA'd from the caller's pinned memory (no host work, 1 B / genotype)
   //   pk2     packed 4 genotypes / byte into pinned staging by the worker pool (0.25 B / genotype)
-  //   staged  raw row window copied into pinned staging (gathered rows, K-major planes)
+  //   staged  raw row window copied into pinned staging (scans, K-major planes, spans too long to gather packed)
   // With both direct and pk2 available the link and the cores work side by side: a chunk goes
   // raw when the copy queue would otherwise run dry before this chunk could be packed.
   auto start_stage = [&](int64_t c) -> int {
@@ -545,54 +605,91 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     const Plan* plp = &pl;
     S.hp = stage;
     S.async = true;
-    if (pack_ok) {
-      S.packed = true;
-      S.h2d_bytes = lcc * pk_stride;
-      S.col_stride = pk_stride;
-      if (use_pread) {
-        // .bk file, contiguous columns: pread() blocks of whole columns into a per-thread buffer
-        // that stays in L2 and pack from there — a fresh mmap pays one page fault per 4 KiB.
-        const int fd = src.fd;
-        const int64_t cpb = std::max<int64_t>(1, (int64_t(1) << 20) / nrow);  // columns per block
-        std::atomic<int>* bad = &io_err;
-        HostPool::instance().begin(lcc, std::max<int64_t>(cpb, (int64_t(1) << 20) / span), [=](int64_t a, int64_t e) {
-          static thread_local std::vector<uint8_t> buf;
-          if (int64_t(buf.size()) < cpb * nrow) buf.resize(size_t(cpb * nrow));
-          for (int64_t k = k0 + a; k < k0 + e; k += cpb) {
-            const int64_t nc = std::min<int64_t>(cpb, k0 + e - k);
-            const int64_t off = (plp->col0 + k) * nrow;
+    S.packed = pack_ok;
+    const int64_t ostride = pack_ok ? pk_stride : span;  // staged bytes per locus
+    S.h2d_bytes = lcc * ostride;
+    S.col_stride = ostride;
+    const bool do_pack = pack_ok;
+    if (use_pread) {
+      // Runs of consecutive raw columns are read with one pread() each (whole columns: the rows outside
+      // [rlo, rhi) of a window are skipped only when the window is short) into a per-thread buffer and
+      // packed / copied from there — a fresh mmap pays one page fault per 4 KiB.  O_DIRECT: offsets,
+      // lengths and the buffer are 4 KiB aligned; the file's tail is a short read.
+      const int fd = direct_io ? src.fd_direct : src.fd;
+      const int64_t cpb = std::max<int64_t>(1, (int64_t(1) << 20) / nrow);  // columns per block
+      std::atomic<int>* bad = &io_err;
+      std::atomic<int64_t>* fbytes = &file_bytes;
+      const bool dio = direct_io;
+      const int64_t file_size = int64_t(src.bytes);
+      HostPool::instance().begin(lcc, std::max<int64_t>(cpb, (int64_t(1) << 20) / std::max<int64_t>(span, 1)), [=](int64_t a, int64_t e) {
+        static thread_local uint8_t* buf = nullptr;
+        static thread_local size_t buf_cap = 0;
+        const size_t need = size_t(cpb * nrow) + 2 * 4096;
+        if (buf_cap < need) {
+          free(buf);
+          buf = static_cast<uint8_t*>(aligned_alloc(4096, (need + 4095) / 4096 * 4096));
+          buf_cap = buf ? need : 0;
+          if (!buf) { bad->store(ENOMEM); return; }
+        }
+        int64_t k = k0 + a;
+        while (k < k0 + e) {
+          const int64_t c_first = plp->cols_contig ? plp->col0 + k : plp->cols0[k];
+          int64_t nc = 1;
+          while (k + nc < k0 + e && nc < cpb &&
+                 (plp->cols_contig || plp->cols0[k + nc] == plp->cols0[k + nc - 1] + 1)) ++nc;
+          // a short row window of long columns: read just the window of each column
+          const bool window = span * 4 < nrow && !dio;
+          const int64_t reads = window ? nc : 1;
+          for (int64_t q = 0; q < reads; ++q) {
+            const int64_t off = window ? (c_first + q) * nrow + rlo : c_first * nrow;
+            const int64_t len = window ? span : nc * nrow;
+            int64_t a0 = off, a1 = off + len;
+            if (dio) { a0 = off / 4096 * 4096; a1 = std::min<int64_t>((off + len + 4095) / 4096 * 4096, (file_size + 4095) / 4096 * 4096); }
+            uint8_t* dst = window ? buf + q * span : buf;
             int64_t got = 0;
-            while (got < nc * nrow) {
-              const ssize_t r = pread(fd, buf.data() + got, size_t(nc * nrow - got), off_t(off + got));
-              if (r <= 0) { bad->store(1); return; }
+            while (a0 + got < off + len) {
+              const ssize_t r = pread(fd, dst + got, size_t(a1 - a0 - got), off_t(a0 + got));
+              if (r < 0) { if (errno == EINTR) continue; bad->store(errno ? errno : EIO); return; }
+              if (r == 0) { bad->store(-1); return; }
               got += r;
             }
-            for (int64_t j = 0; j < nc; ++j)
-              pk2_pack_column(buf.data() + j * nrow + rlo, span, stage + (k - k0 + j) * pk_stride, pk_stride);
+            fbytes->fetch_add(got);
+            if (!window) {
+              const uint8_t* cols = buf + (off - a0);
+              for (int64_t j = 0; j < nc; ++j) {
+                const uint8_t* s0 = cols + j * nrow + rlo;
+                uint8_t* d0 = stage + (k - k0 + j) * ostride;
+                if (do_pack) pk2_pack_column(s0, span, d0, ostride);
+                else memcpy(d0, s0, size_t(span));
+              }
+            }
           }
-        });
-      } else {
-        HostPool::instance().begin(lcc, std::max<int64_t>(1, (int64_t(1) << 20) / span), [=](int64_t a, int64_t e) {
-          for (int64_t k = k0 + a; k < k0 + e; ++k) {
-            const int64_t col = plp->cols_contig ? plp->col0 + k : plp->cols0[k];
-            pk2_pack_column(base + col * nrow + rlo, span, stage + (k - k0) * pk_stride, pk_stride);
-          }
-        });
-      }
+          if (window)
+            for (int64_t j = 0; j < nc; ++j) {
+              uint8_t* d0 = stage + (k - k0 + j) * ostride;
+              if (do_pack) pk2_pack_column(buf + j * span, span, d0, ostride);
+              else memcpy(d0, buf + j * span, size_t(span));
+            }
+          k += nc;
+        }
+      });
+    } else if (do_pack) {
+      HostPool::instance().begin(lcc, std::max<int64_t>(1, (int64_t(1) << 20) / span), [=](int64_t a, int64_t e) {
+        for (int64_t k = k0 + a; k < k0 + e; ++k) {
+          const int64_t col = plp->cols_contig ? plp->col0 + k : plp->cols0[k];
+          pk2_pack_column(base + col * nrow + rlo, span, stage + (k - k0) * pk_stride, pk_stride);
+        }
+      });
+    } else if (pl.cols_contig && span == nrow) {
+      const uint8_t* from = base + (pl.col0 + k0) * nrow;
+      HostPool::instance().begin(lcc * nrow, int64_t(8) << 20, [=](int64_t a, int64_t e) { memcpy(stage + a, from + a, size_t(e - a)); });
     } else {
-      S.h2d_bytes = lcc * span;
-      S.col_stride = span;
-      if (pl.cols_contig && span == nrow) {
-        const uint8_t* from = base + (pl.col0 + k0) * nrow;
-        HostPool::instance().begin(lcc * nrow, int64_t(8) << 20, [=](int64_t a, int64_t e) { memcpy(stage + a, from + a, size_t(e - a)); });
-      } else {
-        HostPool::instance().begin(lcc, std::max<int64_t>(1, (int64_t(4) << 20) / span), [=](int64_t a, int64_t e) {
-          for (int64_t k = k0 + a; k < k0 + e; ++k) {
-            const int64_t col = plp->cols_contig ? plp->col0 + k : plp->cols0[k];
-            memcpy(stage + (k - k0) * span, base + col * nrow + rlo, size_t(span));
-          }
-        });
-      }
+      HostPool::instance().begin(lcc, std::max<int64_t>(1, (int64_t(4) << 20) / span), [=](int64_t a, int64_t e) {
+        for (int64_t k = k0 + a; k < k0 + e; ++k) {
+          const int64_t col = plp->cols_contig ? plp->col0 + k : plp->cols0[k];
+          memcpy(stage + (k - k0) * span, base + col * nrow + rlo, size_t(span));
+        }
+      });
     }
     return TPG_OK;
   };
@@ -605,7 +702,10 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       ms_read += ms;
       const int64_t lcc = std::min(pl.m_shard, (c + 1) * lc) - c * lc;
       if (S.packed && ms > 0) pack_gbps = 0.5 * pack_gbps + 0.5 * double(lcc * span) / (ms * 1e6);
-      if (io_err.load()) return E.fail(TPG_ERR_IO, "reading '%s' failed: %s", job->bk_path, strerror(errno));
+      if (const int err = io_err.load())
+        return E.fail(TPG_ERR_IO, "reading '%s' failed: %s", job->bk_path,
+                      err < 0 ? "unexpected end of file (backing file shorter than nrow x ncol?)" : strerror(err));
+      if (use_pread && direct_io) ++n_dio;
     }
     link_free_at = std::max(link_free_at, now_ms()) + double(S.h2d_bytes) / (link_gbps * 1e6);
     return TPG_OK;
@@ -635,6 +735,9 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     da.nplanes = pl.nplanes;
     da.k_major = k_major;
     da.row_idx = B.d_rows;
+    bool gather_now = false;     // this chunk goes through gather_pack before it is decoded
+    bool gather_packed_in = false;
+    int64_t gather_row_lo = 0;
     if (on_device) {
       da.raw = src.base;
       da.raw_bytes = int64_t(src.bytes);
@@ -642,6 +745,8 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       da.row0 = pl.row0;
       da.col_idx = pl.cols_contig ? nullptr : B.d_cols + k0;
       da.col0 = pl.col0 + k0;
+      gather_now = gp_dev;
+      gather_row_lo = rlo;
       TPG_CUDA_OK(cudaEventRecord(tm[c].c0, ctx->s_copy), E);
       TPG_CUDA_OK(cudaEventRecord(tm[c].c1, ctx->s_copy), E);
     } else {
@@ -670,15 +775,11 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       da.row0 = packed ? 0 : (pl.rows_contig ? pl.row0 - (use_direct ? 0 : rlo) : 0);
       da.col_idx = nullptr;
       da.col0 = 0;
-    }
-    // (2-bit packed chunks decode to 4-bit planes too; TPG_PK2_I8=1 keeps them on the int8 kernels)
-    const bool use_q4 = q4_ok && !(da.packed && pk2_i8);
-    const int64_t q4_lc_pad = round_up(lcc, 256);
-    const int64_t q4_stride = pl.n_pad * (round_up(lc, 256) / 2);  // <= plane_stride: fits the int8 plane buffer
-    if (use_q4) {
-      da.k4 = true;
-      da.lc_pad = q4_lc_pad;
-      da.plane_stride = q4_stride;
+      if (rows_g && (packed || gp_staged)) {
+        gather_now = true;
+        gather_packed_in = packed;
+        gather_row_lo = use_direct ? rlo : 0;  // (a direct chunk of a gathered job only exists direct-only: rlo = 0)
+      }
     }
     if (scan) {  // one pass over the chunk's bytes; no planes, no products
       ScanArgs sa = *scan;
@@ -693,13 +794,35 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       TPG_CUDA_OK(cudaEventRecord(tm[c].g1, ctx->s_compute), E);
       continue;
     }
-    // planes[b] were last read by the gram of chunk c-2
+    // planes[b] (and the gathered copy b) were last read by the gram / decode of chunk c-2
     if (c >= 2) TPG_CUDA_OK(cudaStreamWaitEvent(s_dec, ev_gram_done[b], 0), E);
     TPG_CUDA_OK(cudaEventRecord(tm[c].d0, s_dec), E);
+    if (gather_now) {
+      // gathered rows: stage the row span in shared memory, gather there, write the dense chunk 2-bit
+      // packed (decode.cu, "row gather through shared memory"); ind.col of a device source is applied too
+      rc = launch_gather_pack(ctx, da, gather_packed_in, gather_row_lo, g_span, B.d_gat[b], g_stride, s_dec, E);
+      if (rc) return rc;
+      da.raw = B.d_gat[b];
+      da.raw_bytes = g_stride * lcc;
+      da.raw_stride = g_stride;
+      da.packed = true;
+      da.row_idx = nullptr;
+      da.row0 = 0;
+      da.col_idx = nullptr;
+      da.col0 = 0;
+    }
+    // (2-bit packed chunks decode to 4-bit planes too; pk2_i8 keeps them on the int8 kernels)
+    const bool use_q4 = q4_ok && !(da.packed && C.pk2_i8);
+    const int64_t q4_lc_pad = round_up(lcc, 256);
+    const int64_t q4_stride = pl.n_pad * (round_up(lc, 256) / 2);  // <= plane_stride: fits the int8 plane buffer
+    if (use_q4) {
+      da.k4 = true;
+      da.lc_pad = q4_lc_pad;
+      da.plane_stride = q4_stride;
+    }
     if (compact_gather && use_q4) {
-      // device-resident chunk with gathered rows: compact it first (decode.cu, "row / locus gather"), then
-      // the 4-bit decode takes its contiguous fast path on the dense copy (raw buffer b is free: device
-      // sources stage nothing; s_dec orders compact(c + 2) after decode(c))
+      // span too long for shared memory: compact through L2 (compact_rows_kernel), then the 4-bit decode
+      // takes its contiguous fast path on the dense copy (raw buffer b is free: device sources stage nothing)
       rc = ensure_slot(&ctx->d_raw[b], size_t(pl.n_pad) * size_t(lcc) + 64, false, "compacted chunk", E);
       if (rc) return rc;
       uint8_t* dense = static_cast<uint8_t*>(ctx->d_raw[b].p);
@@ -726,7 +849,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     ga.n_pad = pl.n_pad;
     ga.lc_pad = use_q4 ? q4_lc_pad : lc_pad;
     ga.mxf4 = use_q4;
-    if (use_q4) n_q4++;
+    if (use_q4) n_q4++; else n_i8++;
     ga.k_major = k_major;
     ga.ctas = (job->flags & TPG_FLAG_GRAM_1CTA) ? 1 : 0;
     ga.prod_mask = pl.prod_mask;
@@ -734,6 +857,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     ga.shard_world = job->shard_mode == TPG_SHARD_TILES ? job->shard_world : 1;
     ga.counts = d_counts;
     ga.ld = pl.n_pad;
+    ga.max_chain_out = &max_chain;
     int64_t mm = 0;
     TPG_CUDA_OK(cudaEventRecord(tm[c].g0, ctx->s_compute), E);
     rc = launch_gram(ctx, ga, ctx->s_compute, &mm, E);
@@ -743,6 +867,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     TPG_CUDA_OK(cudaEventRecord(ev_gram_done[b], ctx->s_compute), E);
     if (no_overlap) TPG_CUDA_OK(cudaStreamSynchronize(ctx->s_compute), E);
   }
+  drain.armed = false;
   ctx->pending = true;
   if (!defer) {
     rc = collect_accumulate(ctx, st, E);
@@ -752,6 +877,10 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   st->n_chunks += n_chunks;
   st->n_packed_chunks += n_packed;
   st->n_mxf4_chunks += n_q4;
+  st->n_i8_chunks += n_i8;
+  st->max_chain_loci = std::max(st->max_chain_loci, max_chain);
+  st->bytes_file += file_bytes.load();
+  st->n_direct_io += n_dio;
   st->mma_macs += macs;
   st->ms_total += now_ms() - t_begin;
   return TPG_OK;
@@ -787,7 +916,7 @@ static int results_to_host(Ctx* ctx, const void* const* dev, void* const* host, 
     // A fresh result matrix is untouched memory: the copy below is bound by first-touch page
     // faults (4 KiB each).  Ask for transparent huge pages on its 2 MiB-aligned interior; the
     // call is advisory and fails harmlessly where THP is off.
-    if (bytes >= (size_t(8) << 20) && !getenv("TPG_NO_THP")) {
+    if (bytes >= (size_t(8) << 20) && !cfg().no_thp) {
       const uintptr_t lo = (reinterpret_cast<uintptr_t>(host[o]) + (size_t(2) << 20) - 1) & ~((uintptr_t(2) << 20) - 1);
       const uintptr_t hi = (reinterpret_cast<uintptr_t>(host[o]) + bytes) & ~((uintptr_t(2) << 20) - 1);
       if (hi > lo) madvise(reinterpret_cast<void*>(lo), size_t(hi - lo), MADV_HUGEPAGE);
@@ -915,18 +1044,70 @@ static Ctx* rank_ctx(int slot, int device, const Err& E, int* rc) {
 // a += b, launched on device 0's stream (finish.cu)
 int launch_add_counts(Ctx* ctx, int32_t* a, const int32_t* b, int64_t elems, cudaStream_t st, const Err& E);
 
+// ------------------------------------------------------------------ one pass, several statistics
+static int union_mask(const int32_t* stats, int nstats) {
+  int mask = 0;
+  for (int k = 0; k < nstats; ++k) mask |= prod_mask_for(stats[k]);
+  return mask;
+}
+static const int kAllProducts = (1 << TPG_MAT_DD) | (1 << TPG_MAT_NN) | (1 << TPG_MAT_HH) | (1 << TPG_MAT_HN);
+
+static uint64_t fnv1a(const void* p, size_t bytes, uint64_t h = 1469598103934665603ull) {
+  const uint8_t* b = static_cast<const uint8_t*>(p);
+  for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+// Identity of (X, ind.row, ind.col) for the count-matrix cache (tpg_config.cache_counts): file-backed
+// sources only — device, inode, size and mtime of the .bk say whether the bytes are still the same.
+// Empty = not cacheable.
+static std::string counts_cache_key(const tpg_job* job) {
+  if (!cfg().cache_counts || job->src_kind != TPG_SRC_FILE || !job->bk_path) return std::string();
+  if (job->shard_mode != TPG_SHARD_NONE && job->shard_world > 1) return std::string();
+  struct stat sb;
+  if (stat(job->bk_path, &sb) != 0) return std::string();
+  const int64_t n = job->ind_row ? job->n : job->nrow_total, m = job->ind_col ? job->m : job->ncol_total;
+  const uint64_t hr = job->ind_row ? fnv1a(job->ind_row, sizeof(int32_t) * size_t(n)) : 0;
+  const uint64_t hc = job->ind_col ? fnv1a(job->ind_col, sizeof(int32_t) * size_t(m)) : 0;
+  char key[512];
+  snprintf(key, sizeof key, "%llu:%llu:%lld:%lld.%09ld|%lldx%lld|r%lld:%016llx|c%lld:%016llx",
+           (unsigned long long)sb.st_dev, (unsigned long long)sb.st_ino, (long long)sb.st_size,
+           (long long)sb.st_mtim.tv_sec, (long)sb.st_mtim.tv_nsec, (long long)job->nrow_total,
+           (long long)job->ncol_total, (long long)(job->ind_row ? n : -1), (unsigned long long)hr,
+           (long long)(job->ind_col ? m : -1), (unsigned long long)hc);
+  return std::string(key);
+}
+
+// Finishes every requested statistic from one set of count matrices on ctx.  results[0].stats
+// receives the stage times of the shared pass (the accumulate is collected by the first finish).
+static int finish_many(Ctx* c, const tpg_job* job, const int32_t* stats, int nstats, const int32_t* d_counts,
+                       tpg_result* results, const Err& E) {
+  int rc = TPG_OK;
+  for (int k = 0; k < nstats && rc == TPG_OK; ++k) {
+    tpg_job jk = *job;
+    jk.stat = stats[k];
+    rc = finish_impl(c, &jk, d_counts, &results[k], E);
+  }
+  return rc;
+}
+
 // In-process multi-GPU job (the R process is one process): one host thread per device
 // accumulates its shard (loci slice, or owned output blocks) into its own count matrices;
 // the int32 matrices are then summed onto the first device over NVLink (peer copies) and
 // finished there once.  Exact for both partitions, because counts are integer sums and the
 // tile partition's per-rank matrices are disjoint.
-static int pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* devices, int ndev,
-                          int shard_mode, const Err& E) {
+static int pairwise_multi(const tpg_job* job, const int32_t* stats, int nstats, tpg_result* results,
+                          const int32_t* devices, int ndev, int shard_mode, const Err& E) {
   if (ndev <= 0 || !devices) return E.fail(TPG_ERR_ARG, "no devices given");
   if (ndev > 64) return E.fail(TPG_ERR_ARG, "at most 64 devices");
   if (ndev > 1 && job->src_kind == TPG_SRC_DEVICE)
     return E.fail(TPG_ERR_ARG, "a device-resident source lives on one GPU; multi-GPU jobs take a file or host source");
-  if (!res || !res->out0) return E.fail(TPG_ERR_ARG, "result / out0 is NULL");
+  if (nstats <= 0 || !stats || !results) return E.fail(TPG_ERR_ARG, "no statistics requested");
+  for (int k = 0; k < nstats; ++k) {
+    if (!prod_mask_for(stats[k])) return E.fail(TPG_ERR_ARG, "unknown stat %d", stats[k]);
+    if (!results[k].out0) return E.fail(TPG_ERR_ARG, "result / out0 is NULL");
+    memset(&results[k].stats, 0, sizeof results[k].stats);
+  }
   const int64_t n = job->ind_row ? job->n : job->nrow_total;
   if (n <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row");
   if (shard_mode != TPG_SHARD_LOCI && shard_mode != TPG_SHARD_TILES)
@@ -935,9 +1116,10 @@ static int pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* de
     // device stay within 64 GB (n <= ~63,000), tiles beyond.
     shard_mode = tpg_counts_elems(n) * int64_t(sizeof(int32_t)) <= (int64_t(64) << 30) ? TPG_SHARD_LOCI : TPG_SHARD_TILES;
   const double t_begin = now_ms();
-  memset(&res->stats, 0, sizeof res->stats);
   const size_t celems = size_t(tpg_counts_elems(n));
   const size_t cbytes = sizeof(int32_t) * celems;
+  const std::string key = counts_cache_key(job);
+  const int mask = key.empty() ? union_mask(stats, nstats) : kAllProducts;
 
   std::vector<Ctx*> ctxs(ndev, nullptr);
   for (int r = 0; r < ndev; ++r) {
@@ -945,6 +1127,21 @@ static int pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* de
     ctxs[r] = rank_ctx(r, devices[r], E, &rc);
     if (!ctxs[r]) return rc;
   }
+  Ctx* c0 = ctxs[0];
+  tpg_job j0 = *job;
+  j0.device = c0->device;
+  j0.shard_mode = TPG_SHARD_NONE;
+  j0.shard_rank = 0;
+  j0.shard_world = 1;
+  if (!key.empty() && c0->counts_key == key && c0->counts_key_n == n && c0->d_counts.p) {
+    // the count matrices of this (X, ind.row, ind.col) are still on the first device: finish from them
+    TPG_CUDA_OK(cudaSetDevice(c0->device), E);
+    int rc = finish_many(c0, &j0, stats, nstats, static_cast<int32_t*>(c0->d_counts.p), results, E);
+    results[0].stats.n_cached_jobs = 1;
+    results[0].stats.ms_total = now_ms() - t_begin;
+    return rc;
+  }
+  c0->counts_key.clear();
   std::vector<int> rcs(ndev, TPG_OK);
   std::vector<std::string> msgs(ndev);
   std::vector<tpg_stats> sts(ndev);
@@ -956,6 +1153,7 @@ static int pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* de
       Ctx* c = ctxs[r];
       memset(&sts[r], 0, sizeof(tpg_stats));
       tpg_job j = *job;
+      j.stat = stats[0];
       j.device = devices[r];
       j.shard_mode = ndev > 1 ? shard_mode : TPG_SHARD_NONE;
       j.shard_rank = r;
@@ -965,7 +1163,10 @@ static int pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* de
       if (rc == TPG_OK) rc = ensure_slot(&c->d_counts, cbytes, false, "count matrices", Er);
       if (rc == TPG_OK && cudaMemsetAsync(c->d_counts.p, 0, cbytes, c->s_compute) != cudaSuccess)
         rc = Er.fail(TPG_ERR_CUDA, "memset failed");
-      if (rc == TPG_OK) { c->launches++; rc = accumulate_impl(c, &j, static_cast<int32_t*>(c->d_counts.p), &sts[r], Er); }
+      if (rc == TPG_OK) {
+        c->launches++;
+        rc = accumulate_impl(c, &j, static_cast<int32_t*>(c->d_counts.p), &sts[r], Er, false, nullptr, mask);
+      }
       rcs[r] = rc;
       msgs[r] = buf;
     });
@@ -980,8 +1181,6 @@ static int pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* de
   // by side on their own devices, so 8 ranks need 3 steps instead of 7 serial copy + add rounds.
   // Without peer access between a pair (e.g. the same device listed twice) the pair falls back to a
   // copy through a staging buffer.
-  Ctx* c0 = ctxs[0];
-  const int mask = prod_mask_for(job->stat);
   const int64_t ld = tpg_counts_ld(n), ms = ld * ld;
   const double t_red = now_ms();
   for (int step = 1; step < ndev; step <<= 1) {
@@ -1027,27 +1226,130 @@ static int pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* de
   }
   TPG_CUDA_OK(cudaSetDevice(c0->device), E);
   const double ms_reduce = now_ms() - t_red;
-  tpg_job j0 = *job;
-  j0.device = c0->device;
-  j0.shard_mode = TPG_SHARD_NONE;
-  j0.shard_rank = 0;
-  j0.shard_world = 1;
-  int rc = finish_impl(c0, &j0, static_cast<int32_t*>(c0->d_counts.p), res, E);
+  int rc = finish_many(c0, &j0, stats, nstats, static_cast<int32_t*>(c0->d_counts.p), results, E);
+  if (rc == TPG_OK && !key.empty()) { c0->counts_key = key; c0->counts_key_n = n; }
   // stats: stage times are the max over devices (they ran side by side); bytes and MACs add up
+  tpg_stats& S = results[0].stats;
   for (int r = 0; r < ndev; ++r) {
-    res->stats.ms_read = std::max(res->stats.ms_read, sts[r].ms_read);
-    res->stats.ms_h2d = std::max(res->stats.ms_h2d, sts[r].ms_h2d);
-    res->stats.ms_decode = std::max(res->stats.ms_decode, sts[r].ms_decode);
-    res->stats.ms_gram = std::max(res->stats.ms_gram, sts[r].ms_gram);
-    res->stats.bytes_h2d += sts[r].bytes_h2d;
-    res->stats.n_chunks += sts[r].n_chunks;
-    res->stats.n_packed_chunks += sts[r].n_packed_chunks;
-    res->stats.n_mxf4_chunks += sts[r].n_mxf4_chunks;
-    res->stats.mma_macs += sts[r].mma_macs;
-    res->stats.n_launches += sts[r].n_launches;
+    S.ms_read = std::max(S.ms_read, sts[r].ms_read);
+    S.ms_h2d = std::max(S.ms_h2d, sts[r].ms_h2d);
+    S.ms_decode = std::max(S.ms_decode, sts[r].ms_decode);
+    S.ms_gram = std::max(S.ms_gram, sts[r].ms_gram);
+    S.max_chain_loci = std::max(S.max_chain_loci, sts[r].max_chain_loci);
+    S.bytes_h2d += sts[r].bytes_h2d;
+    S.bytes_file += sts[r].bytes_file;
+    S.n_chunks += sts[r].n_chunks;
+    S.n_packed_chunks += sts[r].n_packed_chunks;
+    S.n_mxf4_chunks += sts[r].n_mxf4_chunks;
+    S.n_i8_chunks += sts[r].n_i8_chunks;
+    S.n_direct_io += sts[r].n_direct_io;
+    S.mma_macs += sts[r].mma_macs;
+    S.n_launches += sts[r].n_launches;
   }
-  res->stats.ms_finish += ms_reduce;  // the NVLink reduction is accounted with the finish stage
-  res->stats.ms_total = now_ms() - t_begin;
+  S.ms_reduce = ms_reduce;
+  S.ms_total = now_ms() - t_begin;
+  return rc;
+}
+
+// Caller-visible result matrices that live in files (tpg_result.out0_path / out1_path): mapped
+// read-write for the duration of a job, synced and unmapped afterwards.
+struct ResultMaps {
+  struct M { void* p = nullptr; size_t bytes = 0; };
+  std::vector<M> maps;
+  ~ResultMaps() {
+    for (M& m : maps)
+      if (m.p) { msync(m.p, m.bytes, MS_SYNC); munmap(m.p, m.bytes); }
+  }
+  int map_one(const char* path, size_t bytes, double** out, const Err& E) {
+    const int fd = open(path, O_RDWR);
+    if (fd < 0) return E.fail(TPG_ERR_IO, "cannot open result backing file '%s': %s", path, strerror(errno));
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || size_t(sb.st_size) < bytes) {
+      close(fd);
+      return E.fail(TPG_ERR_ARG, "result backing file '%s' is smaller than the n x n doubles it must hold (%zu bytes)", path, bytes);
+    }
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return E.fail(TPG_ERR_IO, "mmap('%s') failed: %s", path, strerror(errno));
+    maps.push_back(M{p, bytes});
+    *out = static_cast<double*>(p);
+    return TPG_OK;
+  }
+  // Fills out0 / out1 of a working copy of the caller's results from their paths.
+  int apply(const tpg_job* job, tpg_result* res, int nres, const Err& E) {
+    const int64_t n = job->ind_row ? job->n : job->nrow_total;
+    if (n <= 0) return TPG_OK;  // reported by the job itself
+    const size_t bytes = sizeof(double) * size_t(n) * size_t(n);
+    for (int k = 0; k < nres; ++k) {
+      if ((res[k].out0_path || res[k].out1_path) && res[k].out_on_device)
+        return E.fail(TPG_ERR_ARG, "file-backed results cannot be device pointers");
+      if (!res[k].out0 && res[k].out0_path) { int rc = map_one(res[k].out0_path, bytes, &res[k].out0, E); if (rc) return rc; }
+      if (!res[k].out1 && res[k].out1_path) { int rc = map_one(res[k].out1_path, bytes, &res[k].out1, E); if (rc) return rc; }
+    }
+    return TPG_OK;
+  }
+};
+
+static int pairwise_many_on(Ctx* c, const tpg_job* job, const int32_t* stats, int nstats, tpg_result* results,
+                            const Err& E) {
+  if (job->shard_mode == TPG_SHARD_LOCI && job->shard_world > 1)
+    return E.fail(TPG_ERR_ARG, "loci-sharded jobs need the staged interface (tpg_accumulate, "
+                               "all-reduce of the counts, tpg_finish)");
+  if (nstats <= 0 || !stats || !results) return E.fail(TPG_ERR_ARG, "no statistics requested");
+  const int64_t l0 = c->launches;
+  const double t_begin = now_ms();
+  const int64_t n = job->ind_row ? job->n : job->nrow_total;
+  if (n <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row");
+  for (int k = 0; k < nstats; ++k) {
+    if (!prod_mask_for(stats[k])) return E.fail(TPG_ERR_ARG, "unknown stat %d", stats[k]);
+    if (!results[k].out0) return E.fail(TPG_ERR_ARG, "result / out0 is NULL");
+    memset(&results[k].stats, 0, sizeof results[k].stats);
+  }
+  TPG_CUDA_OK(cudaSetDevice(c->device), E);
+  const size_t cbytes = sizeof(int32_t) * size_t(tpg_counts_elems(n));
+  const std::string key = counts_cache_key(job);
+  int rc = TPG_OK;
+  if (!key.empty() && c->counts_key == key && c->counts_key_n == n && c->d_counts.p && c->d_counts.cap >= cbytes) {
+    // same .bk (size, mtime), same ind.row / ind.col as the job that left its four count matrices
+    // here: nothing to read, decode or multiply
+    rc = finish_many(c, job, stats, nstats, static_cast<int32_t*>(c->d_counts.p), results, E);
+    results[0].stats.n_cached_jobs = 1;
+  } else {
+    c->counts_key.clear();
+    rc = ensure_slot(&c->d_counts, cbytes, false, "count matrices", E);
+    if (rc) return rc;
+    int32_t* d_counts = static_cast<int32_t*>(c->d_counts.p);
+    cudaError_t e = cudaMemsetAsync(d_counts, 0, cbytes, c->s_compute);
+    if (e != cudaSuccess) return E.fail(TPG_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
+    c->launches++;
+    // memset -> decode -> gram -> finish are enqueued back to back; one sync at the very end
+    const int mask = !key.empty() ? kAllProducts : union_mask(stats, nstats);
+    tpg_job jw = *job;
+    jw.stat = stats[0];  // (tpg_pairwise_many ignores job->stat; the plan only needs a valid one)
+    rc = accumulate_impl(c, &jw, d_counts, &results[0].stats, E, /*defer=*/true, nullptr, mask);
+    if (rc == TPG_OK) rc = finish_many(c, job, stats, nstats, d_counts, results, E);
+    if (c->pending) {  // finish bailed out early: still drain the device work
+      tpg_stats scratch;
+      memset(&scratch, 0, sizeof scratch);
+      Err quiet{nullptr, 0};
+      collect_accumulate(c, &scratch, quiet);
+    }
+    if (rc == TPG_OK && !key.empty()) { c->counts_key = key; c->counts_key_n = n; }
+  }
+  results[0].stats.n_launches = c->launches - l0;
+  results[0].stats.ms_total = now_ms() - t_begin;
+  return rc;
+}
+
+// Runs `body` on working copies of the caller's results whose file-backed outputs are mapped, then
+// hands the stats back.
+template <class F>
+static int with_result_maps(const tpg_job* job, tpg_result* results, int nres, const Err& E, F&& body) {
+  std::vector<tpg_result> work(results, results + nres);
+  ResultMaps maps;
+  int rc = maps.apply(job, work.data(), nres, E);
+  if (rc == TPG_OK) rc = body(work.data());
+  for (int k = 0; k < nres; ++k) results[k].stats = work[k].stats;
   return rc;
 }
 
@@ -1057,7 +1359,7 @@ using namespace tpg;
 
 extern "C" {
 
-const char* tpg_version(void) { return "tidypopgen_b200 0.1.0 (sm_100a, abi 1)"; }
+const char* tpg_version(void) { return "tidypopgen_b200 0.2.0 (sm_100a, abi 2)"; }
 
 int tpg_device_count(void) {
   int n = 0;
@@ -1144,56 +1446,44 @@ int tpg_finish(tpg_ctx* h, const tpg_job* job, const int32_t* d_counts, tpg_resu
   return rc;
 }
 
-static int pairwise_on(Ctx* c, const tpg_job* job, tpg_result* res, const Err& E) {
-  if (job->shard_mode == TPG_SHARD_LOCI && job->shard_world > 1)
-    return E.fail(TPG_ERR_ARG, "loci-sharded jobs need the staged interface (tpg_accumulate, "
-                               "all-reduce of the counts, tpg_finish)");
-  const int64_t l0 = c->launches;
-  memset(&res->stats, 0, sizeof res->stats);
-  const int64_t n = job->ind_row ? job->n : job->nrow_total;
-  if (n <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row");
-  if (!res->out0) return E.fail(TPG_ERR_ARG, "result / out0 is NULL");
-  TPG_CUDA_OK(cudaSetDevice(c->device), E);
-  const size_t cbytes = sizeof(int32_t) * size_t(tpg_counts_elems(n));
-  int rc = ensure_slot(&c->d_counts, cbytes, false, "count matrices", E);
-  if (rc) return rc;
-  int32_t* d_counts = static_cast<int32_t*>(c->d_counts.p);
-  cudaError_t e = cudaMemsetAsync(d_counts, 0, cbytes, c->s_compute);
-  if (e != cudaSuccess) return E.fail(TPG_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
-  c->launches++;
-  // memset -> decode -> gram -> finish are enqueued back to back; one sync at the very end
-  rc = accumulate_impl(c, job, d_counts, &res->stats, E, /*defer=*/true);
-  if (rc == TPG_OK) rc = finish_impl(c, job, d_counts, res, E);
-  if (c->pending) {  // finish bailed out early: still drain the device work
-    tpg_stats scratch;
-    memset(&scratch, 0, sizeof scratch);
-    Err quiet{nullptr, 0};
-    collect_accumulate(c, &scratch, quiet);
-  }
-  res->stats.n_launches = c->launches - l0;
-  return rc;
-}
-
 int tpg_pairwise(const tpg_job* job, tpg_result* res, char* err, size_t errlen) {
   Err E{err, errlen};
   if (!job || !res) return E.fail(TPG_ERR_ARG, "job / result is NULL");
   int rc = TPG_OK;
   Ctx* c = cached_ctx(job->device, E, &rc);
   if (!c) return rc;
-  return pairwise_on(c, job, res, E);
+  return with_result_maps(job, res, 1, E, [&](tpg_result* w) { return pairwise_many_on(c, job, &job->stat, 1, w, E); });
 }
 
 int tpg_pairwise_ctx(tpg_ctx* h, const tpg_job* job, tpg_result* res, char* err, size_t errlen) {
   Err E{err, errlen};
   if (!h || !job || !res) return E.fail(TPG_ERR_ARG, "ctx / job / result is NULL");
-  return pairwise_on(reinterpret_cast<Ctx*>(h), job, res, E);
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  return with_result_maps(job, res, 1, E, [&](tpg_result* w) { return pairwise_many_on(c, job, &job->stat, 1, w, E); });
 }
 
 int tpg_pairwise_multi(const tpg_job* job, tpg_result* res, const int32_t* devices, int32_t ndev,
                        int32_t shard_mode, char* err, size_t errlen) {
   Err E{err, errlen};
   if (!job || !res) return E.fail(TPG_ERR_ARG, "job / result is NULL");
-  return pairwise_multi(job, res, devices, ndev, shard_mode, E);
+  return with_result_maps(job, res, 1, E, [&](tpg_result* w) {
+    return pairwise_multi(job, &job->stat, 1, w, devices, ndev, shard_mode, E);
+  });
+}
+
+int tpg_pairwise_many(const tpg_job* job, const int32_t* stats, int32_t nstats, tpg_result* results,
+                      const int32_t* devices, int32_t ndev, int32_t shard_mode, char* err, size_t errlen) {
+  Err E{err, errlen};
+  if (!job || !stats || !results || nstats <= 0) return E.fail(TPG_ERR_ARG, "job / stats / results is NULL");
+  if (nstats > 16) return E.fail(TPG_ERR_ARG, "at most 16 statistics per pass");
+  if (devices && ndev > 1)
+    return with_result_maps(job, results, nstats, E, [&](tpg_result* w) {
+      return pairwise_multi(job, stats, nstats, w, devices, ndev, shard_mode, E);
+    });
+  int rc = TPG_OK;
+  Ctx* c = cached_ctx((devices && ndev == 1) ? devices[0] : job->device, E, &rc);
+  if (!c) return rc;
+  return with_result_maps(job, results, nstats, E, [&](tpg_result* w) { return pairwise_many_on(c, job, stats, nstats, w, E); });
 }
 
 int tpg_grm_from_as(int device, const double* as_in, int64_t n, double* grm_out, double* mb_out,
@@ -1247,7 +1537,7 @@ int tpg_king_filter(const tpg_job* job_in, double kings_threshold, int32_t* keep
   memset(&res, 0, sizeof res);
   res.out0 = static_cast<double*>(c->d_out[0].p);
   res.out_on_device = 1;
-  rc = pairwise_on(c, &job, &res, E);   // KING stays in HBM
+  rc = pairwise_many_on(c, &job, &job.stat, 1, &res, E);   // KING stays in HBM
   if (rc) return rc;
   const double t0 = now_ms();
   rc = run_filter_high_relatedness(c, res.out0, true, n, kings_threshold, keep, order, n_removed, E);
@@ -1280,7 +1570,7 @@ int tpg_as_wg17(const tpg_job* job_in, const int32_t* group, int64_t npop, doubl
   memset(&res, 0, sizeof res);
   res.out0 = static_cast<double*>(c->d_out[0].p);
   res.out_on_device = 1;
-  rc = pairwise_on(c, &job, &res, E);   // allele sharing stays in HBM
+  rc = pairwise_many_on(c, &job, &job.stat, 1, &res, E);   // allele sharing stays in HBM
   if (rc) return rc;
   const double t0 = now_ms();
   rc = run_wg17(c, res.out0, true, n, group, npop, inbreeding, fst, fis, mb_out, E);

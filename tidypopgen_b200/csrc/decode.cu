@@ -327,6 +327,153 @@ int launch_compact_rows(Ctx* ctx, const DecodeArgs& a, uint8_t* out, cudaStream_
   return TPG_OK;
 }
 
+// ------------------------------------------------------------------ row gather through shared memory
+// SubBMAcc's row gather (src/snp_ibs.cpp:35: macc(i, j) = bk[(rowInd[i] - 1) + (colInd[j] - 1) * nrow]) for
+// ind.row in arbitrary order.  A byte gather straight from global memory costs one 32-byte sector per
+// genotype (compact_rows_kernel above: 0.13 of the HBM figure).  Here a CTA first stages the needed row
+// span [row_lo, row_lo + span) of L loci in shared memory with coalesced 16-byte loads — every byte of the
+// span crosses HBM once, in whole lines — and then gathers from shared memory by row index: a thread owns
+// 16 consecutive OUTPUT individuals (their 16 row offsets stay in registers for all L loci) and emits one
+// 32-bit word of 2-bit codes per locus, i.e. the dense chunk leaves in the pk2 layout (pack.cpp) that
+// decode_planes_k4_kernel<true> / decode_planes_pk2_kernel read: a quarter of the bytes of a raw compaction.
+// kPackedIn: the staged chunk is itself 2-bit packed (a host chunk packed by the worker pool while staging),
+// so gathered host jobs cross PCIe at 0.25 B per genotype too.
+// Traffic: span (or span / 4) bytes read per locus + n / 4 bytes written.
+constexpr int kGatherThreads = 256;
+
+struct GatherParams {
+  const uint8_t* raw;        // chunk base
+  const uint8_t* raw_end;
+  int64_t raw_stride;        // bytes between consecutive columns of the chunk
+  const int32_t* row_idx;    // n offsets, relative to the first row of the staged span
+  const int32_t* col_idx;    // device sources with gathered loci (raw columns), or nullptr
+  int64_t col0;              // first column (contiguous loci)
+  int64_t row_lo;            // first row of the span within a column (raw input: bytes; packed input: individuals, multiple of 4)
+  int span_bytes;            // bytes of a column to stage (raw: rows; packed: ceil(rows / 4))
+  int n;                     // output individuals
+  int lc;                    // loci in the chunk
+  int loci_per_cta;
+  int col_pitch;             // smem bytes per staged column (multiple of 16, >= span_bytes + 16)
+  uint8_t* out;              // pk2 dense chunk: column l at out + l * out_stride
+  int64_t out_stride;        // multiple of 16
+};
+
+template <bool kPackedIn>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_pack_kernel(const GatherParams p) {
+  extern __shared__ uint4 gsm4[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>(gsm4);
+  __shared__ int mis_s[64];
+  const int l0 = blockIdx.x * p.loci_per_cta;
+  const int nl = min(p.loci_per_cta, p.lc - l0);
+  // ---- stage: column l lands at sm + l * col_pitch + (its global address & 15), 16-byte chunks
+  const int chunks = (p.span_bytes + 15 + 15) / 16;  // covers any misalignment
+  for (int l = 0; l < nl; ++l) {
+    const int64_t col = p.col_idx ? int64_t(__ldg(p.col_idx + l0 + l)) : p.col0 + l0 + l;
+    const uint8_t* g = p.raw + col * p.raw_stride + (kPackedIn ? (p.row_lo >> 2) : p.row_lo);
+    const int mis = int(reinterpret_cast<uintptr_t>(g) & 15u);
+    if (threadIdx.x == 0) mis_s[l] = mis;
+    const uint8_t* ga = g - mis;
+    uint8_t* sdst = sm + size_t(l) * p.col_pitch;
+    for (int c = threadIdx.x; c < chunks; c += kGatherThreads) {
+      const uint8_t* src = ga + size_t(c) * 16;
+      if (src >= g + p.span_bytes) break;
+      uint4 v;
+      if (src >= p.raw && src + 16 <= p.raw_end) {
+        v = __ldg(reinterpret_cast<const uint4*>(src));
+      } else {  // first / last bytes of the allocation: byte-wise, never outside [raw, raw_end)
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (int b = 0; b < 16; ++b)
+          if (src + b >= p.raw && src + b < p.raw_end) w[b >> 2] |= uint32_t(__ldg(src + b)) << (8 * (b & 3));
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      *reinterpret_cast<uint4*>(sdst + size_t(c) * 16) = v;
+    }
+  }
+  __syncthreads();
+  // ---- gather: one 32-bit word (16 individuals) per thread and locus
+  const int words = int(p.out_stride >> 2);
+  for (int w = threadIdx.x; w < words; w += kGatherThreads) {
+    const int i0 = w * 16;
+    int32_t r[16];
+    if (i0 + 16 <= p.n) {
+      const int4* rp = reinterpret_cast<const int4*>(p.row_idx + i0);  // row_idx is 16-byte aligned (cudaMalloc)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int4 t = __ldg(rp + q);
+        r[4 * q] = t.x; r[4 * q + 1] = t.y; r[4 * q + 2] = t.z; r[4 * q + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = (i0 + j < p.n) ? __ldg(p.row_idx + i0 + j) : -1;
+    }
+    const int rbase = kPackedIn ? int(p.row_lo & 3) : 0;  // (row_lo is a multiple of 4 for packed chunks: always 0)
+    for (int l = 0; l < nl; ++l) {
+      const uint8_t* scol = sm + size_t(l) * p.col_pitch + mis_s[l];
+      uint32_t word = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        uint32_t c = 3u;
+        if (r[j] >= 0) {
+          if (kPackedIn) {
+            const int rr = r[j] + rbase;
+            c = (uint32_t(scol[rr >> 2]) >> ((rr & 3) * 2)) & 3u;
+          } else {
+            c = min(uint32_t(scol[r[j]]), 3u);
+          }
+        }
+        word |= c << (2 * j);
+      }
+      *reinterpret_cast<uint32_t*>(p.out + int64_t(l0 + l) * p.out_stride + int64_t(w) * 4) = word;
+    }
+  }
+}
+
+// Shared memory a gather CTA may use: two CTAs per SM while a column is small, one beyond.
+constexpr int kGatherSmemTwo = 100 * 1024, kGatherSmemMax = 200 * 1024;
+
+bool gather_pack_fits(int64_t span_bytes) { return span_bytes + 32 <= kGatherSmemMax; }
+
+int launch_gather_pack(Ctx* ctx, const DecodeArgs& a, bool packed_in, int64_t row_lo, int64_t span_rows,
+                       uint8_t* out, int64_t out_stride, cudaStream_t st, const Err& E) {
+  const int64_t span_bytes = packed_in ? (span_rows + 3) / 4 : span_rows;
+  if (!a.row_idx || a.n <= 0 || a.lc <= 0 || a.n > INT32_MAX || a.lc > INT32_MAX || out_stride % 16 ||
+      out_stride * 4 < a.n || (reinterpret_cast<uintptr_t>(out) & 15) || (packed_in && (row_lo & 3)))
+    return E.fail(TPG_ERR_ARG, "gather_pack: needs a row index and a 16-byte aligned pk2 target");
+  if (!gather_pack_fits(span_bytes))
+    return E.fail(TPG_ERR_ARG, "gather_pack: a %lld-byte column span does not fit shared memory", (long long)span_bytes);
+  GatherParams p;
+  p.raw = a.raw;
+  p.raw_end = a.raw + a.raw_bytes;
+  p.raw_stride = a.raw_stride;
+  p.row_idx = a.row_idx;
+  p.col_idx = a.col_idx;
+  p.col0 = a.col0;
+  p.row_lo = row_lo;
+  p.span_bytes = int(span_bytes);
+  p.n = int(a.n);
+  p.lc = int(a.lc);
+  p.col_pitch = int((span_bytes + 16 + 15) / 16 * 16);
+  const int budget = p.col_pitch * 2 <= kGatherSmemTwo ? kGatherSmemTwo : kGatherSmemMax;
+  p.loci_per_cta = int(std::max<int64_t>(1, std::min<int64_t>(64, budget / p.col_pitch)));
+  // enough CTAs to fill the machine: shrink the loci per CTA for short chunks
+  while (p.loci_per_cta > 1 && (a.lc + p.loci_per_cta - 1) / p.loci_per_cta < 2 * ctx->num_sms) p.loci_per_cta /= 2;
+  p.out = out;
+  p.out_stride = out_stride;
+  const size_t smem = size_t(p.loci_per_cta) * size_t(p.col_pitch);
+  const unsigned blocks = unsigned((a.lc + p.loci_per_cta - 1) / p.loci_per_cta);
+  if (!ctx->gather_attr_set) {  // function attributes are per device
+    TPG_CUDA_OK(cudaFuncSetAttribute(gather_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmemMax), E);
+    TPG_CUDA_OK(cudaFuncSetAttribute(gather_pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmemMax), E);
+    ctx->gather_attr_set = true;
+  }
+  if (packed_in) gather_pack_kernel<true><<<blocks, kGatherThreads, smem, st>>>(p);
+  else gather_pack_kernel<false><<<blocks, kGatherThreads, smem, st>>>(p);
+  TPG_CUDA_OK(cudaGetLastError(), E);
+  ctx->launches++;
+  return TPG_OK;
+}
+
 // ------------------------------------------------------------------ K-major (transposing)
 // Block = 128 individuals x 128 loci; warp w owns loci [16w, 16w+16), lane owns 4 individuals.
 __global__ void __launch_bounds__(256)
@@ -860,8 +1007,9 @@ int launch_scan(Ctx* ctx, const DecodeArgs& a, const ScanArgs& s, cudaStream_t s
   sp.lut = s.lut; sp.weight = s.weight; sp.ploidy = s.ploidy;
   sp.het_n = s.het_n; sp.na_n = s.na_n; sp.alt2 = s.alt2; sp.valid = s.valid; sp.na_l = s.na_l;
   sp.loci_per_cta = kScanLociDefault;
-  if (const char* ev = getenv("TPG_SCAN_LOCI")) sp.loci_per_cta = std::max(16, atoi(ev) / 16 * 16);
-  sp.flags = getenv("TPG_SCAN_NO_INDIV") ? 1 : 0;
+  const tpg_config C = cfg();
+  if (C.scan_loci_per_cta > 0) sp.loci_per_cta = std::max(16, C.scan_loci_per_cta / 16 * 16);
+  sp.flags = C.scan_no_indiv ? 1 : 0;
   const int64_t blocks = ((a.n + kDecThreads * 4 - 1) / (kDecThreads * 4)) * ((a.lc + sp.loci_per_cta - 1) / sp.loci_per_cta);
   if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "scan: chunk too large for one launch");
   scan_counts_kernel<<<unsigned(blocks), kDecThreads, 0, st>>>(p, sp);
@@ -898,7 +1046,7 @@ int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E) 
       return E.fail(TPG_ERR_ARG, "decode(k4, pk2): packed chunks are ungathered");
     const int64_t blocks = (a.n_pad / 128) * (a.lc_pad / 256);
     if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "decode: chunk too large for one launch");
-    const bool v1 = getenv("TPG_DECODE_K4_V1") != nullptr;  // the first build, kept as a cross-check
+    const bool v1 = cfg().decode_k4_v1 != 0;  // the first build, kept as a cross-check
     if (a.packed) decode_planes_k4_kernel<true><<<unsigned(blocks), 256, 0, st>>>(p);
     else if (v1) decode_planes_k4_v1_kernel<<<unsigned(blocks), 256, 0, st>>>(p);
     else decode_planes_k4_kernel<false><<<unsigned(blocks), 256, 0, st>>>(p);

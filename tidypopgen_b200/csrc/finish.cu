@@ -17,6 +17,7 @@
 // are column-major), the mirror tile goes through shared memory so both output tiles are
 // written coalesced.  HBM-bound: 4 B per count matrix read + 8 B per output written.
 #include "internal.h"
+#include "ddsum.cuh"
 #include "../../include/tpg_synth.h"
 
 namespace tpg {
@@ -76,7 +77,8 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams p) {
       const int32_t dd = DD[e], nn = NN[e];
       if (king) {
         const int32_t ni = HN[e], nj = tN[tx][jl];
-        const double K = double(dd - nn + ni + nj);
+        // (count matrices are int32, each <= m; their combinations are formed in FP64: exact, no wrap)
+        const double K = ((double(dd) - double(nn)) + double(ni)) + double(nj);
         const double Ni = double(ni), Nj = double(nj);
         const double pm = fmin(Ni, Nj);
         const double t1 = __ddiv_rn(K, __dmul_rn(2.0, pm));
@@ -87,12 +89,12 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams p) {
         v[3] = Ni;
         w3 = Nj;
       } else if (p.stat == TPG_STAT_AS || p.stat == TPG_STAT_GRM) {
-        const double num = double(dd + p.n_short), den = double(nn);
+        const double num = double(dd) + double(p.n_short), den = double(nn);
         v[0] = nn == 0 ? na_real() : __dmul_rn(0.5, __dadd_rn(1.0, __ddiv_rn(num, den)));
         v[2] = num;
         v[3] = den;
       } else {
-        const double ibs = double(nn + HH[e] + dd), valid = double(2 * nn);
+        const double ibs = (double(nn) + double(HH[e])) + double(dd), valid = 2.0 * double(nn);
         if (p.stat == TPG_STAT_IBS_RAW) {
           v[0] = ibs;
           v[1] = valid;
@@ -127,43 +129,43 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams p) {
 // ------------------------------------------------------------------ GRM (Weir & Goudet 2017)
 constexpr int kRedBlocks = 1024;
 
+// mb = mean of the off-diagonal, non-NA allele sharing (R: mean(x[off-diag], na.rm = TRUE), a
+// long-double two-pass mean).  Accumulated in double-double (ddsum.cuh) over a fixed tree — the
+// same arithmetic as wg17.cu / relate.cu, so GRM, indiv_inbreeding and pop_fst see ONE mb, correct
+// to the last double and identical from run to run.
 __global__ void __launch_bounds__(256)
-grm_partial_kernel(const double* as, int64_t n, double* psum, unsigned long long* pcnt) {
-  __shared__ double ss[256];
-  __shared__ unsigned long long sc[256];
-  double s = 0;
+grm_partial_kernel(const double* as, int64_t n, double* p_hi, double* p_lo, unsigned long long* pcnt) {
+  __shared__ double s_hi[8], s_lo[8];
+  __shared__ unsigned long long sc[8];
+  dd acc = dd_zero();
   unsigned long long c = 0;
   const int64_t total = n * n;
   for (int64_t e = int64_t(blockIdx.x) * 256 + threadIdx.x; e < total; e += int64_t(gridDim.x) * 256) {
     const int64_t i = e % n, j = e / n;
     const double x = as[e];
-    if (i != j && !isnan(x)) { s += x; ++c; }
+    if (i != j && !isnan(x)) { acc = dd_add_d(acc, x); ++c; }
   }
-  ss[threadIdx.x] = s;
-  sc[threadIdx.x] = c;
+  acc = dd_warp_sum(acc);
+  c = (unsigned long long)i64_warp_sum((long long)c);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_hi[warp] = acc.hi; s_lo[warp] = acc.lo; sc[warp] = c; }
   __syncthreads();
-  for (int h = 128; h > 0; h >>= 1) {
-    if (threadIdx.x < h) { ss[threadIdx.x] += ss[threadIdx.x + h]; sc[threadIdx.x] += sc[threadIdx.x + h]; }
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    dd t = dd_zero();
+    unsigned long long cc = 0;
+    for (int w = 0; w < 8; ++w) { t = dd_add(t, dd{s_hi[w], s_lo[w]}); cc += sc[w]; }
+    p_hi[blockIdx.x] = t.hi; p_lo[blockIdx.x] = t.lo; pcnt[blockIdx.x] = cc;
   }
-  if (threadIdx.x == 0) { psum[blockIdx.x] = ss[0]; pcnt[blockIdx.x] = sc[0]; }
 }
 
-__global__ void __launch_bounds__(256)
-grm_mean_kernel(const double* psum, const unsigned long long* pcnt, int nb, double* mb) {
-  __shared__ double ss[256];
-  __shared__ unsigned long long sc[256];
-  double s = 0;
-  unsigned long long c = 0;
-  for (int b = threadIdx.x; b < nb; b += 256) { s += psum[b]; c += pcnt[b]; }
-  ss[threadIdx.x] = s;
-  sc[threadIdx.x] = c;
-  __syncthreads();
-  for (int h = 128; h > 0; h >>= 1) {
-    if (threadIdx.x < h) { ss[threadIdx.x] += ss[threadIdx.x + h]; sc[threadIdx.x] += sc[threadIdx.x + h]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *mb = ss[0] / double(sc[0]);  // 0/0 -> NaN like R's mean(numeric(0))
+__global__ void __launch_bounds__(32)
+grm_mean_kernel(const double* p_hi, const double* p_lo, const unsigned long long* pcnt, int nb, double* mb) {
+  dd acc = dd_zero();
+  long long c = 0;
+  for (int b = threadIdx.x; b < nb; b += 32) { acc = dd_add(acc, dd{p_hi[b], p_lo[b]}); c += (long long)pcnt[b]; }
+  acc = dd_warp_sum(acc);
+  c = i64_warp_sum(c);
+  if (threadIdx.x == 0) *mb = dd_mean(acc, double(c));  // 0 entries -> NaN like R's mean(numeric(0))
 }
 
 __global__ void __launch_bounds__(256)
@@ -179,16 +181,17 @@ grm_apply_kernel(const double* as, int64_t total, const double* mbp, double* out
 
 int launch_grm(Ctx* ctx, const double* d_as, int64_t n, double* d_grm, double* mb_host,
                cudaStream_t st, const Err& E) {
-  int rc = ensure_slot(&ctx->d_red, kRedBlocks * (sizeof(double) + sizeof(unsigned long long)) + 16,
+  int rc = ensure_slot(&ctx->d_red, kRedBlocks * (2 * sizeof(double) + sizeof(unsigned long long)) + 16,
                        false, "reduction scratch", E);
   if (rc) return rc;
-  double* d_ps = static_cast<double*>(ctx->d_red.p);
-  unsigned long long* d_pc = reinterpret_cast<unsigned long long*>(d_ps + kRedBlocks);
+  double* d_ph = static_cast<double*>(ctx->d_red.p);
+  double* d_pl = d_ph + kRedBlocks;
+  unsigned long long* d_pc = reinterpret_cast<unsigned long long*>(d_pl + kRedBlocks);
   double* d_mb = reinterpret_cast<double*>(d_pc + kRedBlocks);
   const int64_t total = n * n;
   const int nb = int(std::min<int64_t>(kRedBlocks, (total + 255) / 256));
-  grm_partial_kernel<<<nb, 256, 0, st>>>(d_as, n, d_ps, d_pc);
-  grm_mean_kernel<<<1, 256, 0, st>>>(d_ps, d_pc, nb, d_mb);
+  grm_partial_kernel<<<nb, 256, 0, st>>>(d_as, n, d_ph, d_pl, d_pc);
+  grm_mean_kernel<<<1, 32, 0, st>>>(d_ph, d_pl, d_pc, nb, d_mb);
   const int gb = int(std::min<int64_t>(148 * 16, (total + 255) / 256));
   grm_apply_kernel<<<gb, 256, 0, st>>>(d_as, total, d_mb, d_grm);
   ctx->launches += 3;

@@ -589,7 +589,8 @@ static int make_plane_map(Ctx* ctx, CUtensorMap* out, const int8_t* base, uint64
 
 // Chooses how many k-splits a tile gets so that the persistent CTAs finish together.
 static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms) {
-  if (const char* ev = getenv("TPG_GRAM_KS")) return int(std::max<int64_t>(1, std::min<int64_t>(kblocks, atoi(ev))));
+  const tpg_config C = cfg();
+  if (C.gram_ksplit > 0) return int(std::max<int64_t>(1, std::min<int64_t>(kblocks, int64_t(C.gram_ksplit))));
   // Large problems: every CTA runs many items, balance is not the issue — L2 is.  CTAs that
   // run side by side share operand panels only while they stream the same loci; over a long
   // k range they drift apart and every CTA ends up fetching its panels from HBM by itself
@@ -597,7 +598,7 @@ static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms) {
   // n = 50,000 x 500,000: 256 k-blocks 3.25 s, 128 k-blocks 1.71 s).  With items of 128 k-blocks
   // (16,384 loci) the operand panels of a whole 1024 x 1024 tile region (~100 MB) fit in the
   // 126 MB L2, so the reuse no longer depends on the CTAs staying in lock step.
-  const int max_per = getenv("TPG_GRAM_MAXKB") ? std::max(8, atoi(getenv("TPG_GRAM_MAXKB"))) : 128;
+  const int max_per = C.gram_max_kblocks > 0 ? std::max(8, int(C.gram_max_kblocks)) : 128;
   const int ks_l2 = int((kblocks + max_per - 1) / max_per);
   if (n_tile_items >= int64_t(8) * sms) return std::max(1, ks_l2);
   int best = 1;
@@ -649,7 +650,7 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
       }
   } else {
     // the last column tile is trimmed to the valid individuals (multiples of 16, at least 32 for the epilogue)
-    const bool trim = !getenv("TPG_GRAM_NO_TRIM");
+    const bool trim = !cfg().gram_no_trim;
     for (int64_t c0 = 0; c0 < a.n; c0 += kQTileN) {
       const int64_t need = std::max<int64_t>(32, (a.n - c0 + 15) / 16 * 16);
       cols.push_back({int(c0), trim ? int(std::min<int64_t>(kQTileN, need)) : kQTileN});
@@ -673,7 +674,18 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
           }
         }
   if (tiles.empty()) { if (macs_out) *macs_out = 0; return TPG_OK; }
-  const int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units);
+  int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units);
+  // EXACTNESS GUARD.  The FP32 accumulator of kind::mxf4 holds integer sums exactly only below 2^24
+  // (gram_mxf4_pair_kernel): one work item = one accumulation chain never runs more than
+  // TPG_MXF4_MAX_CHAIN_LOCI (2^23) loci, whatever the chunk size, the auto heuristic or a gram_ksplit
+  // override asked for — longer k ranges are split, the int32 atomics combine the parts exactly.
+  constexpr int64_t kMaxChainKb = TPG_MXF4_MAX_CHAIN_LOCI / kQStageLoci;
+  if ((kblocks + ks - 1) / ks > kMaxChainKb) ks = int((kblocks + kMaxChainKb - 1) / kMaxChainKb);
+  if (a.max_chain_out) {
+    int64_t longest = 0;
+    for (int s2 = 0; s2 < ks; ++s2) longest = std::max<int64_t>(longest, kblocks * (s2 + 1) / ks - kblocks * s2 / ks);
+    *a.max_chain_out = std::max(*a.max_chain_out, longest * kQStageLoci);
+  }
   if (macs_out) {
     int64_t cells = 0;
     for (const T& t : tiles) cells += int64_t(kPairTileM) * t.ncols;
@@ -730,8 +742,7 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
 static bool pair_mode(const GramArgs& a) {
   if (a.ctas == 1) return false;
   if (a.ctas == 2) return true;
-  const char* e = getenv("TPG_GRAM_CTAS");
-  return !(e && atoi(e) == 1);
+  return cfg().gram_ctas != 1;
 }
 
 int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out, const Err& E) {
@@ -769,7 +780,7 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
     cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, gram_i8_pair_kernel<false>, &cfg);
     if (e != cudaSuccess) { cudaGetLastError(); nc = 0; }
     ctx->pair_clusters = std::min(nc, ctx->num_sms / 2);
-    if (const char* ev = getenv("TPG_GRAM_CLUSTERS")) ctx->pair_clusters = std::max(1, std::min(atoi(ev), ctx->num_sms / 2));
+    if (tpg::cfg().gram_clusters > 0) ctx->pair_clusters = std::max(1, std::min(int(tpg::cfg().gram_clusters), ctx->num_sms / 2));
     ctx->gram_attr_set = true;
   }
   if (pair && ctx->pair_clusters <= 0)
@@ -801,7 +812,7 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   const int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units);
 
   // The work list only depends on the geometry; chunks of equal size reuse the upload.
-  const bool trim_n = pair && !getenv("TPG_GRAM_NO_TRIM");
+  const bool trim_n = pair && !cfg().gram_no_trim;
   // N of a tile's MMAs: the pair kernel trims the last tile column to its valid columns (multiple of 32)
   auto tile_ncols = [&](int tj) {
     if (!trim_n) return int(kTileN);

@@ -7,6 +7,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include "../../include/tpg_b200.h"
+#include "config.h"
 
 namespace tpg {
 
@@ -42,11 +43,16 @@ struct Ctx {
   int64_t launches = 0;
   bool gram_attr_set = false;
   bool mxf4_attr_set = false;
+  bool gather_attr_set = false;
   int pair_clusters = 0;           // CTA pairs resident at once (cudaOccupancyMaxActiveClusters)
   // Grow-only buffer cache, reused across jobs (cudaMalloc / cudaMallocHost / cudaFree are
   // slow and synchronising; a job must not pay them every call).  tpg_ctx_trim() frees it.
   struct Slot { void* p = nullptr; size_t cap = 0; };
-  Slot d_raw[2], d_planes[2], h_pin[2], h_out[2], d_rows, d_cols, d_counts, d_out[4], d_red;
+  Slot d_raw[2], d_gat[2], d_planes[2], h_pin[2], h_out[2], d_rows, d_cols, d_counts, d_out[4], d_red;
+  // count-matrix cache (tpg_config.cache_counts): d_counts holds all four products of the job
+  // described by counts_key (file identity + indices); empty = nothing cached
+  std::string counts_key;
+  int64_t counts_key_n = 0;
   std::vector<cudaEvent_t> ev_timing, ev_plain;
   // accumulate enqueued but not yet collected (tpg_pairwise defers the sync to the end of finish)
   struct ChunkEv { cudaEvent_t c0, c1, d0, d1, g0, g1; };
@@ -95,6 +101,13 @@ int launch_decode(Ctx* ctx, const DecodeArgs& a, cudaStream_t st, const Err& E);
 // Gathers the rows (and loci) of a raw chunk into a dense column-major chunk: out[l * n_pad + i], padding
 // individuals = 0x03 (decode.cu).  a.planes / layout fields are ignored.
 int launch_compact_rows(Ctx* ctx, const DecodeArgs& a, uint8_t* out, cudaStream_t st, const Err& E);
+// The same gather through shared memory (decode.cu, "row gather through shared memory"): stages rows
+// [row_lo, row_lo + span_rows) of every locus with coalesced loads, gathers by a.row_idx (offsets relative
+// to row_lo) and writes the dense chunk 2-bit packed (pk2: column l at out + l * out_stride).  packed_in:
+// the chunk is itself pk2.  gather_pack_fits: a column span of that many BYTES fits a CTA's shared memory.
+bool gather_pack_fits(int64_t span_bytes);
+int launch_gather_pack(Ctx* ctx, const DecodeArgs& a, bool packed_in, int64_t row_lo, int64_t span_rows,
+                       uint8_t* out, int64_t out_stride, cudaStream_t st, const Err& E);
 
 // One-pass scan of a raw chunk through code256 (decode.cu): device pointers; the per-locus
 // arrays are already offset to the chunk's first locus.  Uses a.raw / row / col addressing only.
@@ -123,6 +136,7 @@ struct GramArgs {
   int shard_rank, shard_world;  // tile sharding (world <= 1: everything)
   int32_t* counts;
   int64_t ld;
+  int64_t* max_chain_out = nullptr;  // 4-bit route: longest accumulation chain (loci) of the launch
 };
 int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out, const Err& E);
 

@@ -23,6 +23,7 @@
 #include <vector>
 #include <immintrin.h>
 #include "hostpool.h"
+#include "config.h"
 
 namespace tpg {
 
@@ -75,10 +76,7 @@ HostPool& HostPool::instance() {
 int HostPool::max_threads() {
   unsigned hw = std::thread::hardware_concurrency();
   if (hw == 0) hw = 4;
-  if (const char* e = getenv("TPG_HOST_THREADS")) {
-    const int v = atoi(e);
-    if (v >= 1) return v;
-  }
+  { const int v = cfg().host_threads; if (v >= 1) return v; }
   // one process per GPU under torchrun: the ranks of a node share its cores
   if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
     const int w = atoi(e);

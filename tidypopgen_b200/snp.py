@@ -12,6 +12,7 @@ Indices follow R: `ind_row` / `ind_col` are 1-based, any order, any subset, no n
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -97,9 +98,10 @@ def _colmajor(n: int) -> np.ndarray:
 
 
 def run_job(X: FBMCode256, ind_row, ind_col, stat: int, block_size_: int, *, want_aux: bool = False,
-            out0=None, out1=None, devices=None, shard: str = "auto", **kw):
+            out0=None, out1=None, out0_path=None, out1_path=None, devices=None, shard: str = "auto", **kw):
     """One tpg_pairwise call (or tpg_pairwise_multi when `devices` lists several GPUs).
-    Returns (out0, out1, aux0, aux1) as [i, j]-indexed arrays."""
+    Returns (out0, out1, aux0, aux1) as [i, j]-indexed arrays.  out0_path / out1_path: the library maps
+    these files itself and writes the n x n doubles into them (the .bk of a bigstatsr FBM(n, n))."""
     global last_stats
     if devices is not None and len(devices) >= 1:
         kw.setdefault("device", int(devices[0]))
@@ -107,15 +109,18 @@ def run_job(X: FBMCode256, ind_row, ind_col, stat: int, block_size_: int, *, wan
     n = job.n if job.ind_row else X.nrow
     if n <= 0 or (job.m if job.ind_col else X.ncol) <= 0:
         raise ValueError("ind.row and ind.col must not be empty")
-    o0 = _colmajor(n) if out0 is None else out0
+    o0 = (_colmajor(n) if out0_path is None else None) if out0 is None else out0
     o1 = out1
-    if stat == L.STAT_IBS_RAW and o1 is None:
+    if stat == L.STAT_IBS_RAW and o1 is None and out1_path is None:
         o1 = _colmajor(n)
     a0 = _colmajor(n) if want_aux and stat != L.STAT_IBS_RAW else None
     a1 = _colmajor(n) if want_aux and stat not in (L.STAT_IBS_RAW, L.STAT_GRM) else None
     res = L.Result()
-    res.out0 = o0.ctypes.data
+    res.out0 = o0.ctypes.data if o0 is not None else None
     res.out1 = o1.ctypes.data if o1 is not None else None
+    p0 = os.fsencode(out0_path) if out0_path is not None else None
+    p1 = os.fsencode(out1_path) if out1_path is not None else None
+    res.out0_path, res.out1_path = p0, p1
     res.aux0 = a0.ctypes.data if a0 is not None else None
     res.aux1 = a1.ctypes.data if a1 is not None else None
     res.out_on_device = 0
@@ -174,10 +179,10 @@ def snp_ibs(X, ind_row=None, ind_col=None, type="proportion", block_size=None, *
     if type == "raw_counts":
         n = X.nrow if ind_row is None else len(np.asarray(ind_row).reshape(-1))
         ibs, valid = FBMDouble(n, n, init=None), FBMDouble(n, n, init=None)
-        # the library writes straight into the FBMs' column-major backing store
-        run_job(X, ind_row, ind_col, L.STAT_IBS_RAW, block_size, out0=ibs.buffer, out1=valid.buffer, **kw)
-        ibs.buffer.flush()
-        valid.buffer.flush()
+        # the library maps the two FBMs' backing files itself (tpg_result.out0_path / out1_path) and
+        # writes the counts there — what the R glue does with ibs$backingfile / valid_n$backingfile
+        run_job(X, ind_row, ind_col, L.STAT_IBS_RAW, block_size, out0_path=ibs.backingfile,
+                out1_path=valid.backingfile, **kw)
         return {"ibs": ibs, "valid_n": valid}
     out, _, _, _ = run_job(X, ind_row, ind_col, _STAT_BY_TYPE[type], block_size, **kw)
     return out
@@ -229,3 +234,48 @@ def grm_from_allele_sharing(as_mat: np.ndarray, device: int = 0):
     rc = L.lib().tpg_grm_from_as(device, a.ctypes.data, n, out.ctypes.data, C.byref(mb), eb, len(eb))
     L.check(rc, eb)
     return out, mb.value
+
+
+def snp_pairwise_many(X, stats=("king", "ibs", "allele_sharing"), ind_row=None, ind_col=None, block_size=None,
+                      pad_quirk=True, devices=None, shard: str = "auto", **kw) -> dict:
+    """KING, IBS and allele sharing (any subset; also "ibs_raw", "ibs_adjusted", "grm") of the same
+    (X, ind_row, ind_col) from ONE pass over the genotypes: tpg_pairwise_many computes the four integer
+    products once and finishes every statistic from them — what snp_king (R/snp_king.R:32), snp_ibs
+    (R/snp_ibs.R:42) and snp_allele_sharing (R/snp_allele_sharing.R:33) would each decode and multiply
+    for themselves.  Every matrix is identical to the one the single call returns.  block_size only
+    feeds the allele-sharing pad constant (default: bigstatsr block_size(nrow), as snp_allele_sharing)."""
+    global last_stats
+    _check_fbm(X)
+    codes = {"king": L.STAT_KING, "ibs": L.STAT_IBS_PROPORTION, "ibs_raw": L.STAT_IBS_RAW,
+             "ibs_adjusted": L.STAT_IBS_ADJUSTED, "allele_sharing": L.STAT_AS, "grm": L.STAT_GRM}
+    names = list(stats)
+    for s_ in names:
+        if s_ not in codes:
+            raise ValueError(f"unknown statistic '{s_}'")
+    if block_size is None:
+        block_size = globals()["block_size"](X.nrow)
+    if devices is not None and len(devices) >= 1:
+        kw.setdefault("device", int(devices[0]))
+    job, keep = make_job(X, ind_row, ind_col, codes[names[0]], block_size, pad_quirk=pad_quirk, **kw)
+    n = job.n if job.ind_row else X.nrow
+    if n <= 0 or (job.m if job.ind_col else X.ncol) <= 0:
+        raise ValueError("ind.row and ind.col must not be empty")
+    st = np.ascontiguousarray([codes[s_] for s_ in names], dtype=np.int32)
+    results = (L.Result * len(names))()
+    outs = {}
+    for k, s_ in enumerate(names):
+        o0 = _colmajor(n)
+        o1 = _colmajor(n) if s_ == "ibs_raw" else None
+        results[k].out0 = o0.ctypes.data
+        results[k].out1 = o1.ctypes.data if o1 is not None else None
+        outs[s_] = o0 if o1 is None else {"ibs": o0, "valid_n": o1}
+    devs = np.ascontiguousarray(devices, dtype=np.int32) if devices is not None and len(devices) > 1 else None
+    mode = {"auto": L.SHARD_NONE, "loci": L.SHARD_LOCI, "tiles": L.SHARD_TILES}[shard]
+    eb = L.errbuf()
+    rc = L.lib().tpg_pairwise_many(C.byref(job), st.ctypes.data, len(names), results,
+                                   devs.ctypes.data if devs is not None else None,
+                                   len(devs) if devs is not None else 0, mode, eb, len(eb))
+    del keep
+    L.check(rc, eb)
+    last_stats = results[0].stats.as_dict()
+    return outs
