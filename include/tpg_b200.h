@@ -404,6 +404,14 @@ int tpg_gram(tpg_ctx* ctx, const int8_t* d_planes, int64_t plane_stride, int64_t
 int tpg_synth_fill(tpg_ctx* ctx, uint8_t* d_raw, int64_t nrow, int64_t ncol, int64_t col_offset,
                    uint64_t seed, double missing_rate, int32_t mode, char* err, size_t errlen);
 
+/* Measures the tensor-pipe issue rate of `device` for the MMA kind of one of the two Gram routes —
+ * kind 0: tcgen05.mma.cta_group::2.kind::i8 (M256 N256 K32), kind 1: kind::mxf4.block_scale (M256 N256 K64)
+ * — with the operands resident in shared memory (no TMA / L2 traffic, no epilogue), on every CTA pair
+ * of the chip at once, for about `seconds`.  *tops = 2 x MACs per second / 1e12: the measured roofline
+ * the Gram kernels are read against (bench.py).  Short runs give the burst figure, runs of a second or
+ * more the power-limited sustained one. */
+int tpg_mma_peak(int device, int32_t kind, double seconds, double* tops, double* ms, char* err, size_t errlen);
+
 /* The 2-bit chunk format of the streamer ("pk2", csrc/pack.cpp): bytes per packed column for a
  * row window of span individuals, and the packer itself (runs on the library's worker pool):
  * column c is read at src + c*src_stride (span raw bytes) and written at dst + c*stride. */

@@ -11,7 +11,7 @@ HERE="$(cd "$(dirname "$0")/.." && pwd)"
 test -f "$PKG/DESCRIPTION" && grep -q '^Package: tidypopgen' "$PKG/DESCRIPTION" || { echo "$PKG is not a tidypopgen source tree" >&2; exit 1; }
 CS="$HERE/tidypopgen_b200/csrc"
 # sources: the includes are rewritten from the repository layout ("../../include/x.h") to a flat src/
-for f in api.cu decode.cu gram.cu finish.cu relate.cu wg17.cu pack.cpp config.cpp internal.h config.h hostpool.h ptx.cuh swar.cuh ddsum.cuh; do
+for f in api.cu decode.cu gram.cu finish.cu relate.cu wg17.cu peak.cu pack.cpp config.cpp internal.h config.h hostpool.h ptx.cuh swar.cuh ddsum.cuh; do
   sed 's#"\.\./\.\./include/#"#' "$CS/$f" > "$PKG/src/$f"
 done
 cp "$HERE/include/tpg_b200.h" "$HERE/include/tpg_synth.h" "$PKG/src/"

@@ -188,12 +188,12 @@ def test_r_package_build_through_makevars(tmp_path):
     r = subprocess.run(["bash", str(root / "r" / "install_into_tidypopgen.sh"), str(pkg)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert (pkg / "R" / "snp_gpu_drivers.R").exists() and not (pkg / "R" / "snp_king.R").exists()
-    objs = ["api.o", "decode.o", "gram.o", "finish.o", "relate.o", "wg17.o", "pack.o", "config.o", "gpu_glue.o"]
+    objs = ["api.o", "decode.o", "gram.o", "finish.o", "relate.o", "wg17.o", "peak.o", "pack.o", "config.o", "gpu_glue.o"]
     stubs = f"-I. -I{root / 'tests' / 'stubs'}"
     r = subprocess.run(["make", "-j8", "-f", "Makevars", "CXX=g++", f"ALL_CPPFLAGS={stubs}", f"CPPFLAGS={stubs}",
                         "CXXFLAGS=-std=c++17 -fPIC -O1"] + objs, cwd=pkg / "src", capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("arch=compute_100a,code=sm_100a") == 6 and "--fmad=false" in r.stdout
+    assert r.stdout.count("arch=compute_100a,code=sm_100a") == 7 and "--fmad=false" in r.stdout
     so = pkg / "src" / "tidypopgen.so"
     r = subprocess.run(["g++", "-shared", "-o", str(so)] + objs + ["-L/usr/local/cuda/lib64", "-lcudart_static", "-ldl",
                         "-lrt", "-lpthread"], cwd=pkg / "src", capture_output=True, text=True)

@@ -174,6 +174,7 @@ SIGNATURES = {
                                     C.c_void_p, C.c_int64, C.c_int32] + _ERR),
     "tpg_gram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                            C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_float)] + _ERR),
+    "tpg_mma_peak": (C.c_int, [C.c_int, C.c_int32, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)] + _ERR),
     "tpg_synth_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_uint64,
                                  C.c_double, C.c_int32] + _ERR),
     "tpg_synth_fill_host": (None, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_double,

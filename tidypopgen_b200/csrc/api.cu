@@ -1161,10 +1161,10 @@ static int pairwise_multi(const tpg_job* job, const int32_t* stats, int nstats, 
       int rc = TPG_OK;
       if (cudaSetDevice(c->device) != cudaSuccess) rc = Er.fail(TPG_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
       if (rc == TPG_OK) rc = ensure_slot(&c->d_counts, cbytes, false, "count matrices", Er);
-      if (rc == TPG_OK && cudaMemsetAsync(c->d_counts.p, 0, cbytes, c->s_compute) != cudaSuccess)
-        rc = Er.fail(TPG_ERR_CUDA, "memset failed");
+      // loci-sharded: every device adds into all blocks; tile-sharded: its own blocks only — but the tree
+      // reduction below sums WHOLE matrices, so everything a peer may read has to be zero
+      if (rc == TPG_OK) rc = launch_zero_counts(c, static_cast<int32_t*>(c->d_counts.p), n, mask, 0, 1, c->s_compute, Er);
       if (rc == TPG_OK) {
-        c->launches++;
         rc = accumulate_impl(c, &j, static_cast<int32_t*>(c->d_counts.p), &sts[r], Er, false, nullptr, mask);
       }
       rcs[r] = rc;
@@ -1319,11 +1319,11 @@ static int pairwise_many_on(Ctx* c, const tpg_job* job, const int32_t* stats, in
     rc = ensure_slot(&c->d_counts, cbytes, false, "count matrices", E);
     if (rc) return rc;
     int32_t* d_counts = static_cast<int32_t*>(c->d_counts.p);
-    cudaError_t e = cudaMemsetAsync(d_counts, 0, cbytes, c->s_compute);
-    if (e != cudaSuccess) return E.fail(TPG_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
-    c->launches++;
-    // memset -> decode -> gram -> finish are enqueued back to back; one sync at the very end
     const int mask = !key.empty() ? kAllProducts : union_mask(stats, nstats);
+    // zero -> decode -> gram -> finish are enqueued back to back; one sync at the very end
+    const bool tiles = job->shard_mode == TPG_SHARD_TILES && job->shard_world > 1;
+    rc = launch_zero_counts(c, d_counts, n, mask, tiles ? job->shard_rank : 0, tiles ? job->shard_world : 1, c->s_compute, E);
+    if (rc) return rc;
     tpg_job jw = *job;
     jw.stat = stats[0];  // (tpg_pairwise_many ignores job->stat; the plan only needs a valid one)
     rc = accumulate_impl(c, &jw, d_counts, &results[0].stats, E, /*defer=*/true, nullptr, mask);
@@ -1414,6 +1414,9 @@ void* tpg_ctx_stream(tpg_ctx* h) {
 void tpg_release(int device) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (device >= 0 && device < 64 && g_ctx[device]) trim_ctx(g_ctx[device]);
+  // ... and the per-rank contexts tpg_pairwise_multi / tpg_pairwise_many keep on that device
+  for (Ctx* c : g_rank_ctx)
+    if (c && c->device == device) trim_ctx(c);
 }
 
 int tpg_accumulate(tpg_ctx* h, const tpg_job* job, int32_t* d_counts, tpg_stats* stats, char* err,
@@ -1724,6 +1727,15 @@ int tpg_gram(tpg_ctx* h, const int8_t* d_planes, int64_t plane_stride, int64_t n
   if (rc == TPG_OK && ms_out) cudaEventElapsedTime(ms_out, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return rc;
+}
+
+int tpg_mma_peak(int device, int32_t kind, double seconds, double* tops, double* ms, char* err, size_t errlen) {
+  Err E{err, errlen};
+  int rc = TPG_OK;
+  Ctx* c = cached_ctx(device, E, &rc);
+  if (!c) return rc;
+  TPG_CUDA_OK(cudaSetDevice(c->device), E);
+  return run_mma_peak(c, kind, seconds, tops, ms, E);
 }
 
 int tpg_synth_fill(tpg_ctx* h, uint8_t* d_raw, int64_t nrow, int64_t ncol, int64_t col_offset,

@@ -358,38 +358,48 @@ struct GatherParams {
   int64_t out_stride;        // multiple of 16
 };
 
+__device__ __forceinline__ uint32_t smem_u32_(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
 template <bool kPackedIn>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_pack_kernel(const GatherParams p) {
   extern __shared__ uint4 gsm4[];
   uint8_t* sm = reinterpret_cast<uint8_t*>(gsm4);
   __shared__ int mis_s[64];
+  __shared__ const uint8_t* col_s[64];
   const int l0 = blockIdx.x * p.loci_per_cta;
   const int nl = min(p.loci_per_cta, p.lc - l0);
-  // ---- stage: column l lands at sm + l * col_pitch + (its global address & 15), 16-byte chunks
+  // ---- stage: column l lands at sm + l * col_pitch + (its global address & 15), in 16-byte chunks copied
+  // asynchronously (cp.async: no register staging, every chunk of the CTA in flight at once)
   const int chunks = (p.span_bytes + 15 + 15) / 16;  // covers any misalignment
-  for (int l = 0; l < nl; ++l) {
+  if (threadIdx.x < nl) {
+    const int l = threadIdx.x;
     const int64_t col = p.col_idx ? int64_t(__ldg(p.col_idx + l0 + l)) : p.col0 + l0 + l;
     const uint8_t* g = p.raw + col * p.raw_stride + (kPackedIn ? (p.row_lo >> 2) : p.row_lo);
-    const int mis = int(reinterpret_cast<uintptr_t>(g) & 15u);
-    if (threadIdx.x == 0) mis_s[l] = mis;
-    const uint8_t* ga = g - mis;
-    uint8_t* sdst = sm + size_t(l) * p.col_pitch;
-    for (int c = threadIdx.x; c < chunks; c += kGatherThreads) {
-      const uint8_t* src = ga + size_t(c) * 16;
-      if (src >= g + p.span_bytes) break;
-      uint4 v;
-      if (src >= p.raw && src + 16 <= p.raw_end) {
-        v = __ldg(reinterpret_cast<const uint4*>(src));
-      } else {  // first / last bytes of the allocation: byte-wise, never outside [raw, raw_end)
-        uint32_t w[4] = {0, 0, 0, 0};
-        for (int b = 0; b < 16; ++b)
-          if (src + b >= p.raw && src + b < p.raw_end) w[b >> 2] |= uint32_t(__ldg(src + b)) << (8 * (b & 3));
-        v = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-      *reinterpret_cast<uint4*>(sdst + size_t(c) * 16) = v;
+    col_s[l] = g;
+    mis_s[l] = int(reinterpret_cast<uintptr_t>(g) & 15u);
+  }
+  __syncthreads();
+  const int total = nl * chunks;
+  for (int f = threadIdx.x; f < total; f += kGatherThreads) {
+    const int l = f / chunks, c = f - l * chunks;
+    const uint8_t* g = col_s[l];
+    const uint8_t* src = g - mis_s[l] + size_t(c) * 16;
+    if (src >= g + p.span_bytes) continue;
+    uint8_t* dst = sm + size_t(l) * p.col_pitch + size_t(c) * 16;
+    if (src >= p.raw && src + 16 <= p.raw_end) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32_(dst)), "l"(src) : "memory");
+    } else {  // first / last bytes of the allocation: byte-wise, never outside [raw, raw_end)
+      uint32_t w[4] = {0, 0, 0, 0};
+      for (int b = 0; b < 16; ++b)
+        if (src + b >= p.raw && src + b < p.raw_end) w[b >> 2] |= uint32_t(__ldg(src + b)) << (8 * (b & 3));
+      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   // ---- gather: one 32-bit word (16 individuals) per thread and locus
   const int words = int(p.out_stride >> 2);

@@ -261,6 +261,40 @@ int launch_add_counts(Ctx* ctx, int32_t* a, const int32_t* b, int64_t elems, cud
   return TPG_OK;
 }
 
+// ------------------------------------------------------------------ zeroing the count matrices
+// A job's accumulators start at zero.  A plain memset of the whole buffer (16 n_pad^2 bytes: 40 GB at
+// n = 50,000) writes four full matrices; what the Gram epilogue and finish ever touch is less: only the
+// products of the job (prod_mask), only 256 x 256 blocks on or above the diagonal of the symmetric ones,
+// and — tile-sharded — only the blocks this rank owns (an eighth of them on 8 GPUs).  One CTA per
+// (matrix, block): 256 columns x 1 KiB.
+__global__ void __launch_bounds__(256)
+zero_counts_kernel(int32_t* counts, int64_t ld, int nblocks, int prod_mask, int rank, int world) {
+  const int mat = blockIdx.z;
+  if (!(prod_mask & (1 << mat))) return;
+  const int bi = blockIdx.y, bj = blockIdx.x;   // row block, column block
+  if (mat != TPG_MAT_HN && bi > bj) return;      // symmetric products live in the upper blocks
+  if (!block_owned(min(bi, bj), max(bi, bj), nblocks, rank, world)) return;
+  int4* base = reinterpret_cast<int4*>(counts + int64_t(mat) * ld * ld + int64_t(bj) * 256 * ld + int64_t(bi) * 256);
+  const int64_t ld4 = ld / 4;
+  const int4 z = make_int4(0, 0, 0, 0);
+  // 256 columns x 64 int4: thread t writes int4 (t & 63) of columns (t >> 6) + 4 k
+  const int q = threadIdx.x & 63, c0 = threadIdx.x >> 6;
+#pragma unroll 8
+  for (int c = c0; c < 256; c += 4) base[int64_t(c) * ld4 + q] = z;
+}
+
+int launch_zero_counts(Ctx* ctx, int32_t* counts, int64_t n, int prod_mask, int shard_rank, int shard_world,
+                       cudaStream_t st, const Err& E) {
+  const int64_t ld = (n + 255) / 256 * 256;
+  const int nb = int(ld / 256);
+  if (nb > 65535) return E.fail(TPG_ERR_ARG, "zero_counts: too many blocks");
+  zero_counts_kernel<<<dim3(nb, nb, TPG_NUM_COUNT_MATS), 256, 0, st>>>(counts, ld, nb, prod_mask, shard_rank,
+                                                                      shard_world > 1 ? shard_world : 1);
+  TPG_CUDA_OK(cudaGetLastError(), E);
+  ctx->launches++;
+  return TPG_OK;
+}
+
 // ------------------------------------------------------------------ synthetic genotypes
 __global__ void __launch_bounds__(256)
 synth_kernel(uint8_t* raw, int64_t nrow, int64_t ncol, int64_t col_offset, uint64_t seed,

@@ -199,6 +199,12 @@ int run_wg17(Ctx* ctx, const double* as_in, bool on_device, int64_t n, const int
 
 int check_err_flag(Ctx* ctx, const Err& E);
 int launch_add_counts(Ctx* ctx, int32_t* a, const int32_t* b, int64_t elems, cudaStream_t st, const Err& E);
+// Zeroes what a job will accumulate into: the matrices of prod_mask, upper 256-blocks of the symmetric ones,
+// owned blocks only when tile-sharded (finish.cu).
+int launch_zero_counts(Ctx* ctx, int32_t* counts, int64_t n, int prod_mask, int shard_rank, int shard_world,
+                       cudaStream_t st, const Err& E);
+
+int run_mma_peak(Ctx* ctx, int kind, double seconds, double* tops, double* ms_out, const Err& E);
 
 // ---- host helpers (split.cpp)
 int64_t block_size_default(int64_t n);

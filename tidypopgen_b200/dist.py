@@ -90,6 +90,32 @@ def choose_mode(n: int, world: int) -> str:
     return "loci" if world == 1 or n <= 30000 else "tiles"
 
 
+def needed_matrices(stat: int) -> list[int]:
+    """Count matrices a statistic reads (prod_mask_for in csrc/api.cu): KING DD, NN, HN; IBS DD, NN, HH;
+    allele sharing / GRM DD, NN."""
+    if stat == L.STAT_KING:
+        return [L.MAT_DD, L.MAT_NN, L.MAT_HN]
+    if stat in (L.STAT_IBS_RAW, L.STAT_IBS_PROPORTION, L.STAT_IBS_ADJUSTED):
+        return [L.MAT_DD, L.MAT_NN, L.MAT_HH]
+    return [L.MAT_DD, L.MAT_NN]
+
+
+def all_reduce_counts(counts: torch.Tensor, stat: int, n: int, group=None):
+    """The one exchange step of a loci-sharded job: integer SUM of the count matrices the statistic
+    needs — contiguous runs of them, so KING (DD, NN | HN) costs two collectives over 3/4 of the
+    buffer and allele sharing one over half of it, instead of one over all four matrices."""
+    ld = int(L.lib().tpg_counts_ld(n))
+    ms = ld * ld
+    mats = needed_matrices(stat)
+    k = 0
+    while k < len(mats):
+        j = k
+        while j + 1 < len(mats) and mats[j + 1] == mats[j] + 1:
+            j += 1
+        dist.all_reduce(counts[mats[k] * ms:(mats[j] + 1) * ms], op=dist.ReduceOp.SUM, group=group)
+        k = j + 1
+
+
 class CudaEngine:
     """The product engine: staged C-ABI calls on this rank's GPU."""
 
@@ -171,9 +197,9 @@ def pairwise_sharded(engine, X, ind_row=None, ind_col=None, stat: int = L.STAT_K
         # the one exchange step of the path: integer sum of the count matrices
         if stream is not None:
             with torch.cuda.stream(stream):
-                dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+                all_reduce_counts(counts, stat, n, group)
         else:
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+            all_reduce_counts(counts, stat, n, group)
         job.shard_mode = L.SHARD_NONE  # finish sees the whole job (m = all loci, pad constant once)
         job.shard_world = 1
         job.shard_rank = 0
