@@ -230,14 +230,15 @@ def measure_mma_peaks(L, local):
     out = {}
     eb = L.errbuf()
     for kind, name in ((1, "mxf4"), (0, "i8")):
-        for secs, tag in ((0.05, "burst"), (1.0, "sustained")):
+        for secs, tag, k in ((0.05, "burst", kind), (1.0, "sustained", kind), (0.05, "burst_zero_operands", kind + 2)):
             tops, ms = C.c_double(0), C.c_double(0)
-            rc = L.lib().tpg_mma_peak(local, kind, secs, C.byref(tops), C.byref(ms), eb, len(eb))
+            rc = L.lib().tpg_mma_peak(local, k, secs, C.byref(tops), C.byref(ms), eb, len(eb))
             out[f"{name}_{tag}_tops"] = tops.value if rc == 0 else None
             if rc != 0:
                 out[f"{name}_{tag}_error"] = eb.value.decode(errors="replace")
     out["how"] = ("tpg_mma_peak: tcgen05.mma.cta_group::2 M256 N256 (K32 int8 / K64 E2M1) issued back to back on all 74 CTA "
-                  "pairs, operands resident in shared memory; 2 ops per MAC")
+                  "pairs, pseudo-random -1/0/+1 operands resident in shared memory; 2 ops per MAC; burst = 0.05 s, sustained = 1 s "
+                  "(power-capped)")
     return out
 
 

@@ -297,6 +297,19 @@ int tpg_filter_high_relatedness(int device, const double* matrix, int32_t on_dev
 int tpg_king_filter(const tpg_job* job, double kings_threshold, int32_t* keep, int32_t* order,
                     int64_t* n_removed, double* king_host, tpg_stats* stats, char* err, size_t errlen);
 
+/* qc_report_indiv on a GROUPED gen_tibble (R/qc_report_indiv.R:110-181): the reference runs one
+ * pairwise_king and one filter_high_relatedness per group (:161, :169-180) — many small jobs.  Here the
+ * individuals are sorted by group inside the library, ONE KING job computes only the tiles that hold a
+ * same-group pair (the groups are the diagonal blocks), and each block is filtered where it is.
+ *   group     (n) 0-based group of each individual of ind_row (job order), ngroups groups
+ *   keep      (n, job order) 1 = passes its group's filter (the concatenated [[3]] of the reference)
+ *   n_removed (ngroups, or NULL)
+ *   king_host (sum of n_g^2 doubles, or NULL) the per-group KING matrices, group after group, each
+ *             column-major n_g x n_g in the job's within-group order (attr(to_keep, "king")) */
+int tpg_king_filter_groups(const tpg_job* job, const int32_t* group, int32_t ngroups, double kings_threshold,
+                           int32_t* keep, int64_t* n_removed, double* king_host, tpg_stats* stats, char* err,
+                           size_t errlen);
+
 /* Weir & Goudet (2017) statistics from an allele-sharing matrix:
  *   inbreeding (n, or NULL)       indiv_inbreeding — R/indiv_inbreeding.R:56-81
  *   fst  (npop + 1, or NULL)      pop_fst, last entry = global — R/pop_fst.R:31-76
@@ -408,8 +421,9 @@ int tpg_synth_fill(tpg_ctx* ctx, uint8_t* d_raw, int64_t nrow, int64_t ncol, int
  * kind 0: tcgen05.mma.cta_group::2.kind::i8 (M256 N256 K32), kind 1: kind::mxf4.block_scale (M256 N256 K64)
  * — with the operands resident in shared memory (no TMA / L2 traffic, no epilogue), on every CTA pair
  * of the chip at once, for about `seconds`.  *tops = 2 x MACs per second / 1e12: the measured roofline
- * the Gram kernels are read against (bench.py).  Short runs give the burst figure, runs of a second or
- * more the power-limited sustained one. */
+ * the Gram kernels are read against (bench.py).  The operands are pseudo-random -1 / 0 / +1 like the
+ * indicator planes (kind + 2: all zeros — same issue rate, far less power); short runs give the burst
+ * figure, runs of a second or more the power-limited sustained one. */
 int tpg_mma_peak(int device, int32_t kind, double seconds, double* tops, double* ms, char* err, size_t errlen);
 
 /* The 2-bit chunk format of the streamer ("pk2", csrc/pack.cpp): bytes per packed column for a

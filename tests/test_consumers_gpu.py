@@ -189,10 +189,14 @@ def test_scans_example(example_gt):
 @pytest.mark.parametrize("case", [(929, 3000, "all", "all"), (300, 2000, "shuffle", "shuffle"), (1500, 700, "window", "every3"),
                                   (64, 5000, "dup", "all"), (2500, 513, "subset", "subset")])
 @pytest.mark.parametrize("src_kind", ["file", "device", "pinned"])
-def test_scans_random_parity(case, src_kind):
+@pytest.mark.parametrize("table_kernel", [0, 1], ids=["table_free", "lut"])
+def test_scans_random_parity(case, src_kind, table_kernel, tpg_cfg):
+    """Every case on both scan kernels: the table-free build (standard code tables, contiguous rows and
+    loci — the other cases fall back by themselves) and the lookup-table one (tpg_config.scan_table)."""
     import torch
     from test_parity_gpu import pick
 
+    tpg_cfg(scan_table=table_kernel)
     n_tot, m_tot, rk, ck = case
     rng = np.random.default_rng(n_tot + m_tot)
     raw = rng.choice(np.array([0, 1, 2, 3, 4, 5, 6, 200], np.uint8), size=m_tot * n_tot, p=[.35, .25, .2, .08, .04, .03, .03, .02])
@@ -243,3 +247,35 @@ def test_qc_report_indiv_families(families):
     assert rel[0] == tpg.filter_high_relatedness(king, gt, kings_threshold=0.2)[0]
     assert "to_keep" not in tpg.qc_report_indiv(gt)
     assert tpg.qc_report_indiv(gt, kings_threshold="first")["to_keep"].sum() == 10
+
+
+@pytest.mark.parametrize("n,npop,contiguous", [(12, 3, True), (700, 9, False), (1500, 40, False), (900, 1, True)])
+def test_grouped_king_filter_equals_one_job_per_group(n, npop, contiguous):
+    """qc_report_indiv on a grouped gen_tibble (R/qc_report_indiv.R:110-181): one KING + one filter per group.
+    tpg_king_filter_groups does it in ONE block-diagonal job; every group's matrix and flags equal the
+    oracle's per-group computation, and to_keep is assembled in the reference's order."""
+    rng = np.random.default_rng(n + npop)
+    m = 1500
+    raw = rng.choice(np.array([0, 1, 2, 3], np.uint8), size=m * n, p=[.45, .3, .2, .05])
+    g = raw.reshape(m, n)
+    for a in range(0, n - 1, 7):                      # plant related pairs (near-duplicates) inside the data
+        g[:, a + 1] = np.where(rng.random(m) < 0.9, g[:, a], g[:, a + 1])
+    raw = g.reshape(-1)
+    pops = np.sort(rng.integers(0, npop, n)) if contiguous else rng.integers(0, npop, n)
+    labels = [f"pop{p:03d}" for p in pops]
+    gt = tpg.gen_tibble(fbm_of(raw, n, m), population=labels)
+    keep, mats, keys = tpg.king_filter_groups(gt, labels, 0.177, return_king=True)
+    assert keys == sorted(set(labels))
+    bs = O.block_size(n)
+    for lab in keys:
+        idx = np.flatnonzero(np.array(labels) == lab)
+        ref_king = O.snp_king(raw, n, m, (idx + 1).astype(np.int32), None, block_size_=bs)["king"]
+        assert same(mats[lab], ref_king), lab
+        ref_keep = O.filter_high_relatedness(ref_king, 0.177)["keep"] if len(idx) > 1 else np.array([True])
+        assert np.array_equal(keep[idx], ref_keep), lab
+    assert (~keep).sum() > 0 or npop >= 40
+    rep = tpg.qc_report_indiv(gt, kings_threshold="first", grouped=True)
+    first_seen = list(dict.fromkeys(labels))
+    assert np.array_equal(rep["to_keep"], np.concatenate([keep[np.array(labels) == lab] for lab in first_seen]))
+    if contiguous:
+        assert np.array_equal(rep["to_keep"], keep)

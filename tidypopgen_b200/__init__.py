@@ -23,6 +23,7 @@ from .consumers import (  # noqa: F401
     indiv_inbreeding,
     indiv_missingness,
     king_filter,
+    king_filter_groups,
     loci_alt_freq,
     loci_missingness,
     pop_fis,

@@ -154,6 +154,8 @@ SIGNATURES = {
                                               C.c_void_p, C.POINTER(C.c_int64)] + _ERR),
     "tpg_king_filter": (C.c_int, [C.POINTER(Job), C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p,
                                   C.POINTER(Stats)] + _ERR),
+    "tpg_king_filter_groups": (C.c_int, [C.POINTER(Job), C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(Stats)] + _ERR),
     "tpg_as_wg17": (C.c_int, [C.POINTER(Job), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.POINTER(Stats)] + _ERR),
     "tpg_wg17": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,

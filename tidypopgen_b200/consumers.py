@@ -77,6 +77,44 @@ def king_filter(x: GenTibble, kings_threshold, return_king: bool = False, block_
     return [passed, [nm for k, nm in enumerate(names) if not kept[k]], kept], king
 
 
+def king_filter_groups(x: GenTibble, group, kings_threshold, return_king: bool = False, block_size: int | None = None, **kw):
+    """One pairwise_king + filter_high_relatedness PER GROUP (R/qc_report_indiv.R:161,169-180) in one native
+    call (tpg_king_filter_groups): the library sorts the individuals by group, one KING job computes only the
+    tiles that hold a same-group pair, and every diagonal block is filtered in HBM.
+    group: one label per individual.  Returns (keep per individual [job order], {label: KING matrix} or None,
+    labels in dplyr's group_keys order)."""
+    from . import snp
+
+    labels = sorted(set(group))                       # dplyr::group_keys sorts the keys
+    code = {lab: k for k, lab in enumerate(labels)}
+    g = np.ascontiguousarray([code[v] for v in group], dtype=np.int32)
+    n = len(x)
+    if len(g) != n:
+        raise ValueError("group must have one entry per individual")
+    if block_size is None:
+        block_size = snp.block_size(len(x))
+    job, keepalive = snp.make_job(x.fbm, x.row_index, x.big_index, L.STAT_KING, block_size, **kw)
+    keep = np.zeros(n, np.int32)
+    removed = np.zeros(len(labels), np.int64)
+    sizes = np.bincount(g, minlength=len(labels))
+    king = np.zeros(int((sizes.astype(np.int64) ** 2).sum()), np.float64) if return_king else None
+    st = L.Stats()
+    eb = L.errbuf()
+    rc = L.lib().tpg_king_filter_groups(C.byref(job), g.ctypes.data, len(labels), float(kings_threshold), keep.ctypes.data,
+                                        removed.ctypes.data, None if king is None else king.ctypes.data, C.byref(st),
+                                        eb, len(eb))
+    del keepalive
+    L.check(rc, eb)
+    snp.last_stats = st.as_dict()
+    mats = None
+    if king is not None:
+        mats, off = {}, 0
+        for lab, ng in zip(labels, sizes):
+            mats[lab] = king[off:off + ng * ng].reshape(ng, ng).T.copy()   # column-major n_g x n_g
+            off += ng * ng
+    return keep.astype(bool), mats, labels
+
+
 def _wg17(as_mat, group, npop, want_inb=False, want_fst=False, want_fis=False, device: int = 0, x: GenTibble | None = None,
           block_size: int | None = None, **kw):
     """tpg_wg17 on a given allele-sharing matrix, or — as_mat None — tpg_as_wg17: the matrix is
@@ -226,11 +264,14 @@ def loci_missingness(x: GenTibble, as_counts: bool = False, **kw):
     return r["loc_na"] if as_counts else r["loc_na"] / len(x)
 
 
-def qc_report_indiv(x: GenTibble, kings_threshold=None, **kw):
-    """qc_report_indiv for an ungrouped diploid gen_tibble (R/qc_report_indiv.R:45-101):
+def qc_report_indiv(x: GenTibble, kings_threshold=None, grouped: bool = False, **kw):
+    """qc_report_indiv for a diploid gen_tibble (R/qc_report_indiv.R:45-101; grouped_df method :110-181):
     het_obs, missingness and — with kings_threshold (a number, "first" = 0.177 or "second" =
     0.088) — to_keep from filter_high_relatedness on the KING matrix, which is attached as
-    "king"."""
+    "king".  grouped=True is the method for a gen_tibble grouped by `population`: one KING and one
+    filter per group, and to_keep assembled exactly as the reference does — the groups' flags
+    concatenated in order of first appearance (:174-177), which lines up with the rows when the
+    individuals of a group are contiguous."""
     if kings_threshold is not None and not isinstance(kings_threshold, (int, float)):
         if kings_threshold not in ("first", "second"):
             raise ValueError("kings_threshold must be a numeric or one of 'first' or 'second'")
@@ -238,7 +279,18 @@ def qc_report_indiv(x: GenTibble, kings_threshold=None, **kw):
     n_loci = len(x.big_index)
     r = scan_counts(x.fbm, x.row_index, x.big_index, code256=_code(x), **kw)
     rep = {"het_obs": r["het_n"] / (n_loci - r["na_n"]), "missingness": r["na_n"] / n_loci}
-    if kings_threshold is not None:
+    if kings_threshold is not None and grouped:
+        if x.population is None:
+            raise ValueError(".x should be a grouped gen_tibble")
+        keep, mats, _ = king_filter_groups(x, list(x.population), kings_threshold, return_king=True, **kw)
+        pop = np.asarray(x.population, dtype=object)
+        first_seen = list(dict.fromkeys(x.population))                   # unique(qc_report$group)
+        rep["group"] = list(x.population)
+        rep["to_keep"] = np.concatenate([keep[pop == lab] for lab in first_seen])
+        rep["to_keep_by_individual"] = keep
+        rep["id"] = list(x.id)
+        rep["king"] = mats
+    elif kings_threshold is not None:
         # one native call: KING is computed, filtered in HBM and shipped once for attr(to_keep, "king")
         rel, king = king_filter(x, kings_threshold, return_king=True, **kw)
         rep["to_keep"] = rel[2]

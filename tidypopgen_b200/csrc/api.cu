@@ -368,7 +368,7 @@ static int collect_accumulate(Ctx* ctx, tpg_stats* st, const Err& E) {
 // for several statistics: tpg_pairwise_many, the count-matrix cache).
 static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_stats* st,
                            const Err& E, bool defer = false, const ScanArgs* scan = nullptr,
-                           int prod_mask_override = 0) {
+                           int prod_mask_override = 0, const int32_t* group_sorted = nullptr, uint64_t group_sig = 0) {
   const double t_begin = now_ms();
   const tpg_config C = cfg();
   Plan pl;
@@ -858,6 +858,8 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     ga.counts = d_counts;
     ga.ld = pl.n_pad;
     ga.max_chain_out = &max_chain;
+    ga.group_sorted = group_sorted;
+    ga.group_sig = group_sig;
     int64_t mm = 0;
     TPG_CUDA_OK(cudaEventRecord(tm[c].g0, ctx->s_compute), E);
     rc = launch_gram(ctx, ga, ctx->s_compute, &mm, E);
@@ -1291,7 +1293,7 @@ struct ResultMaps {
 };
 
 static int pairwise_many_on(Ctx* c, const tpg_job* job, const int32_t* stats, int nstats, tpg_result* results,
-                            const Err& E) {
+                            const Err& E, const int32_t* group_sorted = nullptr, uint64_t group_sig = 0) {
   if (job->shard_mode == TPG_SHARD_LOCI && job->shard_world > 1)
     return E.fail(TPG_ERR_ARG, "loci-sharded jobs need the staged interface (tpg_accumulate, "
                                "all-reduce of the counts, tpg_finish)");
@@ -1307,7 +1309,7 @@ static int pairwise_many_on(Ctx* c, const tpg_job* job, const int32_t* stats, in
   }
   TPG_CUDA_OK(cudaSetDevice(c->device), E);
   const size_t cbytes = sizeof(int32_t) * size_t(tpg_counts_elems(n));
-  const std::string key = counts_cache_key(job);
+  const std::string key = group_sorted ? std::string() : counts_cache_key(job);
   int rc = TPG_OK;
   if (!key.empty() && c->counts_key == key && c->counts_key_n == n && c->d_counts.p && c->d_counts.cap >= cbytes) {
     // same .bk (size, mtime), same ind.row / ind.col as the job that left its four count matrices
@@ -1326,7 +1328,7 @@ static int pairwise_many_on(Ctx* c, const tpg_job* job, const int32_t* stats, in
     if (rc) return rc;
     tpg_job jw = *job;
     jw.stat = stats[0];  // (tpg_pairwise_many ignores job->stat; the plan only needs a valid one)
-    rc = accumulate_impl(c, &jw, d_counts, &results[0].stats, E, /*defer=*/true, nullptr, mask);
+    rc = accumulate_impl(c, &jw, d_counts, &results[0].stats, E, /*defer=*/true, nullptr, mask, group_sorted, group_sig);
     if (rc == TPG_OK) rc = finish_many(c, job, stats, nstats, d_counts, results, E);
     if (c->pending) {  // finish bailed out early: still drain the device work
       tpg_stats scratch;
@@ -1554,6 +1556,86 @@ int tpg_king_filter(const tpg_job* job_in, double kings_threshold, int32_t* keep
   return rc;
 }
 
+int tpg_king_filter_groups(const tpg_job* job_in, const int32_t* group, int32_t ngroups, double kings_threshold,
+                           int32_t* keep, int64_t* n_removed, double* king_host, tpg_stats* stats, char* err,
+                           size_t errlen) {
+  Err E{err, errlen};
+  if (!job_in || !group || !keep || ngroups <= 0) return E.fail(TPG_ERR_ARG, "job / group / keep is NULL or no groups");
+  tpg_job job = *job_in;
+  job.stat = TPG_STAT_KING;
+  job.shard_mode = TPG_SHARD_NONE;
+  job.shard_world = 1;
+  job.shard_rank = 0;
+  const int64_t n = job.ind_row ? job.n : job.nrow_total;
+  if (n <= 0) return E.fail(TPG_ERR_ARG, "empty ind.row");
+  if (n > INT32_MAX) return E.fail(TPG_ERR_ARG, "too many individuals");
+  // individuals sorted by group (stable: the order within a group is the job's), so that every group is a
+  // diagonal block of ONE n x n KING job whose Gram kernels skip the tiles that hold no same-group pair
+  std::vector<int64_t> start(size_t(ngroups) + 1, 0);
+  for (int64_t k = 0; k < n; ++k) {
+    if (group[k] < 0 || group[k] >= ngroups)
+      return E.fail(TPG_ERR_ARG, "group[%lld] = %d is out of range [0, %d)", (long long)k, group[k], ngroups);
+    start[size_t(group[k]) + 1]++;
+  }
+  for (int32_t g = 0; g < ngroups; ++g) start[g + 1] += start[g];
+  std::vector<int32_t> perm(n), rows(n), gsorted(n);
+  {
+    std::vector<int64_t> fill(start.begin(), start.end() - 1);
+    for (int64_t k = 0; k < n; ++k) perm[size_t(fill[group[k]]++)] = int32_t(k);
+  }
+  for (int64_t s = 0; s < n; ++s) {
+    rows[s] = job.ind_row ? job.ind_row[perm[s]] : perm[s] + 1;
+    gsorted[s] = group[perm[s]];
+  }
+  job.ind_row = rows.data();
+  job.n = n;
+  int rc = TPG_OK;
+  Ctx* c = cached_ctx(job.device, E, &rc);
+  if (!c) return rc;
+  TPG_CUDA_OK(cudaSetDevice(c->device), E);
+  const size_t bytes = sizeof(double) * size_t(n) * size_t(n);
+  rc = ensure_slot(&c->d_out[0], bytes, false, "KING matrix", E);
+  if (rc) return rc;
+  tpg_result res;
+  memset(&res, 0, sizeof res);
+  res.out0 = static_cast<double*>(c->d_out[0].p);
+  res.out_on_device = 1;
+  uint64_t sig = 1469598103934665603ull;
+  for (int32_t g = 0; g <= ngroups; ++g) { sig ^= uint64_t(start[g]); sig *= 1099511628211ull; }
+  rc = pairwise_many_on(c, &job, &job.stat, 1, &res, E, gsorted.data(), sig);   // KING stays in HBM
+  if (rc) return rc;
+  const double t0 = now_ms();
+  std::vector<int32_t> keep_g;
+  int64_t king_off = 0;
+  for (int32_t g = 0; g < ngroups && rc == TPG_OK; ++g) {
+    const int64_t s = start[g], ng = start[g + 1] - start[g];
+    if (n_removed) n_removed[g] = 0;
+    if (ng <= 0) continue;
+    // the group's diagonal block as a dense ng x ng matrix
+    const size_t gbytes = sizeof(double) * size_t(ng) * size_t(ng);
+    rc = ensure_slot(&c->d_out[1], gbytes, false, "group KING matrix", E);
+    if (rc) break;
+    double* dense = static_cast<double*>(c->d_out[1].p);
+    TPG_CUDA_OK(cudaMemcpy2DAsync(dense, sizeof(double) * size_t(ng), res.out0 + s + s * n, sizeof(double) * size_t(n),
+                                  sizeof(double) * size_t(ng), size_t(ng), cudaMemcpyDeviceToDevice, c->s_compute), E);
+    keep_g.assign(size_t(ng), 1);
+    int64_t removed = 0;
+    rc = run_filter_high_relatedness(c, dense, true, ng, kings_threshold, keep_g.data(), nullptr, &removed, E);
+    if (rc) break;
+    for (int64_t k = 0; k < ng; ++k) keep[perm[size_t(s + k)]] = keep_g[size_t(k)];
+    if (n_removed) n_removed[g] = removed;
+    if (king_host) {
+      TPG_CUDA_OK(cudaMemcpyAsync(king_host + king_off, dense, gbytes, cudaMemcpyDeviceToHost, c->s_compute), E);
+      TPG_CUDA_OK(cudaStreamSynchronize(c->s_compute), E);
+      res.stats.bytes_d2h += int64_t(gbytes);
+      king_off += ng * ng;
+    }
+  }
+  res.stats.ms_finish += now_ms() - t0;  // the filters are accounted with the finishing stage
+  if (stats) *stats = res.stats;
+  return rc;
+}
+
 int tpg_as_wg17(const tpg_job* job_in, const int32_t* group, int64_t npop, double* inbreeding, double* fst,
                 double* fis, double* mb_out, double* as_host, tpg_stats* stats, char* err, size_t errlen) {
   Err E{err, errlen};
@@ -1651,6 +1733,17 @@ int tpg_scan(const tpg_job* job_in, const double* code256, const double* ploidy,
   TPG_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(int32_t) * (2 * size_t(n) + 3 * size_t(m)), c->s_compute), E);
   c->launches++;
   ScanArgs sa;
+  {
+    // the two tables tidypopgen uses (bigsnpr CODE_012 / CODE_IMPUTE_PRED) decode without a lookup
+    bool t012 = true, timp = true;
+    for (int b = 0; b < 256; ++b) {
+      const uint8_t e012 = b <= 2 ? uint8_t(b) : 0xFF;
+      const uint8_t eimp = b <= 2 ? uint8_t(b) : (b >= 4 && b <= 6) ? uint8_t(b - 4) : 0xFF;
+      t012 &= lut[b] == e012;
+      timp &= lut[b] == eimp;
+    }
+    sa.std_table = t012 ? 1 : timp ? 2 : 0;
+  }
   sa.lut = base; sa.weight = base + 256; sa.ploidy = base + 256 + n;
   sa.het_n = acc; sa.na_n = acc + n; sa.alt2 = acc + 2 * n; sa.valid = sa.alt2 + m; sa.na_l = sa.valid + m;
   rc = accumulate_impl(c, &job, nullptr, st, E, /*defer=*/false, &sa);

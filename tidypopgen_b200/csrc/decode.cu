@@ -995,6 +995,119 @@ scan_counts_kernel(const DecodeParams p, const ScanParams sp) {
     }
 }
 
+// Table-free build for the two standard code tables (bigsnpr CODE_012: 0 / 1 / 2, everything else NA;
+// CODE_IMPUTE_PRED: 4 / 5 / 6 decode to 0 / 1 / 2 as well).  The per-byte shared-memory lookups and the
+// shuffle-assembled loads kept scan_counts_kernel at 0.18 of the HBM figure (instruction bound); here
+//   * the table is arithmetic: clamp4 (swar.cuh) maps every byte above 2 to code 3, and for the imputed
+//     table clamp4(g) & clamp4(g ^ 0x04040404) folds 4 / 5 / 6 onto 0 / 1 / 2;
+//   * a lane loads both aligned words of its four genotypes itself (the second one is an L1 hit), as
+//     decode_planes_k4_kernel does: no shuffle, no select;
+//   * the 16 per-locus sums of a round are 16 REDUX.SUM (one instruction per locus and warp) instead of a
+//     16-shuffle butterfly with its selects.
+// Contiguous rows and loci only (launch_scan routes everything else to scan_counts_kernel); same outputs,
+// bit for bit.
+template <bool kImpute>
+__global__ void __launch_bounds__(kDecThreads)
+scan_counts_fast_kernel(const DecodeParams p, const ScanParams sp) {
+  __shared__ uint32_t part[kDecThreads / 32][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nib = (p.n + kDecThreads * 4 - 1) / (kDecThreads * 4);
+  const int ib = blockIdx.x % nib, lb = blockIdx.x / nib;
+  const int i0 = (ib * kDecThreads + threadIdx.x) * 4;
+  const int nv = min(max(p.n - i0, 0), 4);
+  const uint32_t keep = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
+  const int n_here = min(kDecThreads * 4, p.n - ib * kDecThreads * 4);
+  uint32_t w4 = 0, dip4 = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+    if (b < nv) {
+      w4 |= uint32_t(sp.weight[i0 + b]) << (8 * b);
+      dip4 |= (sp.ploidy[i0 + b] == 2 ? 1u : 0u) << (8 * b);
+    }
+  int het[4] = {0, 0, 0, 0}, na[4] = {0, 0, 0, 0};
+  const int lbase = lb * sp.loci_per_cta;
+  const uint32_t stride = uint32_t(p.raw_stride);
+  for (int round = 0; round < sp.loci_per_cta / 16; ++round) {
+    const int l0 = lbase + round * 16;
+    if (l0 >= p.lc) break;  // uniform over the CTA
+    uint32_t g[16];
+    // every word this CTA touches in the round lies inside the buffer (3 bytes of slack below, 8 above)?
+    const int64_t lo = (p.col0 + l0) * p.raw_stride + p.row0 + int64_t(ib) * kDecThreads * 4 - 3;
+    const int64_t hi = (p.col0 + l0 + 15) * p.raw_stride + p.row0 + int64_t(ib + 1) * kDecThreads * 4 + 8;
+    const bool full_round = l0 + 16 <= p.lc;
+    if (full_round && lo >= 0 && hi <= int64_t(p.raw_end - p.raw)) {
+      const uint64_t a0 = uint64_t(reinterpret_cast<uintptr_t>(p.raw + (p.col0 + l0) * p.raw_stride + p.row0 + i0));
+      uint32_t w1[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        uint64_t au;
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(au) : "r"(stride), "r"(uint32_t(u)), "l"(a0));
+        const uint32_t* al = reinterpret_cast<const uint32_t*>(uintptr_t(au & ~uint64_t(3)));
+        g[u] = __ldg(al);
+        w1[u] = __ldg(al + 1);
+      }
+      const uint32_t a8 = uint32_t(a0) << 3, s8 = stride << 3;  // the funnel shift takes its amount mod 32
+#pragma unroll
+      for (int u = 0; u < 16; ++u) g[u] = __funnelshift_r(g[u], w1[u], a8 + uint32_t(u) * s8) | ~keep;
+    } else {
+      RowSel rs;
+      rs.gather = false;
+      rs.keep = keep;
+      rs.off = p.row0 + i0;
+      rs.ld = i0 < p.n + 4;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        g[u] = 0xFFFFFFFFu;
+        if (l0 + u < p.lc) g[u] = load4<false>(p, rs, p.col0 + l0 + u, lane) | ~keep;
+      }
+    }
+    // codes: 0 / 1 / 2 = dosage, 3 = missing (padding individuals and loci were forced to 0xFF above).
+    uint32_t mine = 0;           // lane u keeps the warp total of locus u
+    uint32_t het4 = 0, na4 = 0;  // byte counters, at most 16 per round
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      uint32_t c = clamp4(g[u]);
+      if (kImpute) c &= clamp4(g[u] ^ 0x04040404u);
+      const uint32_t hi1 = (c >> 1) & 0x01010101u;           // bit 1 of each code
+      const uint32_t na01 = hi1 & c;                          // 3
+      const uint32_t het01 = (hi1 ^ 0x01010101u) & c & 0x01010101u;  // 1
+      const uint32_t typed01 = na01 ^ 0x01010101u;
+      const uint32_t dos = c ^ (na01 * 3u);                   // missing -> 0
+      // alt [0,15) | typed [15,23) | typed diploids [23,31): warp totals (<= 32512, 128, 128) cannot carry
+      const uint32_t v = __dp4a(dos, w4, 0u) | (__dp4a(typed01, 0x01010101u, 0u) << 15) | (__dp4a(typed01, dip4, 0u) << 23);
+      const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, v);
+      if (lane == u) mine = tot;
+      het4 += het01;
+      na4 += na01 & ((full_round || l0 + u < p.lc) ? (keep & 0x01010101u) : 0u);  // padding loci / individuals are not NAs
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { het[b] += (het4 >> (8 * b)) & 0xFFu; na[b] += (na4 >> (8 * b)) & 0xFFu; }
+    if (lane < 16) part[warp][lane] = mine;
+    __syncthreads();
+    if (threadIdx.x < 16 && l0 + int(threadIdx.x) < p.lc) {
+      uint32_t alt = 0, typed = 0, td = 0;
+#pragma unroll
+      for (int w = 0; w < kDecThreads / 32; ++w) {
+        const uint32_t x = part[w][threadIdx.x];
+        alt += x & 0x7FFFu; typed += (x >> 15) & 0xFFu; td += x >> 23;
+      }
+      const int l = l0 + threadIdx.x;
+      const int32_t val = int32_t(typed + td);  // sum of ploidy over the typed: 1 each + 1 more per diploid
+      const int32_t nal = n_here - int32_t(typed);
+      if (nib == 1) { sp.alt2[l] += int32_t(alt); sp.valid[l] += val; sp.na_l[l] += nal; }
+      else { atomicAdd(sp.alt2 + l, int32_t(alt)); atomicAdd(sp.valid + l, val); atomicAdd(sp.na_l + l, nal); }
+    }
+    __syncthreads();
+  }
+  if (!(sp.flags & 1))
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (b < nv) {
+        if (het[b]) atomicAdd(sp.het_n + i0 + b, het[b]);
+        if (na[b]) atomicAdd(sp.na_n + i0 + b, na[b]);
+      }
+}
+
 int launch_scan(Ctx* ctx, const DecodeArgs& a, const ScanArgs& s, cudaStream_t st, const Err& E) {
   if (a.n <= 0 || a.lc <= 0 || a.n > INT32_MAX / 2 || a.lc > INT32_MAX / 2)
     return E.fail(TPG_ERR_ARG, "scan: bad geometry n=%lld lc=%lld", (long long)a.n, (long long)a.lc);
@@ -1022,7 +1135,13 @@ int launch_scan(Ctx* ctx, const DecodeArgs& a, const ScanArgs& s, cudaStream_t s
   sp.flags = C.scan_no_indiv ? 1 : 0;
   const int64_t blocks = ((a.n + kDecThreads * 4 - 1) / (kDecThreads * 4)) * ((a.lc + sp.loci_per_cta - 1) / sp.loci_per_cta);
   if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "scan: chunk too large for one launch");
-  scan_counts_kernel<<<unsigned(blocks), kDecThreads, 0, st>>>(p, sp);
+  // the table-free build: a standard code table, contiguous rows and loci, a stride the 32-bit address
+  // arithmetic of the fast loads can take
+  const bool fast = s.std_table != 0 && !C.scan_table && !a.row_idx && !a.col_idx && !a.packed &&
+                    a.raw_stride < (int64_t(1) << 27);
+  if (fast && s.std_table == 2) scan_counts_fast_kernel<true><<<unsigned(blocks), kDecThreads, 0, st>>>(p, sp);
+  else if (fast) scan_counts_fast_kernel<false><<<unsigned(blocks), kDecThreads, 0, st>>>(p, sp);
+  else scan_counts_kernel<<<unsigned(blocks), kDecThreads, 0, st>>>(p, sp);
   TPG_CUDA_OK(cudaGetLastError(), E);
   ctx->launches++;
   return TPG_OK;

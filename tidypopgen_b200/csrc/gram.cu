@@ -614,6 +614,17 @@ static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms) {
   return std::max(best, std::min(ks_l2, max_ks));
 }
 
+// Block-diagonal jobs: does the tile rows [r0, r1) x columns [c0, c1) hold a pair of individuals of the same
+// group?  Group ids are non-decreasing along the (sorted) individuals, so it is an interval overlap.
+static bool tile_wanted(const GramArgs& a, int64_t r0, int64_t r1, int64_t c0, int64_t c1) {
+  if (!a.group_sorted) return true;
+  const int64_t last = a.n - 1;
+  if (r0 > last || c0 > last) return false;
+  const int32_t gr0 = a.group_sorted[r0], gr1 = a.group_sorted[std::min(r1 - 1, last)];
+  const int32_t gc0 = a.group_sorted[c0], gc1 = a.group_sorted[std::min(c1 - 1, last)];
+  return gr0 <= gc1 && gc0 <= gr1;
+}
+
 // Host side of the 4-bit variant: 256 x 240 tiles over K-major 4-bit planes, k-blocks of 256 loci.
 static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out, const Err& E) {
   if (a.n_pad % kRowPad || a.lc_pad % kQStageLoci || a.lc_pad <= 0)
@@ -665,6 +676,7 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
           if (kPairTileM * ti >= a.n) continue;  // rows of padding individuals only
           const int c0 = cols[cj].first, nc = cols[cj].second;
           const bool upper = c0 + nc - 1 >= kPairTileM * ti;
+          if (!tile_wanted(a, kPairTileM * ti, kPairTileM * (ti + 1), c0, c0 + nc)) continue;
           const int64_t bi = ti, bj = c0 / 256;  // 256-blocks; ownership is per 1024 region, so any block of the tile will do
           for (int prod = 0; prod < TPG_NUM_COUNT_MATS; ++prod) {
             if (!(a.prod_mask & (1 << prod))) continue;
@@ -692,8 +704,8 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
     *macs_out = cells * a.lc_pad;
   }
   char key[200];
-  snprintf(key, sizeof key, "q4/%lld/%lld/%lld/%d/%d/%d/%d", (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad, a.prod_mask, ks,
-           a.shard_rank, a.shard_world);
+  snprintf(key, sizeof key, "q4/%lld/%lld/%lld/%d/%d/%d/%d/%llx", (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad, a.prod_mask, ks,
+           a.shard_rank, a.shard_world, (unsigned long long)(a.group_sorted ? a.group_sig | 1u : 0u));
   if (ctx->items_key != key) {
     std::vector<WorkItem>& items = ctx->h_items;
     items.clear();
@@ -797,6 +809,7 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
       for (int64_t tj = rj; tj < std::min(rj + RJ, tiles_n); ++tj)
         for (int64_t ti = ri; ti < std::min(ri + RI, tiles_m); ++ti) {
           const bool upper = kTileN * tj + (kTileN - 1) >= tile_m * ti;
+          if (!tile_wanted(a, tile_m * ti, tile_m * (ti + 1), kTileN * tj, kTileN * (tj + 1))) continue;
           // 256x256 ownership block of the tile; lower blocks mirror
           const int64_t bi = ti * tile_m / 256, bj = tj;
           for (int prod = 0; prod < TPG_NUM_COUNT_MATS; ++prod) {
@@ -825,8 +838,9 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
     *macs_out = cells * a.lc_pad;
   }
   char key[200];
-  snprintf(key, sizeof key, "%lld/%lld/%lld/%d/%d/%d/%d/%d/%d", (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad,
-           a.prod_mask, a.shard_rank, a.shard_world, ks, tile_m, int(trim_n));
+  snprintf(key, sizeof key, "%lld/%lld/%lld/%d/%d/%d/%d/%d/%d/%llx", (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad,
+           a.prod_mask, a.shard_rank, a.shard_world, ks, tile_m, int(trim_n),
+           (unsigned long long)(a.group_sorted ? a.group_sig | 1u : 0u));
   if (ctx->items_key != key) {
     std::vector<WorkItem>& items = ctx->h_items;
     items.clear();

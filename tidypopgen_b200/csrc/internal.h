@@ -120,6 +120,7 @@ struct ScanArgs {
   int32_t* alt2;
   int32_t* valid;
   int32_t* na_l;
+  int std_table = 0;  // 1 = the table is bigsnpr CODE_012, 2 = CODE_IMPUTE_PRED (table-free kernel), 0 = anything else
 };
 int launch_scan(Ctx* ctx, const DecodeArgs& a, const ScanArgs& s, cudaStream_t st, const Err& E);
 
@@ -137,6 +138,10 @@ struct GramArgs {
   int32_t* counts;
   int64_t ld;
   int64_t* max_chain_out = nullptr;  // 4-bit route: longest accumulation chain (loci) of the launch
+  // Block-diagonal jobs (one KING per group, individuals sorted by group): host array of n non-decreasing
+  // group ids; only tiles that hold at least one same-group pair are computed.  nullptr = every tile.
+  const int32_t* group_sorted = nullptr;
+  uint64_t group_sig = 0;            // identifies the grouping in the cached work list's key
 };
 int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out, const Err& E);
 

@@ -19,15 +19,29 @@ constexpr int kPeakSmem = 2 * kPeakHalf + 1024 + 64;      // A half + B half per
 
 template <bool kMxf4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPeakThreads, 1)
-mma_peak_kernel(int groups, int* err_flag) {
+mma_peak_kernel(int groups, int random_operands, int* err_flag) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * kPeakHalf);  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
   const int warp = threadIdx.x >> 5;
   const uint32_t rank = cluster_ctarank();
-  // operands: zeros (a valid int8 / E2M1 tile; the tensor pipe does not care about the values)
-  for (int e = threadIdx.x; e < 2 * kPeakHalf / 16; e += kPeakThreads) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
+  // operands: pseudo-random -1 / 0 / +1 like the indicator planes (E2M1 nibbles 0xA / 0x0 / 0x2, int8 bytes
+  // 0xFF / 0x00 / 0x01), or all zeros.  The values do not change the issue rate, but they do change the power
+  // the tensor cores draw: a run of a second on zeros stays at the maximum clock, real data meets the power cap.
+  for (int e = threadIdx.x; e < 2 * kPeakHalf / 4; e += kPeakThreads) {
+    uint32_t w = 0;
+    if (random_operands) {
+      uint32_t h = (uint32_t(e) * 2654435761u) ^ (blockIdx.x * 0x9E3779B9u);
+      for (int b = 0; b < (kMxf4 ? 8 : 4); ++b) {
+        h = h * 1664525u + 1013904223u;
+        const uint32_t t = (h >> 24) % 3u;  // 0, 1, 2 -> 0, +1, -1
+        if (kMxf4) w |= (t == 0 ? 0x0u : t == 1 ? 0x2u : 0xAu) << (4 * b);
+        else w |= (t == 0 ? 0x00u : t == 1 ? 0x01u : 0xFFu) << (8 * b);
+      }
+    }
+    reinterpret_cast<uint32_t*>(smem)[e] = w;
+  }
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -85,18 +99,19 @@ mma_peak_kernel(int groups, int* err_flag) {
 }
 
 // Runs the probe for about `seconds` (one calibration launch first); *tops = 2 * MACs / s / 1e12.
-int run_mma_peak(Ctx* ctx, int kind, double seconds, double* tops, double* ms_out, const Err& E) {
-  if (kind != 0 && kind != 1) return E.fail(TPG_ERR_ARG, "mma_peak: kind must be 0 (int8) or 1 (4-bit mxf4)");
+int run_mma_peak(Ctx* ctx, int kind_in, double seconds, double* tops, double* ms_out, const Err& E) {
+  const int kind = kind_in & 1, random_ops = (kind_in & 2) ? 0 : 1;   // bit 1: all-zero operands
+  if (kind_in < 0 || kind_in > 3) return E.fail(TPG_ERR_ARG, "mma_peak: kind must be 0 (int8) or 1 (4-bit mxf4), + 2 for zero operands");
   if (!(seconds > 0) || seconds > 5.0) return E.fail(TPG_ERR_ARG, "mma_peak: seconds must be in (0, 5]");
   const int pairs = ctx->num_sms / 2;
   cudaStream_t st = ctx->s_compute;
   auto launch = [&](int groups) -> cudaError_t {
     if (kind == 1) {
       cudaFuncSetAttribute(mma_peak_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPeakSmem);
-      mma_peak_kernel<true><<<2 * pairs, kPeakThreads, kPeakSmem, st>>>(groups, ctx->d_err_flag);
+      mma_peak_kernel<true><<<2 * pairs, kPeakThreads, kPeakSmem, st>>>(groups, random_ops, ctx->d_err_flag);
     } else {
       cudaFuncSetAttribute(mma_peak_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPeakSmem);
-      mma_peak_kernel<false><<<2 * pairs, kPeakThreads, kPeakSmem, st>>>(groups, ctx->d_err_flag);
+      mma_peak_kernel<false><<<2 * pairs, kPeakThreads, kPeakSmem, st>>>(groups, random_ops, ctx->d_err_flag);
     }
     return cudaGetLastError();
   };
