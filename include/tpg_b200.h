@@ -193,6 +193,8 @@ typedef struct tpg_config {
   int32_t gram_max_kblocks;   /* TPG_GRAM_MAXKB: k-blocks per work item in the many-tiles regime, 0 = 128 */
   int32_t gram_clusters;      /* TPG_GRAM_CLUSTERS: CTA pairs to launch, 0 = all resident */
   int32_t gram_no_trim;       /* TPG_GRAM_NO_TRIM: 1 = do not trim the last tile column to the valid individuals */
+  int32_t gram_wide;          /* TPG_GRAM_WIDE: 4-bit route, 256 x 480 tiles (one A stream feeds two B tiles: a quarter  *
+                               * less L2 traffic per MAC). 0 = where tiles are plentiful (default), 1 = never, 2 = always */
   int32_t pack_mode;          /* TPG_PACK_MODE: 0 = hybrid (pack or raw DMA per chunk), 1 = never pack (TPG_NO_PACK), *
                                * 2 = always pack (TPG_NO_HYBRID) */
   int32_t pk2_i8;             /* TPG_PK2_I8: 1 = packed chunks take the int8 kernels */

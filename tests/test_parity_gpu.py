@@ -492,9 +492,12 @@ def test_decode_planes_k4_kernel(gather, nrow, build, tpg_cfg):
 
 
 @pytest.mark.parametrize("shape", [(256, 256), (512, 1280), (1024, 4096), (2560, 2048)])
-def test_gram_mxf4_kernel(shape):
-    """kind::mxf4 Gram kernel on K-major 4-bit planes: integer counts, exact."""
+@pytest.mark.parametrize("wide", [1, 2], ids=["pingpong_256x240", "wide_256x480"])
+def test_gram_mxf4_kernel(shape, wide, tpg_cfg):
+    """kind::mxf4 Gram kernels on K-major 4-bit planes (the ping-pong 256 x 240 kernel and the wide 256 x 480
+    one): integer counts, exact."""
     import torch
+    tpg_cfg(gram_wide=wide)
     n_pad, lc_pad = shape
     ctx = L.Context(0)
     rng = np.random.default_rng(2)

@@ -267,3 +267,26 @@ def test_grm_mb_is_the_double_double_mean():
     from tidypopgen_b200 import consumers
     _, _, _, mbs = consumers._wg17(a, None, 1, want_inb=True)
     assert mbs[0] == mb
+
+
+@pytest.mark.parametrize("n_tot,rk", [(389, "all"), (929, "shuffle"), (1300, "subset")])
+def test_wide_gram_kernel_whole_jobs(n_tot, rk, tpg_cfg):
+    """gram_mxf4_wide_kernel forced on small matrices (ragged last tiles: 240 + 149, 480 + 449, ...): every
+    statistic equals the oracle, for one chunk and several, with and without a row gather."""
+    rng = np.random.default_rng(n_tot)
+    m_tot = 2100
+    raw = random_bk(rng, n_tot, m_tot, 0.08, codes=(0, 1, 2, 3, 4, 5, 6, 255))
+    X = fbm_of(raw, n_tot, m_tot)
+    rows = pick(rk, n_tot, rng)
+    tpg_cfg(gram_wide=2)
+    ref_k = O.snp_king(raw, n_tot, m_tot, rows, None)
+    for chunk in (0, 512):
+        king, K, N = tpg.snp_king_counts(X, rows, None, gpu_chunk_loci=chunk)
+        assert tpg.snp.last_stats["n_mxf4_chunks"] >= 1
+        assert np.array_equal(K, ref_k["K"]) and np.array_equal(N, ref_k["N_Aa_i"]) and same(king, ref_k["king"])
+    ref_i = O.snp_ibs(raw, n_tot, m_tot, rows, None, type="raw_counts")
+    got = tpg.snp_ibs(X, rows, None, type="raw_counts")
+    assert np.array_equal(got["ibs"][:], ref_i["ibs"]) and np.array_equal(got["valid_n"][:], ref_i["valid_n"])
+    ref_a = O.snp_allele_sharing(raw, n_tot, m_tot, rows, None, block_size_=500)
+    a, num, den = tpg.snp_allele_sharing_counts(X, rows, None, block_size=500)
+    assert np.array_equal(num, ref_a["num"]) and np.array_equal(den, ref_a["denom"]) and same(a, ref_a["as"])

@@ -113,6 +113,7 @@ class Config(C.Structure):
         ("gram_max_kblocks", C.c_int32),
         ("gram_clusters", C.c_int32),
         ("gram_no_trim", C.c_int32),
+        ("gram_wide", C.c_int32),
         ("pack_mode", C.c_int32),
         ("pk2_i8", C.c_int32),
         ("no_compact", C.c_int32),

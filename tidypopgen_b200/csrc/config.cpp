@@ -45,6 +45,7 @@ void tpg_config_init(tpg_config* c) {
   c->gram_max_kblocks = env_int("TPG_GRAM_MAXKB", 0);
   c->gram_clusters = env_int("TPG_GRAM_CLUSTERS", 0);
   c->gram_no_trim = env_set("TPG_GRAM_NO_TRIM") ? 1 : 0;
+  c->gram_wide = env_int("TPG_GRAM_WIDE", 0);
   c->pack_mode = env_int("TPG_PACK_MODE", 0);
   if (env_set("TPG_NO_PACK")) c->pack_mode = 1;
   else if (env_set("TPG_NO_HYBRID")) c->pack_mode = 2;
@@ -75,6 +76,7 @@ int tpg_config_set(const tpg_config* c, char* err, size_t errlen) {
   if (c->gram_route < 0 || c->gram_route > 1) return fail("gram_route must be 0 (4-bit where exact) or 1 (int8)");
   if (c->gram_ctas < 0 || c->gram_ctas > 2) return fail("gram_ctas must be 0, 1 or 2");
   if (c->gram_ksplit < 0 || c->gram_max_kblocks < 0 || c->gram_clusters < 0) return fail("gram_* must be >= 0");
+  if (c->gram_wide < 0 || c->gram_wide > 2) return fail("gram_wide must be 0 (auto), 1 (never) or 2 (always)");
   if (c->pack_mode < 0 || c->pack_mode > 2) return fail("pack_mode must be 0 (hybrid), 1 (never) or 2 (always)");
   if (c->io_mode < 0 || c->io_mode > 2) return fail("io_mode must be 0 (page cache), 1 (O_DIRECT) or 2 (mmap)");
   if (c->host_threads < 0 || c->host_threads > 1024) return fail("host_threads out of range");

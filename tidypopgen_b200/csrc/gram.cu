@@ -565,6 +565,191 @@ gram_mxf4_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------ 4-bit variant, wide tiles
+// gram_mxf4_pair_kernel is bound by the L2 -> shared-memory operand stream, not by the tensor pipe: a CTA
+// stages 32 KiB per 256 loci for 128 x 240 x 256 MACs, 10 - 12 TB/s over the whole chip — the measured
+// ceiling of the L2 slices (ncu: lts throughput at its cap, tensor pipe 75 % active).
+// Fewer operand bytes per MAC is the only lever, and the bytes per MAC of an output-stationary tile are
+// 1/M + 1/N.  This kernel doubles N: a work item is a 256 x 480 tile — BOTH 240-column accumulators of the
+// CTA pair's TMEM belong to it — so one A stage (16 KiB per CTA) feeds two B stages: 48 KiB per 256 loci
+// for twice the MACs, a quarter less L2 traffic per MAC.  The price is the epilogue, which no longer
+// overlaps the next item's MMAs (there is no third accumulator to ping-pong with); with 128 k-blocks per
+// item it is a few per cent, so the host uses this kernel where tiles are plentiful (launch_gram_mxf4) and
+// the ping-pong kernel for small matrices.  Everything else — CTA pairs, barriers, scale-factor columns
+// [240, 256), the int32 atomics, the chain-length guard — is as in gram_mxf4_pair_kernel.
+constexpr int kWideStages = 4;
+constexpr int kWideStageBytes = 3 * kHalfBytes;       // per CTA: A half + two B halves
+constexpr int kWideSmemBytes = kWideStages * kWideStageBytes + 1024 + 256;
+
+// work item: prod [0,4) | (n0 / 16 - 1) [4,8) | (n1 / 16) [8,12) | ti [12,32); tj = first column;
+// half 0 = columns [tj, tj + n0), half 1 = columns [tj + 240, tj + 240 + n1) (n1 = 0: absent)
+template <int kDummy>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGramThreads, 1)
+gram_mxf4_wide_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_nm,
+                      const __grid_constant__ CUtensorMap tm_h1, const GramParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWideStages * kWideStageBytes);
+  uint64_t* full_bar = bars;                          // [kWideStages] used in the leader only
+  uint64_t* empty_bar = bars + kWideStages;           // [kWideStages] in each CTA
+  uint64_t* tfull_bar = bars + 2 * kWideStages;       // [1] in each CTA
+  uint64_t* tempty_bar = bars + 2 * kWideStages + 1;  // [1] used in the leader only (8 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWideStages + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_d);
+    tma_prefetch_desc(&tm_nm);
+    tma_prefetch_desc(&tm_h1);
+    for (int s = 0; s < kWideStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 2) {  // scale factors: UE8M0 1.0 (0x7F) in columns [224, 256) of this warp's lanes;
+                    // [224, 240) belongs to accumulator 0 and is overwritten by its first MMA
+    tmem_fill_32x32(tmem_base + (uint32_t((warp & 3) * 32) << 16) + 224u, 0x7F7F7F7Fu);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = cluster; it < p.n_items; it += n_clusters) {
+        const WorkItem w = p.items[it];
+        const int prod = w.prod_ti & 15, ti = int(uint32_t(w.prod_ti) >> 12);
+        const int n0 = (((w.prod_ti >> 4) & 15) + 1) * 16, n1 = ((w.prod_ti >> 8) & 15) * 16;
+        int pa, pb;
+        prod_planes(prod, pa, pb);
+        const CUtensorMap* ma = pa == 0 ? &tm_d : pa == 1 ? &tm_nm : &tm_h1;
+        const CUtensorMap* mb = pb == 0 ? &tm_d : pb == 1 ? &tm_nm : &tm_h1;
+        const int row_a = ti * kPairTileM + int(rank) * 128;
+        const int row_b0 = w.tj + int(rank) * (n0 / 2);            // N/2 of the 128 loaded rows are used
+        const int row_b1 = w.tj + kQTileN + int(rank) * (n1 / 2);
+        const uint32_t bytes = 2u * uint32_t(n1 ? kWideStageBytes : kPairStageBytes);
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+          uint8_t* sa = smem + stage * kWideStageBytes;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          const uint32_t bar0 = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_pair(sa, ma, bar0, kb * 128, row_a);   // (byte along K, row)
+          tma_load_2d_pair(sa + kHalfBytes, mb, bar0, kb * 128, row_b0);
+          if (n1) tma_load_2d_pair(sa + 2 * kHalfBytes, mb, bar0, kb * 128, row_b1);
+          if (++stage == kWideStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc0 = make_idesc_mxf4(kPairTileM, 0);
+      const uint32_t sfa = tmem_base + 240u, sfb = tmem_base + 244u;
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int it = cluster; it < p.n_items; it += n_clusters) {
+        const WorkItem w = p.items[it];
+        const uint32_t n0 = (((uint32_t(w.prod_ti) >> 4) & 15u) + 1u) * 16u, n1 = ((uint32_t(w.prod_ti) >> 8) & 15u) * 16u;
+        const uint32_t idesc_a = idesc0 | ((n0 >> 3) << 17), idesc_b = idesc0 | ((n1 >> 3) << 17);
+        mbar_wait(tempty_bar, acc_phase ^ 1, p.err_flag, 2);   // both accumulators drained by the previous item
+        tc_fence_after();
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kWideStageBytes);
+          const uint64_t da = make_smem_desc_sw128(sa, 16u, 1024u);
+          const uint64_t db0 = make_smem_desc_sw128(sa + kHalfBytes, 16u, 1024u);
+          const uint64_t db1 = make_smem_desc_sw128(sa + 2 * kHalfBytes, 16u, 1024u);
+          const uint32_t accum0 = kb > w.kb0 ? 1u : 0u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 32 bytes = 64 loci per MMA; the A step is used twice in a row
+            umma_mxf4_pair(tmem_base, da + uint64_t(k * 2), db0 + uint64_t(k * 2), idesc_a, (accum0 | uint32_t(k)) ? 1u : 0u, sfa, sfb);
+            if (n1) umma_mxf4_pair(tmem_base + 256u, da + uint64_t(k * 2), db1 + uint64_t(k * 2), idesc_b, (accum0 | uint32_t(k)) ? 1u : 0u, sfa, sfb);
+          }
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (++stage == kWideStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(tfull_bar, 3);
+        acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue (warps 2..5, both CTAs)
+    const int q = warp & 3;
+    uint32_t acc_phase = 0;
+    for (int it = cluster; it < p.n_items; it += n_clusters) {
+      const WorkItem w = p.items[it];
+      const int prod = w.prod_ti & 15, ti = int(uint32_t(w.prod_ti) >> 12);
+      const int n0 = (((w.prod_ti >> 4) & 15) + 1) * 16, n1 = ((w.prod_ti >> 8) & 15) * 16;   // each >= 32 or absent
+      const bool sym = prod != TPG_MAT_HN;
+      mbar_wait(tfull_bar, acc_phase, p.err_flag, 4);
+      tc_fence_after();
+      const int i = ti * kPairTileM + int(rank) * 128 + q * 32 + lane;
+      int32_t* cbase = p.counts + int64_t(prod) * p.mat_stride + i;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int ncols = half ? n1 : n0;
+        if (ncols == 0) break;
+        const int j0 = w.tj + half * kQTileN;
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(half * 256);
+        const bool last_half = half == 1 || n1 == 0;
+#pragma unroll 1
+        for (int c = 0; c < ncols; c += 32) {
+          const bool last = c + 32 >= ncols;
+          const int cc = last ? ncols - 32 : c;       // the last 32-column load overlaps the previous one
+          const int first = last ? 32 - (ncols - c) : 0;
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + uint32_t(cc), v);
+          tmem_ld_wait();
+          if (last && last_half) {  // both accumulators drained: hand them back (to the leader's barrier)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(tempty_bar), 0));
+          }
+          if (j0 + cc < p.n && i < p.n) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              const int j = j0 + cc + jj;
+              if (jj >= first && j < p.n && (!sym || i <= j))
+                atomicAdd(cbase + int64_t(j) * p.ld, __float2int_rn(__uint_as_float(v[jj])));
+            }
+          }
+        }
+      }
+      acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -642,6 +827,7 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   }
   if (!ctx->mxf4_attr_set) {
     TPG_CUDA_OK(cudaFuncSetAttribute(gram_mxf4_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes), E);
+    TPG_CUDA_OK(cudaFuncSetAttribute(gram_mxf4_wide_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideSmemBytes), E);
     ctx->mxf4_attr_set = true;
   }
   if (ctx->pair_clusters <= 0) return E.fail(TPG_ERR_CUDA, "gram(mxf4): the device reports no resident CTA pairs");
@@ -650,8 +836,6 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   const int64_t kblocks = a.lc_pad / kQStageLoci;
   // Column tiles: every 1024-column region (the ownership / L2 unit) is cut into 240 + 240 + 240 + 240 + 64,
   // so tiles never straddle a region; unsharded jobs simply run 240-wide tiles across the whole width.
-  struct T { int prod, ti, col0, ncols; };
-  std::vector<T> tiles;
   std::vector<std::pair<int, int>> cols;  // (first column, N)
   if (a.shard_world > 1) {
     for (int64_t r0 = 0; r0 < a.n; r0 += 1024)
@@ -667,22 +851,54 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
       cols.push_back({int(c0), trim ? int(std::min<int64_t>(kQTileN, need)) : kQTileN});
     }
   }
+  // Wide tiles (gram_mxf4_wide_kernel): two neighbouring 240-column tiles share one A stream.  Worth it where
+  // tiles are plentiful (the kernel is then bound by the L2 -> smem operand stream); small matrices keep the
+  // ping-pong kernel, whose epilogue overlaps the next item.  tpg_config.gram_wide: 0 auto, 1 never, 2 always.
+  struct WC { int c0, n0, n1; };
+  std::vector<WC> wcols;
+  auto count_tiles = [&](bool wide_cols) {
+    int64_t cnt = 0;
+    for (int64_t ti = 0; ti < tiles_m; ++ti) {
+      if (kPairTileM * ti >= a.n) continue;
+      if (wide_cols) { for (const WC& w : wcols) if (w.c0 + (w.n1 ? kQTileN + w.n1 : w.n0) - 1 >= kPairTileM * ti) ++cnt; }
+      else { for (const auto& c : cols) if (c.first + c.second - 1 >= kPairTileM * ti) ++cnt; }
+    }
+    return cnt;
+  };
+  const tpg_config C = cfg();
+  bool wide = C.gram_wide == 2 || (C.gram_wide == 0 && count_tiles(false) >= int64_t(4) * units);
+  if (wide) {
+    // pair up: unsharded 240 | 240 | 240 ...; sharded, per 1024-column region, (240 + 240) (240 + 240) (64)
+    const size_t per_region = a.shard_world > 1 ? 5 : cols.size();
+    for (size_t r0 = 0; r0 < cols.size(); r0 += per_region)
+      for (size_t k = r0; k < std::min(r0 + per_region, cols.size());) {
+        const bool pair2 = k + 1 < std::min(r0 + per_region, cols.size()) && cols[k].second == kQTileN &&
+                           cols[k + 1].first == cols[k].first + kQTileN;
+        wcols.push_back({cols[k].first, cols[k].second, pair2 ? cols[k + 1].second : 0});
+        k += pair2 ? 2 : 1;
+      }
+  } else {
+    for (const auto& c : cols) wcols.push_back({c.first, c.second, 0});
+  }
   const int64_t RI = 4;
-  const size_t RJ = a.shard_world > 1 ? 5 : 4;
-  for (size_t rj = 0; rj < cols.size(); rj += RJ)
+  const size_t RJ = wide ? (a.shard_world > 1 ? 3 : 2) : (a.shard_world > 1 ? 5 : 4);
+  struct T { int prod, ti, col0, n0, n1; };
+  std::vector<T> tiles;
+  for (size_t rj = 0; rj < wcols.size(); rj += RJ)
     for (int64_t ri = 0; ri < tiles_m; ri += RI)
-      for (size_t cj = rj; cj < std::min(rj + RJ, cols.size()); ++cj)
+      for (size_t cj = rj; cj < std::min(rj + RJ, wcols.size()); ++cj)
         for (int64_t ti = ri; ti < std::min(ri + RI, tiles_m); ++ti) {
           if (kPairTileM * ti >= a.n) continue;  // rows of padding individuals only
-          const int c0 = cols[cj].first, nc = cols[cj].second;
-          const bool upper = c0 + nc - 1 >= kPairTileM * ti;
-          if (!tile_wanted(a, kPairTileM * ti, kPairTileM * (ti + 1), c0, c0 + nc)) continue;
+          const int c0 = wcols[cj].c0, n0 = wcols[cj].n0, n1 = wcols[cj].n1;
+          const int c_end = c0 + (n1 ? kQTileN + n1 : n0);
+          const bool upper = c_end - 1 >= kPairTileM * ti;
+          if (!tile_wanted(a, kPairTileM * ti, kPairTileM * (ti + 1), c0, c_end)) continue;
           const int64_t bi = ti, bj = c0 / 256;  // 256-blocks; ownership is per 1024 region, so any block of the tile will do
           for (int prod = 0; prod < TPG_NUM_COUNT_MATS; ++prod) {
             if (!(a.prod_mask & (1 << prod))) continue;
             if (prod != TPG_MAT_HN && !upper) continue;
             if (!block_owned(std::min(bi, bj), std::max(bi, bj), nblocks, a.shard_rank, a.shard_world)) continue;
-            tiles.push_back({prod, int(ti), c0, nc});
+            tiles.push_back({prod, int(ti), c0, n0, n1});
           }
         }
   if (tiles.empty()) { if (macs_out) *macs_out = 0; return TPG_OK; }
@@ -700,12 +916,12 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   }
   if (macs_out) {
     int64_t cells = 0;
-    for (const T& t : tiles) cells += int64_t(kPairTileM) * t.ncols;
+    for (const T& t : tiles) cells += int64_t(kPairTileM) * (t.n0 + t.n1);
     *macs_out = cells * a.lc_pad;
   }
   char key[200];
-  snprintf(key, sizeof key, "q4/%lld/%lld/%lld/%d/%d/%d/%d/%llx", (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad, a.prod_mask, ks,
-           a.shard_rank, a.shard_world, (unsigned long long)(a.group_sorted ? a.group_sig | 1u : 0u));
+  snprintf(key, sizeof key, "q4%c/%lld/%lld/%lld/%d/%d/%d/%d/%llx", wide ? 'w' : 'p', (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad,
+           a.prod_mask, ks, a.shard_rank, a.shard_world, (unsigned long long)(a.group_sorted ? a.group_sig | 1u : 0u));
   if (ctx->items_key != key) {
     std::vector<WorkItem>& items = ctx->h_items;
     items.clear();
@@ -713,7 +929,10 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
     for (int s = 0; s < ks; ++s) {
       const int32_t kb0 = int32_t(kblocks * s / ks), kb1 = int32_t(kblocks * (s + 1) / ks);
       if (kb1 <= kb0) continue;
-      for (const T& t : tiles) items.push_back({int32_t(t.prod | ((t.ncols / 16 - 1) << 4) | (t.ti << 8)), t.col0, kb0, kb1});
+      for (const T& t : tiles) {
+        if (wide) items.push_back({int32_t(uint32_t(t.prod) | (uint32_t(t.n0 / 16 - 1) << 4) | (uint32_t(t.n1 / 16) << 8) | (uint32_t(t.ti) << 12)), t.col0, kb0, kb1});
+        else items.push_back({int32_t(t.prod | ((t.n0 / 16 - 1) << 4) | (t.ti << 8)), t.col0, kb0, kb1});
+      }
     }
     if (items.size() > ctx->d_items_cap) {
       TPG_CUDA_OK(cudaStreamSynchronize(st), E);
@@ -745,7 +964,8 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   p.n = int(a.n);
   p.err_flag = ctx->d_err_flag;
   const int grid = 2 * int(std::min<size_t>(n_items, size_t(units)));
-  gram_mxf4_pair_kernel<0><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
+  if (wide) gram_mxf4_wide_kernel<0><<<grid, kGramThreads, kWideSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
+  else gram_mxf4_pair_kernel<0><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
   TPG_CUDA_OK(cudaGetLastError(), E);
   ctx->launches++;
   return TPG_OK;
