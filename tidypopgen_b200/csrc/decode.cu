@@ -439,8 +439,10 @@ gather_pack_kernel(const GatherParams p) {
   }
 }
 
-// Shared memory a gather CTA may use: two CTAs per SM while a column is small, one beyond.
-constexpr int kGatherSmemTwo = 100 * 1024, kGatherSmemMax = 200 * 1024;
+// Shared memory a gather CTA may use.  A CTA alternates between two phases that want different resources —
+// staging (HBM latency / bandwidth) and the gather (shared-memory lookups) — so several small CTAs per SM
+// overlap better than two large ones: four per SM while a few columns fit 52 KiB, fewer for longer columns.
+constexpr int kGatherSmemTwo = 52 * 1024, kGatherSmemMax = 200 * 1024;
 
 bool gather_pack_fits(int64_t span_bytes) { return span_bytes + 32 <= kGatherSmemMax; }
 
@@ -464,7 +466,10 @@ int launch_gather_pack(Ctx* ctx, const DecodeArgs& a, bool packed_in, int64_t ro
   p.n = int(a.n);
   p.lc = int(a.lc);
   p.col_pitch = int((span_bytes + 16 + 15) / 16 * 16);
-  const int budget = p.col_pitch * 2 <= kGatherSmemTwo ? kGatherSmemTwo : kGatherSmemMax;
+  int budget = kGatherSmemTwo;
+  if (const tpg_config C = cfg(); C.gather_smem_kb > 0) budget = std::min(kGatherSmemMax, std::max(8, int(C.gather_smem_kb)) * 1024);
+  while (budget < kGatherSmemMax && p.col_pitch * 2 > budget) budget *= 2;   // long columns: at least two loci per CTA
+  budget = std::min(budget, kGatherSmemMax);
   p.loci_per_cta = int(std::max<int64_t>(1, std::min<int64_t>(64, budget / p.col_pitch)));
   // enough CTAs to fill the machine: shrink the loci per CTA for short chunks
   while (p.loci_per_cta > 1 && (a.lc + p.loci_per_cta - 1) / p.loci_per_cta < 2 * ctx->num_sms) p.loci_per_cta /= 2;
