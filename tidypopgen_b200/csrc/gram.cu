@@ -575,22 +575,33 @@ gram_mxf4_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
 // for twice the MACs, a quarter less L2 traffic per MAC.  The price is the epilogue, which no longer
 // overlaps the next item's MMAs (there is no third accumulator to ping-pong with); with 128 k-blocks per
 // item it is a few per cent, so the host uses this kernel where tiles are plentiful (launch_gram_mxf4) and
-// the ping-pong kernel for small matrices.  Everything else — CTA pairs, barriers, scale-factor columns
-// [240, 256), the int32 atomics, the chain-length guard — is as in gram_mxf4_pair_kernel.
+// the ping-pong kernel for small matrices.
+// That only pays if the exposed epilogue is short, and red.global is not: ~1.3 cycles per lane, 80,000 cycles
+// for a 128 x 480 accumulator against 123,000 of MMAs.  So this kernel's epilogue goes through the TMA instead:
+// a warp converts 32 x 32 accumulator values, stores them to a 4 KiB staging box in shared memory (conflict
+// free: lane = row) and ONE cp.reduce.async.bulk.tensor adds the box into the int32 count matrix in the
+// memory system — 32 shared-memory stores per thread instead of 32 global atomics, two boxes per warp in flight.
+// Whole boxes are added: entries below the diagonal of the symmetric products receive values too (nothing
+// reads them), padding rows / columns add zeros (their planes are zero).
+// Everything else — CTA pairs, barriers, scale-factor columns [240, 256), the chain-length guard — is as in
+// gram_mxf4_pair_kernel.
 constexpr int kWideStages = 4;
 constexpr int kWideStageBytes = 3 * kHalfBytes;       // per CTA: A half + two B halves
-constexpr int kWideSmemBytes = kWideStages * kWideStageBytes + 1024 + 256;
+constexpr int kWideEpiBytes = 4 * 2 * 4096;           // epilogue staging: per warp two 32 x 32 int32 boxes
+constexpr int kWideSmemBytes = kWideStages * kWideStageBytes + kWideEpiBytes + 1024 + 256;
 
 // work item: prod [0,4) | (n0 / 16 - 1) [4,8) | (n1 / 16) [8,12) | ti [12,32); tj = first column;
 // half 0 = columns [tj, tj + n0), half 1 = columns [tj + 240, tj + 240 + n1) (n1 = 0: absent)
 template <int kDummy>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGramThreads, 1)
 gram_mxf4_wide_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_nm,
-                      const __grid_constant__ CUtensorMap tm_h1, const GramParams p) {
+                      const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_counts,
+                      const GramParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWideStages * kWideStageBytes);
+  uint8_t* epi = smem + kWideStages * kWideStageBytes;  // [4 warps][2][32 x 32 int32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + kWideEpiBytes);
   uint64_t* full_bar = bars;                          // [kWideStages] used in the leader only
   uint64_t* empty_bar = bars + kWideStages;           // [kWideStages] in each CTA
   uint64_t* tfull_bar = bars + 2 * kWideStages;       // [1] in each CTA
@@ -606,6 +617,7 @@ gram_mxf4_wide_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
     tma_prefetch_desc(&tm_d);
     tma_prefetch_desc(&tm_nm);
     tma_prefetch_desc(&tm_h1);
+    tma_prefetch_desc(&tm_counts);
     for (int s = 0; s < kWideStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -699,15 +711,16 @@ gram_mxf4_wide_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
     // ===================================================== epilogue (warps 2..5, both CTAs)
     const int q = warp & 3;
     uint32_t acc_phase = 0;
+    int buf = 0;
+    uint8_t* ebase = epi + q * 2 * 4096;
     for (int it = cluster; it < p.n_items; it += n_clusters) {
       const WorkItem w = p.items[it];
       const int prod = w.prod_ti & 15, ti = int(uint32_t(w.prod_ti) >> 12);
       const int n0 = (((w.prod_ti >> 4) & 15) + 1) * 16, n1 = ((w.prod_ti >> 8) & 15) * 16;   // each >= 32 or absent
-      const bool sym = prod != TPG_MAT_HN;
       mbar_wait(tfull_bar, acc_phase, p.err_flag, 4);
       tc_fence_after();
-      const int i = ti * kPairTileM + int(rank) * 128 + q * 32 + lane;
-      int32_t* cbase = p.counts + int64_t(prod) * p.mat_stride + i;
+      const int i0 = ti * kPairTileM + int(rank) * 128 + q * 32;       // this warp's 32 rows
+      const int jmat = prod * int(p.ld);                                // count matrices are stacked along j
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         const int ncols = half ? n1 : n0;
@@ -728,18 +741,26 @@ gram_mxf4_wide_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(tempty_bar), 0));
           }
-          if (j0 + cc < p.n && i < p.n) {
+          // the staging box this warp used two chunks ago must have been read by its reduction
+          if (lane == 0) bulk_wait_group_read<1>();
+          __syncwarp();
+          int32_t* box = reinterpret_cast<int32_t*>(ebase + buf * 4096);   // [32 columns][32 rows]
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-              const int j = j0 + cc + jj;
-              if (jj >= first && j < p.n && (!sym || i <= j))
-                atomicAdd(cbase + int64_t(j) * p.ld, __float2int_rn(__uint_as_float(v[jj])));
-            }
+          for (int jj = 0; jj < 32; ++jj)   // columns already added by the previous (overlapping) chunk add zero
+            box[jj * 32 + lane] = jj >= first ? __float2int_rn(__uint_as_float(v[jj])) : 0;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tm_counts, box, i0, jmat + j0 + cc);
+            bulk_commit_group();
           }
+          buf ^= 1;
         }
       }
       acc_phase ^= 1;
     }
+    if (lane == 0) bulk_wait_group<0>();   // every reduction of this warp has landed before the CTA exits
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -964,7 +985,21 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   p.n = int(a.n);
   p.err_flag = ctx->d_err_flag;
   const int grid = 2 * int(std::min<size_t>(n_items, size_t(units)));
-  if (wide) gram_mxf4_wide_kernel<0><<<grid, kGramThreads, kWideSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
+  if (wide) {
+    // the count matrices as one 2-D int32 tensor (rows i fastest, the four matrices stacked along j): the
+    // epilogue's TMA reductions add 32 x 32 boxes into it
+    if (!ctx->encode_tiled) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled entry point missing");
+    CUtensorMap cmap;
+    cuuint64_t dims[2] = {cuuint64_t(a.ld), cuuint64_t(a.ld) * TPG_NUM_COUNT_MATS};
+    cuuint64_t strides[1] = {cuuint64_t(a.ld) * sizeof(int32_t)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+        &cmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, a.counts, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled(counts) failed (CUresult %d)", int(r));
+    gram_mxf4_wide_kernel<0><<<grid, kGramThreads, kWideSmemBytes, st>>>(maps[0], maps[1], maps[2], cmap, p);
+  }
   else gram_mxf4_pair_kernel<0><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
   TPG_CUDA_OK(cudaGetLastError(), E);
   ctx->launches++;
