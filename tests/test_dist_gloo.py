@@ -146,5 +146,8 @@ def test_partitions_cover_exactly():
         cnt = np.bincount([tdist.block_owner(i * r, j * r, nb, w) for i in range(nr) for j in range(i, nr)], minlength=w)
         assert cnt.max() - cnt.min() <= 1  # round-robin balance over the regions
         assert nr * (nr + 1) // 2 >= 8 * w or r == 1
-    assert tdist.shard_region_blocks(196, 8) == 4 and tdist.shard_region_blocks(24, 8) == 2 and tdist.shard_region_blocks(4, 2) == 1
+    # 50,000 individuals on 8 ranks: 3840 x 3840 regions (whole 256-row and 240- / 480-column tiles);
+    # 20,000 on 8: too few of those, 1024 x 1024; small matrices 512, 256
+    assert tdist.shard_region_blocks(196, 8) == 15 and tdist.shard_region_blocks(79, 8) == 4
+    assert tdist.shard_region_blocks(24, 8) == 2 and tdist.shard_region_blocks(4, 2) == 1
     assert tdist.choose_mode(929, 8) == "loci" and tdist.choose_mode(50000, 8) == "tiles"

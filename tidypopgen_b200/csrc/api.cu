@@ -418,7 +418,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   // 1024-column ownership regions use the int8 kernels; both kinds add into the same int32 counts.
   const bool q4_forced_off = (job->flags & (TPG_FLAG_GRAM_I8 | TPG_FLAG_GRAM_1CTA)) || C.gram_route == 1 || C.gram_ctas == 1;
   const bool q4_tiles_ok = !(job->shard_mode == TPG_SHARD_TILES && job->shard_world > 1) ||
-                           shard_region_blocks(pl.n_pad / 256, job->shard_world) == 4;
+                           shard_region_blocks(pl.n_pad / 256, job->shard_world) >= 4;
   const bool q4_ok = !scan && !k_major && !q4_forced_off && q4_tiles_ok;
   const bool direct_only = direct_ok && !pack_ok;
   if (direct_only) { span = nrow; rlo = 0; }

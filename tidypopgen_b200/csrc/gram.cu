@@ -837,8 +837,9 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
     return E.fail(TPG_ERR_ARG, "gram(mxf4): n_pad (%lld) / lc_pad (%lld) not multiples of 256",
                   (long long)a.n_pad, (long long)a.lc_pad);
   const int64_t nblocks = a.n_pad / 256;
-  if (a.shard_world > 1 && shard_region_blocks(nblocks, a.shard_world) != 4)
-    return E.fail(TPG_ERR_ARG, "gram(mxf4): tile sharding needs 1024-column ownership regions (int8 kernels otherwise)");
+  const int64_t region_w = a.shard_world > 1 ? 256 * shard_region_blocks(nblocks, a.shard_world) : 0;
+  if (a.shard_world > 1 && region_w < 1024)
+    return E.fail(TPG_ERR_ARG, "gram(mxf4): tile sharding needs ownership regions of at least 1024 columns (int8 kernels otherwise)");
   if (!ctx->gram_attr_set) {
     GramArgs probe = a;   // sets the attributes of every gram kernel and counts the resident CTA pairs
     probe.mxf4 = false;
@@ -855,14 +856,18 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   const int units = ctx->pair_clusters;
   const int64_t tiles_m = a.n_pad / kPairTileM;
   const int64_t kblocks = a.lc_pad / kQStageLoci;
-  // Column tiles: every 1024-column region (the ownership / L2 unit) is cut into 240 + 240 + 240 + 240 + 64,
-  // so tiles never straddle a region; unsharded jobs simply run 240-wide tiles across the whole width.
+  // Column tiles never straddle an ownership region: a 3840-column region is sixteen 240-column tiles, a
+  // 1024-column one 240 + 240 + 240 + 240 + 64; unsharded jobs simply run 240-wide tiles across the whole width.
+  // The last tile of the matrix is trimmed to the valid individuals (multiples of 16, at least 32 for the epilogue).
   std::vector<std::pair<int, int>> cols;  // (first column, N)
+  size_t tiles_per_region = 0;
   if (a.shard_world > 1) {
-    for (int64_t r0 = 0; r0 < a.n; r0 += 1024)
-      for (int s5 = 0; s5 < 5; ++s5) {
-        const int64_t c0 = r0 + 240 * s5;
-        if (c0 < a.n) cols.push_back({int(c0), s5 < 4 ? kQTileN : 64});
+    tiles_per_region = size_t((region_w + kQTileN - 1) / kQTileN);
+    for (int64_t r0 = 0; r0 < a.n; r0 += region_w)
+      for (int64_t c0 = r0; c0 < r0 + region_w && c0 < a.n; c0 += kQTileN) {
+        const int64_t room = std::min<int64_t>(kQTileN, r0 + region_w - c0);
+        const int64_t need = std::max<int64_t>(32, (a.n - c0 + 15) / 16 * 16);
+        cols.push_back({int(c0), int(std::min(room, need))});
       }
   } else {
     // the last column tile is trimmed to the valid individuals (multiples of 16, at least 32 for the epilogue)
@@ -890,19 +895,20 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   bool wide = C.gram_wide == 2 || (C.gram_wide == 0 && count_tiles(false) >= int64_t(4) * units);
   if (wide) {
     // pair up: unsharded 240 | 240 | 240 ...; sharded, per 1024-column region, (240 + 240) (240 + 240) (64)
-    const size_t per_region = a.shard_world > 1 ? 5 : cols.size();
-    for (size_t r0 = 0; r0 < cols.size(); r0 += per_region)
-      for (size_t k = r0; k < std::min(r0 + per_region, cols.size());) {
-        const bool pair2 = k + 1 < std::min(r0 + per_region, cols.size()) && cols[k].second == kQTileN &&
+    // (a pair never spans two ownership regions)
+    for (size_t k = 0; k < cols.size();) {
+        const bool same_region = !region_w || (k + 1 < cols.size() && cols[k].first / region_w == cols[k + 1].first / region_w);
+        const bool pair2 = k + 1 < cols.size() && same_region && cols[k].second == kQTileN &&
                            cols[k + 1].first == cols[k].first + kQTileN;
         wcols.push_back({cols[k].first, cols[k].second, pair2 ? cols[k + 1].second : 0});
         k += pair2 ? 2 : 1;
-      }
+    }
   } else {
     for (const auto& c : cols) wcols.push_back({c.first, c.second, 0});
   }
   const int64_t RI = 4;
-  const size_t RJ = wide ? (a.shard_world > 1 ? 3 : 2) : (a.shard_world > 1 ? 5 : 4);
+  // L2 neighbourhoods of about 1024 columns: 2 wide / 4 narrow tiles (5 where a 1024-column region ends in a 64-column one)
+  const size_t RJ = wide ? (tiles_per_region == 5 ? 3 : 2) : (tiles_per_region == 5 ? 5 : 4);
   struct T { int prod, ti, col0, n0, n1; };
   std::vector<T> tiles;
   for (size_t rj = 0; rj < wcols.size(); rj += RJ)

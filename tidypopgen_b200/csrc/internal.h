@@ -147,15 +147,21 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
 
 // Tile sharding: the 256x256 output blocks (bi <= bj, nblocks per side) are grouped into square
 // REGIONS of R x R blocks and the regions of the upper triangle are dealt round-robin in row-major
-// order; identical on every rank, host and device.  A rank therefore owns whole 1024 x 1024
-// neighbourhoods (R = 4) — the unit whose operand panels the Gram scheduler keeps in L2; owning
-// scattered single blocks made every tile fetch its panels from HBM (C4 on 8 GPUs: 1752 TOP/s
-// per GPU against 2945 for one GPU on the whole matrix).  R shrinks for small matrices so that
-// there are still at least 8 regions per rank.
+// order; identical on every rank, host and device.  A rank therefore owns whole neighbourhoods — the unit
+// whose operand panels the Gram scheduler keeps in L2; owning scattered single blocks made every tile fetch
+// its panels from HBM (C4 on 8 GPUs: 1752 TOP/s per GPU against 2945 for one GPU on the whole matrix).
+// R = 15 (3840 x 3840: a multiple of the 256-row AND of the 240- / 480-column tiles of the 4-bit kernels,
+// so a region is cut into whole tiles — with R = 4 every 1024-column region ends in a 64-column tile that
+// moves as many operand bytes as a full one) while there are at least 8 regions per rank; R = 4, 2, 1 for
+// smaller matrices.
 #ifdef __CUDACC__
 __host__ __device__
 #endif
 inline int64_t shard_region_blocks(int64_t nblocks, int world) {
+  {
+    const int64_t nr = (nblocks + 14) / 15;
+    if (nr * (nr + 1) / 2 >= int64_t(8) * world) return 15;
+  }
   int64_t r = 4;
   while (r > 1) {
     const int64_t nr = (nblocks + r - 1) / r;

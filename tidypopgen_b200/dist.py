@@ -54,8 +54,11 @@ def loci_slice(m: int, rank: int, world: int) -> tuple[int, int]:
 
 def shard_region_blocks(nblocks: int, world: int) -> int:
     """Side (in 256-blocks) of the square regions tile ownership is dealt in — identical to
-    shard_region_blocks() in csrc/internal.h: 4 (1024 x 1024 neighbourhoods, what the Gram
-    scheduler keeps in L2), smaller while a rank would get fewer than 8 regions."""
+    shard_region_blocks() in csrc/internal.h: 15 (3840 x 3840: whole 256-row and 240- / 480-column tiles of
+    the 4-bit Gram kernels) while a rank gets at least 8 regions, else 4 (1024 x 1024), 2, 1."""
+    nr = (nblocks + 14) // 15
+    if nr * (nr + 1) // 2 >= 8 * world:
+        return 15
     r = 4
     while r > 1:
         nr = (nblocks + r - 1) // r
