@@ -908,7 +908,7 @@ static int results_to_host(Ctx* ctx, const void* const* dev, void* const* host, 
     if (e != cudaSuccess) return e;
     uint8_t* dst = q.dst;
     const uint8_t* from = q.from;
-    parallel_for(int64_t(q.len), int64_t(256) << 10, [=](int64_t a, int64_t z) { memcpy(dst + a, from + a, size_t(z - a)); });
+    parallel_for(int64_t(q.len), int64_t(256) << 10, [=](int64_t a, int64_t z) { copy_streaming(dst + a, from + a, size_t(z - a)); });
     return cudaSuccess;
   };
   cudaEvent_t evp[2] = {pooled_event(ctx, false), pooled_event(ctx, false)};

@@ -1,5 +1,6 @@
 // Persistent host worker pool + the 2-bit (pk2) packer of the .bk streamer (pack.cpp).
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <functional>
 
@@ -23,6 +24,9 @@ class HostPool {
   struct Impl;
   Impl* impl_;
 };
+
+// memcpy with non-temporal stores (large result pieces: written once, no read-for-ownership).
+void copy_streaming(void* dst, const void* src, size_t n);
 
 // pk2 layout: bytes per packed column for a staged row window of `span` individuals.
 int64_t pk2_stride(int64_t span);

@@ -207,9 +207,38 @@ __attribute__((target("avx2"))) static void pack_col_avx2(const uint8_t* src, in
   }
 }
 
+// memcpy for result pieces leaving the pinned bounce buffers: non-temporal stores.  The destination (a
+// 20 GB R matrix at n = 50,000) is written once and not read again by us, so fetching its cache lines for
+// ownership — what cached stores of a plain memcpy of this size per thread do — is a third of the DRAM
+// traffic of the copy for nothing.
+__attribute__((target("avx2"))) static void copy_stream_avx2(uint8_t* dst, const uint8_t* src, size_t n) {
+  size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
+  if (head > n) head = n;
+  memcpy(dst, src, head);
+  dst += head; src += head; n -= head;
+  size_t i = 0;
+  for (; i + 128 <= n; i += 128) {
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
+    const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
+    const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), b);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), c);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), d);
+  }
+  _mm_sfence();
+  memcpy(dst + i, src + i, n - i);
+}
+
 static bool have_avx2() {
   static const bool v = __builtin_cpu_supports("avx2");
   return v;
+}
+
+void copy_streaming(void* dst, const void* src, size_t n) {
+  if (n >= 4096 && have_avx2()) copy_stream_avx2(static_cast<uint8_t*>(dst), static_cast<const uint8_t*>(src), n);
+  else memcpy(dst, src, n);
 }
 
 int64_t pk2_stride(int64_t span) { return ((span + 3) / 4 + 15) / 16 * 16; }
