@@ -371,6 +371,11 @@ int tpg_pairwise_ctx(tpg_ctx* ctx, const tpg_job* job, tpg_result* res, char* er
  * falls in the same 128x256 tile). */
 #define TPG_NUM_COUNT_MATS 4
 enum { TPG_MAT_DD = 0, TPG_MAT_NN = 1, TPG_MAT_HH = 2, TPG_MAT_HN = 3 };
+/* Tile sharding (TPG_SHARD_TILES): the rank of shard_world that owns the 256 x 256 output block (bi <= bj)
+ * of a job on n individuals.  Blocks are grouped into square regions — 3840 x 3840 (whole 256-row and
+ * 240- / 480-column tiles of the 4-bit Gram kernels) assigned by weight, largest first to the least loaded
+ * rank, while a rank gets at least 8 of them; else 1024 x 1024 (512, 256) dealt round-robin.  Host only. */
+int32_t tpg_tile_owner(int64_t n, int64_t bi, int64_t bj, int32_t shard_world);
 int64_t tpg_counts_ld(int64_t n);       /* n rounded up to the tile multiple       */
 int64_t tpg_counts_elems(int64_t n);    /* TPG_NUM_COUNT_MATS * ld * ld            */
 

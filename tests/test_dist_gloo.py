@@ -146,6 +146,23 @@ def test_partitions_cover_exactly():
         cnt = np.bincount([tdist.block_owner(i * r, j * r, nb, w) for i in range(nr) for j in range(i, nr)], minlength=w)
         assert cnt.max() - cnt.min() <= 1  # round-robin balance over the regions
         assert nr * (nr + 1) // 2 >= 8 * w or r == 1
+    # the host mirror and the library agree on every block's owner, round-robin and weighted regimes alike
+    lib = L.lib()
+    for n, w in ((929, 2), (5000, 3), (20000, 8), (50000, 8), (50000, 4), (50000, 2), (61000, 7)):
+        nb = (n + 255) // 256
+        blocks = [(i, j) for i in range(0, nb, max(1, nb // 23)) for j in range(i, nb, max(1, nb // 19))]
+        for bi, bj in blocks:
+            assert lib.tpg_tile_owner(n, bi, bj, w) == tdist.block_owner(bi, bj, nb, w), (n, w, bi, bj)
+    # 3840 x 3840 regions are few and unequal: the weighted assignment keeps every rank within 4 % of the mean
+    for w in (2, 4, 8):
+        nb, r = 196, 15
+        nr = (nb + r - 1) // r
+        load = np.zeros(w)
+        for ri in range(nr):
+            for rj in range(ri, nr):
+                h, wd = min(r, nb - ri * r), min(r, nb - rj * r)
+                load[tdist.block_owner(ri * r, rj * r, nb, w)] += h * wd if ri == rj else 2 * h * wd
+        assert load.max() / load.mean() < 1.04
     # 50,000 individuals on 8 ranks: 3840 x 3840 regions (whole 256-row and 240- / 480-column tiles);
     # 20,000 on 8: too few of those, 1024 x 1024; small matrices 512, 256
     assert tdist.shard_region_blocks(196, 8) == 15 and tdist.shard_region_blocks(79, 8) == 4

@@ -151,11 +151,63 @@ int ensure_slot(Ctx::Slot* s, size_t bytes, bool host, const char* what, const E
   return TPG_OK;
 }
 
+void build_owner_table(int64_t nblocks, int world, std::vector<uint8_t>* out) {
+  out->clear();
+  if (world <= 1 || world > 255) return;
+  const int64_t r = shard_region_blocks(nblocks, world);
+  if (r != 15) return;  // small regions are plentiful: round-robin balances them
+  const int64_t nr = (nblocks + r - 1) / r, total = nr * (nr + 1) / 2;
+  struct Reg { int64_t w, idx; };
+  std::vector<Reg> regs;
+  regs.reserve(size_t(total));
+  for (int64_t ri = 0; ri < nr; ++ri)
+    for (int64_t rj = ri; rj < nr; ++rj) {
+      const int64_t h = std::min(r, nblocks - ri * r), w = std::min(r, nblocks - rj * r);
+      regs.push_back({ri == rj ? h * w : 2 * h * w, ri * nr - ri * (ri - 1) / 2 + (rj - ri)});
+    }
+  std::stable_sort(regs.begin(), regs.end(), [](const Reg& a, const Reg& b) { return a.w != b.w ? a.w > b.w : a.idx < b.idx; });
+  std::vector<int64_t> load(size_t(world), 0);
+  out->assign(size_t(total), 0);
+  for (const Reg& g : regs) {
+    int best = 0;
+    for (int k = 1; k < world; ++k) if (load[k] < load[best]) best = k;
+    load[best] += g.w;
+    (*out)[size_t(g.idx)] = uint8_t(best);
+  }
+}
+
+int owner_table(Ctx* ctx, int64_t n_pad, int world, const uint8_t** host, const uint8_t** dev, const Err& E) {
+  *host = nullptr;
+  *dev = nullptr;
+  if (world <= 1) return TPG_OK;
+  const int64_t nblocks = n_pad / 256;
+  char key[64];
+  snprintf(key, sizeof key, "%lld/%d", (long long)nblocks, world);
+  if (ctx->owner_key != key) {
+    build_owner_table(nblocks, world, &ctx->h_owner);
+    if (!ctx->h_owner.empty()) {
+      int rc = ensure_slot(&ctx->d_owner, ctx->h_owner.size(), false, "owner table", E);
+      if (rc) return rc;
+      // (synchronous: the table of a previous geometry may still be read by kernels in flight)
+      TPG_CUDA_OK(cudaDeviceSynchronize(), E);
+      TPG_CUDA_OK(cudaMemcpy(ctx->d_owner.p, ctx->h_owner.data(), ctx->h_owner.size(), cudaMemcpyHostToDevice), E);
+    }
+    ctx->owner_key = key;
+  }
+  if (!ctx->h_owner.empty()) {
+    *host = ctx->h_owner.data();
+    *dev = static_cast<const uint8_t*>(ctx->d_owner.p);
+  }
+  return TPG_OK;
+}
+
 void trim_ctx(Ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   c->counts_key.clear();
-  Ctx::Slot* dev[] = {&c->d_raw[0], &c->d_raw[1], &c->d_gat[0], &c->d_gat[1], &c->d_planes[0], &c->d_planes[1], &c->d_rows,
+  c->owner_key.clear();
+  c->h_owner.clear();
+  Ctx::Slot* dev[] = {&c->d_owner, &c->d_raw[0], &c->d_raw[1], &c->d_gat[0], &c->d_gat[1], &c->d_planes[0], &c->d_planes[1], &c->d_rows,
                       &c->d_cols, &c->d_counts, &c->d_out[0], &c->d_out[1], &c->d_out[2],
                       &c->d_out[3], &c->d_red};
   for (Ctx::Slot* s : dev) { if (s->p) cudaFree(s->p); s->p = nullptr; s->cap = 0; }
@@ -416,6 +468,11 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   // The 4-bit route: decode_planes_k4 (raw bytes or 2-bit packed chunks) + the kind::mxf4 Gram kernel
   // (twice the int8 MAC rate, half the plane bytes, exact: gram.cu).  Tile-sharded jobs too small for
   // 1024-column ownership regions use the int8 kernels; both kinds add into the same int32 counts.
+  const uint8_t *owner_h = nullptr, *owner_d = nullptr;
+  if (job->shard_mode == TPG_SHARD_TILES && job->shard_world > 1) {
+    rc = owner_table(ctx, pl.n_pad, job->shard_world, &owner_h, &owner_d, E);
+    if (rc) return rc;
+  }
   const bool q4_forced_off = (job->flags & (TPG_FLAG_GRAM_I8 | TPG_FLAG_GRAM_1CTA)) || C.gram_route == 1 || C.gram_ctas == 1;
   const bool q4_tiles_ok = !(job->shard_mode == TPG_SHARD_TILES && job->shard_world > 1) ||
                            shard_region_blocks(pl.n_pad / 256, job->shard_world) >= 4;
@@ -855,6 +912,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     ga.prod_mask = pl.prod_mask;
     ga.shard_rank = job->shard_mode == TPG_SHARD_TILES ? job->shard_rank : 0;
     ga.shard_world = job->shard_mode == TPG_SHARD_TILES ? job->shard_world : 1;
+    ga.owner = owner_h;
     ga.counts = d_counts;
     ga.ld = pl.n_pad;
     ga.max_chain_out = &max_chain;
@@ -963,6 +1021,11 @@ static int finish_impl(Ctx* ctx, const tpg_job* job, const int32_t* d_counts, tp
   fa.n_short = n_short;
   fa.shard_rank = job->shard_mode == TPG_SHARD_TILES ? job->shard_rank : 0;
   fa.shard_world = job->shard_mode == TPG_SHARD_TILES ? job->shard_world : 1;
+  if (fa.shard_world > 1) {
+    const uint8_t* owner_h = nullptr;
+    int rc0 = owner_table(ctx, n_pad, fa.shard_world, &owner_h, &fa.owner, E);
+    if (rc0) return rc0;
+  }
   double* host[4] = {res->out0, res->out1, res->aux0, res->aux1};
   double* dev[4] = {nullptr, nullptr, nullptr, nullptr};
   const size_t bytes = sizeof(double) * size_t(n) * size_t(n);
@@ -1165,7 +1228,7 @@ static int pairwise_multi(const tpg_job* job, const int32_t* stats, int nstats, 
       if (rc == TPG_OK) rc = ensure_slot(&c->d_counts, cbytes, false, "count matrices", Er);
       // loci-sharded: every device adds into all blocks; tile-sharded: its own blocks only — but the tree
       // reduction below sums WHOLE matrices, so everything a peer may read has to be zero
-      if (rc == TPG_OK) rc = launch_zero_counts(c, static_cast<int32_t*>(c->d_counts.p), n, mask, 0, 1, c->s_compute, Er);
+      if (rc == TPG_OK) rc = launch_zero_counts(c, static_cast<int32_t*>(c->d_counts.p), n, mask, 0, 1, nullptr, c->s_compute, Er);
       if (rc == TPG_OK) {
         rc = accumulate_impl(c, &j, static_cast<int32_t*>(c->d_counts.p), &sts[r], Er, false, nullptr, mask);
       }
@@ -1324,7 +1387,9 @@ static int pairwise_many_on(Ctx* c, const tpg_job* job, const int32_t* stats, in
     const int mask = !key.empty() ? kAllProducts : union_mask(stats, nstats);
     // zero -> decode -> gram -> finish are enqueued back to back; one sync at the very end
     const bool tiles = job->shard_mode == TPG_SHARD_TILES && job->shard_world > 1;
-    rc = launch_zero_counts(c, d_counts, n, mask, tiles ? job->shard_rank : 0, tiles ? job->shard_world : 1, c->s_compute, E);
+    const uint8_t *owner_h = nullptr, *owner_d = nullptr;
+    if (tiles) { rc = owner_table(c, round_up(n, kRowPad), job->shard_world, &owner_h, &owner_d, E); if (rc) return rc; }
+    rc = launch_zero_counts(c, d_counts, n, mask, tiles ? job->shard_rank : 0, tiles ? job->shard_world : 1, owner_d, c->s_compute, E);
     if (rc) return rc;
     tpg_job jw = *job;
     jw.stat = stats[0];  // (tpg_pairwise_many ignores job->stat; the plan only needs a valid one)
@@ -1377,6 +1442,22 @@ int64_t tpg_split_len(int64_t m, int64_t block_size, int64_t* lower, int64_t* up
 }
 
 int64_t tpg_as_pad_count(int64_t m, int64_t block_size) { return as_pad_count(m, block_size); }
+
+int32_t tpg_tile_owner(int64_t n, int64_t bi, int64_t bj, int32_t world) {
+  if (n <= 0 || world <= 1) return 0;
+  const int64_t nblocks = round_up(n, kRowPad) / 256;
+  if (bi > bj) std::swap(bi, bj);
+  if (bi < 0 || bj >= nblocks) return -1;
+  static std::mutex mu;
+  static std::vector<uint8_t> table;
+  static int64_t t_nb = -1;
+  static int t_world = -1;
+  std::lock_guard<std::mutex> lk(mu);
+  if (t_nb != nblocks || t_world != world) { build_owner_table(nblocks, world, &table); t_nb = nblocks; t_world = world; }
+  for (int r = 0; r < world; ++r)
+    if (block_owned(bi, bj, nblocks, r, world, table.empty() ? nullptr : table.data())) return r;
+  return -1;
+}
 
 int64_t tpg_counts_ld(int64_t n) { return round_up(n, kRowPad); }
 int64_t tpg_counts_elems(int64_t n) {
@@ -1805,6 +1886,11 @@ int tpg_gram(tpg_ctx* h, const int8_t* d_planes, int64_t plane_stride, int64_t n
   a.lc_pad = lc_pad; a.k_major = (k_major & 1) != 0; a.ctas = (k_major & 2) ? 1 : 0; a.mxf4 = (k_major & 8) != 0;
   a.prod_mask = prod_mask;
   a.shard_rank = shard_rank; a.shard_world = shard_world; a.counts = d_counts; a.ld = n_pad;
+  if (shard_world > 1) {
+    const uint8_t* owner_d = nullptr;
+    int rc0 = owner_table(c, n_pad, shard_world, &a.owner, &owner_d, E);
+    if (rc0) return rc0;
+  }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, c->s_compute);

@@ -30,6 +30,7 @@ struct FinishParams {
   double m;
   int n_short;
   int shard_rank, shard_world;
+  const uint8_t* owner;
   double* out[4];  // out0, out1, aux0, aux1 (nullable)
 };
 
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams p) {
   if (p.shard_world > 1) {
     const int64_t nb = (p.ld + 255) / 256;
     if (!block_owned((int64_t(bi) * 32) / 256, (int64_t(bj) * 32) / 256, nb, p.shard_rank,
-                     p.shard_world))
+                     p.shard_world, p.owner))
       return;
   }
   __shared__ int32_t tN[32][33];
@@ -220,6 +221,7 @@ int launch_finish(Ctx* ctx, const FinishArgs& a, cudaStream_t st, const Err& E) 
   p.n_short = int(a.n_short);
   p.shard_rank = a.shard_rank;
   p.shard_world = a.shard_world;
+  p.owner = a.owner;
   p.out[0] = a.out0;
   p.out[1] = a.out1;
   p.out[2] = a.aux0;
@@ -268,12 +270,12 @@ int launch_add_counts(Ctx* ctx, int32_t* a, const int32_t* b, int64_t elems, cud
 // and — tile-sharded — only the blocks this rank owns (an eighth of them on 8 GPUs).  One CTA per
 // (matrix, block): 256 columns x 1 KiB.
 __global__ void __launch_bounds__(256)
-zero_counts_kernel(int32_t* counts, int64_t ld, int nblocks, int prod_mask, int rank, int world) {
+zero_counts_kernel(int32_t* counts, int64_t ld, int nblocks, int prod_mask, int rank, int world, const uint8_t* owner) {
   const int mat = blockIdx.z;
   if (!(prod_mask & (1 << mat))) return;
   const int bi = blockIdx.y, bj = blockIdx.x;   // row block, column block
   if (mat != TPG_MAT_HN && bi > bj) return;      // symmetric products live in the upper blocks
-  if (!block_owned(min(bi, bj), max(bi, bj), nblocks, rank, world)) return;
+  if (!block_owned(min(bi, bj), max(bi, bj), nblocks, rank, world, owner)) return;
   int4* base = reinterpret_cast<int4*>(counts + int64_t(mat) * ld * ld + int64_t(bj) * 256 * ld + int64_t(bi) * 256);
   const int64_t ld4 = ld / 4;
   const int4 z = make_int4(0, 0, 0, 0);
@@ -284,12 +286,12 @@ zero_counts_kernel(int32_t* counts, int64_t ld, int nblocks, int prod_mask, int 
 }
 
 int launch_zero_counts(Ctx* ctx, int32_t* counts, int64_t n, int prod_mask, int shard_rank, int shard_world,
-                       cudaStream_t st, const Err& E) {
+                       const uint8_t* d_owner, cudaStream_t st, const Err& E) {
   const int64_t ld = (n + 255) / 256 * 256;
   const int nb = int(ld / 256);
   if (nb > 65535) return E.fail(TPG_ERR_ARG, "zero_counts: too many blocks");
   zero_counts_kernel<<<dim3(nb, nb, TPG_NUM_COUNT_MATS), 256, 0, st>>>(counts, ld, nb, prod_mask, shard_rank,
-                                                                      shard_world > 1 ? shard_world : 1);
+                                                                      shard_world > 1 ? shard_world : 1, d_owner);
   TPG_CUDA_OK(cudaGetLastError(), E);
   ctx->launches++;
   return TPG_OK;

@@ -924,7 +924,7 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
           for (int prod = 0; prod < TPG_NUM_COUNT_MATS; ++prod) {
             if (!(a.prod_mask & (1 << prod))) continue;
             if (prod != TPG_MAT_HN && !upper) continue;
-            if (!block_owned(std::min(bi, bj), std::max(bi, bj), nblocks, a.shard_rank, a.shard_world)) continue;
+            if (!block_owned(std::min(bi, bj), std::max(bi, bj), nblocks, a.shard_rank, a.shard_world, a.owner)) continue;
             tiles.push_back({prod, int(ti), c0, n0, n1});
           }
         }
@@ -1077,7 +1077,7 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
             if (!(a.prod_mask & (1 << prod))) continue;
             if (prod != TPG_MAT_HN && !upper) continue;
             const int64_t lo = std::min(bi, bj), hi = std::max(bi, bj);
-            if (!block_owned(lo, hi, tiles_n, a.shard_rank, a.shard_world)) continue;
+            if (!block_owned(lo, hi, tiles_n, a.shard_rank, a.shard_world, a.owner)) continue;
             tiles.push_back({prod, int(ti), int(tj)});
           }
         }

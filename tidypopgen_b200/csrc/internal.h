@@ -48,7 +48,9 @@ struct Ctx {
   // Grow-only buffer cache, reused across jobs (cudaMalloc / cudaMallocHost / cudaFree are
   // slow and synchronising; a job must not pay them every call).  tpg_ctx_trim() frees it.
   struct Slot { void* p = nullptr; size_t cap = 0; };
-  Slot d_raw[2], d_gat[2], d_planes[2], h_pin[2], h_out[2], d_rows, d_cols, d_counts, d_out[4], d_red;
+  Slot d_raw[2], d_gat[2], d_planes[2], h_pin[2], h_out[2], d_rows, d_cols, d_counts, d_out[4], d_red, d_owner;
+  std::vector<uint8_t> h_owner;    // tile-sharding owner table of owner_key = "nblocks/world" (internal.h)
+  std::string owner_key;
   // count-matrix cache (tpg_config.cache_counts): d_counts holds all four products of the job
   // described by counts_key (file identity + indices); empty = nothing cached
   std::string counts_key;
@@ -135,6 +137,7 @@ struct GramArgs {
   bool mxf4 = false;  // planes are K-major 4-bit E2M1 (decode k4): kind::mxf4 pair kernel, 256 x 240 tiles
   int prod_mask;
   int shard_rank, shard_world;  // tile sharding (world <= 1: everything)
+  const uint8_t* owner = nullptr;  // HOST copy of the owner table (or nullptr): the work list is built on the host
   int32_t* counts;
   int64_t ld;
   int64_t* max_chain_out = nullptr;  // 4-bit route: longest accumulation chain (loci) of the launch
@@ -170,16 +173,26 @@ inline int64_t shard_region_blocks(int64_t nblocks, int world) {
   }
   return r;
 }
+// owner: optional table (one rank per region, row-major over the upper triangle of regions) — the balanced
+// assignment build_owner_table() makes for the large regions; nullptr = round-robin by region index.
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-inline bool block_owned(int64_t bi, int64_t bj, int64_t nblocks, int rank, int world) {
+inline bool block_owned(int64_t bi, int64_t bj, int64_t nblocks, int rank, int world, const uint8_t* owner = nullptr) {
   if (world <= 1) return true;
   const int64_t r = shard_region_blocks(nblocks, world);
   const int64_t ri = bi / r, rj = bj / r, nr = (nblocks + r - 1) / r;
   const int64_t idx = ri * nr - ri * (ri - 1) / 2 + (rj - ri);
-  return int(idx % world) == rank;
+  return owner ? int(owner[idx]) == rank : int(idx % world) == rank;
 }
+// With 3840 x 3840 regions there are few of them (105 for 50,000 individuals) and they differ in weight —
+// diagonal ones are half, the last row / column is a sliver — so dealing them round-robin leaves one of
+// 8 ranks with 18 % more work than the mean.  For R = 15 the regions are therefore assigned by weight:
+// largest first, each to the least loaded rank (ties: lower index, lower rank) — a pure function of
+// (nblocks, world), identical on every rank, in dist.py and here.  Empty for smaller regions (round-robin).
+void build_owner_table(int64_t nblocks, int world, std::vector<uint8_t>* out);
+// The table for (n_pad, world) on ctx's device (cached): *host / *dev = nullptr where round-robin applies.
+int owner_table(struct Ctx* ctx, int64_t n_pad, int world, const uint8_t** host, const uint8_t** dev, const struct Err& E);
 
 struct FinishArgs {
   int stat;
@@ -189,6 +202,7 @@ struct FinishArgs {
   int64_t m;        // total loci (adjusted_counts multiplies by it)
   int64_t n_short;  // allele-sharing pad-quirk constant
   int shard_rank, shard_world;  // TILES mode: only owned blocks are written
+  const uint8_t* owner = nullptr;  // device copy of the owner table (or nullptr)
   double* out0;     // device, n x n column-major
   double* out1;
   double* aux0;
@@ -213,7 +227,7 @@ int launch_add_counts(Ctx* ctx, int32_t* a, const int32_t* b, int64_t elems, cud
 // Zeroes what a job will accumulate into: the matrices of prod_mask, upper 256-blocks of the symmetric ones,
 // owned blocks only when tile-sharded (finish.cu).
 int launch_zero_counts(Ctx* ctx, int32_t* counts, int64_t n, int prod_mask, int shard_rank, int shard_world,
-                       cudaStream_t st, const Err& E);
+                       const uint8_t* d_owner, cudaStream_t st, const Err& E);
 
 int run_mma_peak(Ctx* ctx, int kind, double seconds, double* tops, double* ms_out, const Err& E);
 

@@ -68,13 +68,44 @@ def shard_region_blocks(nblocks: int, world: int) -> int:
     return r
 
 
+_owner_cache: dict = {}
+
+
+def owner_table(nblocks: int, world: int):
+    """Region -> rank for the large (15 x 15 block) regions — identical to build_owner_table() in csrc/api.cu:
+    regions sorted by weight (2 h w blocks off the diagonal, h w on it), largest first, each given to the
+    least loaded rank (ties: lower region index, lower rank).  None where round-robin applies (smaller regions)."""
+    key = (nblocks, world)
+    if key in _owner_cache:
+        return _owner_cache[key]
+    r = shard_region_blocks(nblocks, world)
+    table = None
+    if world > 1 and r == 15:
+        nr = (nblocks + r - 1) // r
+        regs = []
+        for ri in range(nr):
+            for rj in range(ri, nr):
+                h, w = min(r, nblocks - ri * r), min(r, nblocks - rj * r)
+                regs.append((-(h * w if ri == rj else 2 * h * w), ri * nr - ri * (ri - 1) // 2 + (rj - ri)))
+        regs.sort()
+        load = [0] * world
+        table = np.zeros(nr * (nr + 1) // 2, np.int64)
+        for negw, idx in regs:
+            best = min(range(world), key=lambda k: (load[k], k))
+            load[best] -= negw
+            table[idx] = best
+    _owner_cache[key] = table
+    return table
+
+
 def block_owner(bi: int, bj: int, nblocks: int, world: int) -> int:
     """Owner rank of output block (bi <= bj) of the 256 x 256 block grid — identical to
     block_owned() in csrc/internal.h."""
     r = shard_region_blocks(nblocks, world)
     ri, rj, nr = bi // r, bj // r, (nblocks + r - 1) // r
     idx = ri * nr - ri * (ri - 1) // 2 + (rj - ri)
-    return idx % world
+    table = owner_table(nblocks, world)
+    return int(table[idx]) if table is not None else idx % world
 
 
 def owned_mask(n: int, rank: int, world: int) -> np.ndarray:
@@ -85,7 +116,8 @@ def owned_mask(n: int, rank: int, world: int) -> np.ndarray:
     b = np.arange(n) // 256 // r
     bi, bj = np.minimum.outer(b, b), np.maximum.outer(b, b)
     idx = bi * nr - bi * (bi - 1) // 2 + (bj - bi)
-    return (idx % world) == rank
+    table = owner_table(nb, world)
+    return (table[idx] if table is not None else idx % world) == rank
 
 
 def choose_mode(n: int, world: int) -> str:
