@@ -420,6 +420,9 @@ def run_b200(args, rank, world, local):
         try:
             Xf = tpg.FBMCode256(path, n, m)
             devices = list(range(world))
+            # one process drives all N GPUs here, as an R session does; torchrun's LOCAL_WORLD_SIZE would otherwise
+            # make this rank's staging pool take only 1/N of the host cores (the other ranks are idle in a host barrier)
+            L.config(host_threads=min(32, len(os.sched_getaffinity(0))))
             king_host = np.zeros((n, n), np.float64, order="F")
 
             def e2e_call():
@@ -442,6 +445,7 @@ def run_b200(args, rank, world, local):
                            "(loci-sharded, int32 counts summed over NVLink by peer-reading add kernels, finished once)",
                    "stage_ms": {k: st[k] for k in ("ms_read", "ms_h2d", "ms_decode", "ms_gram", "ms_reduce", "ms_finish", "ms_d2h")},
                    "chunks": int(st["n_chunks"]), "packed_chunks": int(st["n_packed_chunks"]),
+                   "host_threads": L.config()["host_threads"],
                    "sampled_pairs_exact": bool(ok_pairs), "matches_device_run": ok_fp, "bk_write_s": t_write}
             # disk -> HBM streaming, reported separately from the kernels (north_star): the same call on a COLD
             # file (page cache dropped), read with O_DIRECT and through the page cache

@@ -490,9 +490,16 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
 
   // ---- chunk size (loci per GPU chunk), decoupled from R's block.size
   int64_t lc = job->gpu_chunk_loci;
-  // device bytes per locus: raw double buffer (largest form in use) + gathered copy + plane double buffer
+  // device bytes per locus: raw double buffer (largest form in use) + gathered copy + plane double buffer.
+  // Planes are 4-bit (half a byte per genotype and plane) when every chunk of the job takes the 4-bit route.
   const int64_t raw_per_locus = on_device ? 0 : std::max(direct_ok ? nrow : 0, pack_ok ? pk_stride : span);
-  const int64_t per_locus = 2 * raw_per_locus + (gp_any ? 2 * g_stride : 0) + 2 * int64_t(pl.nplanes) * pl.n_pad;
+  const bool all_q4 = q4_ok && !(C.pk2_i8 && (pack_ok || gp_any));
+  auto plane_bytes = [&](int64_t loci) {
+    return all_q4 ? size_t(pl.n_pad) * size_t(round_up(loci, 256) / 2) * size_t(pl.nplanes)
+                  : size_t(pl.n_pad) * size_t(loci) * size_t(pl.nplanes);
+  };
+  const int64_t per_locus = 2 * raw_per_locus + (gp_any ? 2 * g_stride : 0) +
+                            (all_q4 ? int64_t(pl.nplanes) * pl.n_pad : 2 * int64_t(pl.nplanes) * pl.n_pad);
   if (lc <= 0) {
     // device-resident bytes: nothing to overlap with (decode and gram contend for HBM when run
     // side by side — measured), so one big chunk = fewest launches and atomics
@@ -509,7 +516,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   {
     // Cap by free HBM — but cudaMemGetInfo is slow, so only ask when the cached buffers
     // would have to grow for this chunk size.
-    const size_t need_planes = size_t(pl.n_pad) * size_t(lc) * size_t(pl.nplanes);
+    const size_t need_planes = plane_bytes(lc);
     const size_t need_raw = on_device ? 0 : size_t(raw_per_locus) * size_t(lc) + 16;
     const size_t need_gat = gp_any ? size_t(g_stride) * size_t(lc) + 16 : 0;
     const bool two = pl.m_shard > lc;
@@ -521,9 +528,14 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       TPG_CUDA_OK(cudaMemGetInfo(&free_b, &total_b), E);
       const size_t held = ctx->d_planes[0].cap + ctx->d_planes[1].cap + ctx->d_raw[0].cap + ctx->d_raw[1].cap +
                           ctx->d_gat[0].cap + ctx->d_gat[1].cap;
-      const int64_t mem_cap = std::max<int64_t>(kLociPad, int64_t(double(free_b + held) * 0.45 / double(per_locus)));
-      lc = std::min(lc, mem_cap);
-      lc = std::max<int64_t>(kLociPad, lc / kLociPad * kLociPad);
+      // a job that would be ONE chunk needs every buffer once, not twice: C4's 37.6 GB of 4-bit planes fit
+      // beside 25 GB of bytes, 40 GB of counts and the 20 GB result, and the whole job is one decode + one Gram launch
+      const size_t single = need_planes + need_raw + need_gat;
+      if (two || double(single) > 0.85 * double(free_b + held)) {
+        const int64_t mem_cap = std::max<int64_t>(kLociPad, int64_t(double(free_b + held) * 0.45 / double(per_locus)));
+        lc = std::min(lc, mem_cap);
+        lc = std::max<int64_t>(kLociPad, lc / kLociPad * kLociPad);
+      }
     }
   }
   const int64_t n_chunks = (pl.m_shard + lc - 1) / lc;
@@ -536,7 +548,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   const int64_t stage_per_locus = pack_ok ? pk_stride : span;  // pinned staging bytes per locus
   for (int b = 0; b < 2 && b < n_chunks; ++b) {
     if (!scan) {
-      rc = ensure_slot(&ctx->d_planes[b], size_t(plane_stride) * pl.nplanes, false, "plane storage", E);
+      rc = ensure_slot(&ctx->d_planes[b], plane_bytes(lc), false, "plane storage", E);
       if (rc) return rc;
       B.d_planes[b] = static_cast<int8_t*>(ctx->d_planes[b].p);
     }
@@ -952,7 +964,9 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
 // cudaMemcpy straight into pageable memory runs at ~3 GB/s, first-touch faults included.
 static int results_to_host(Ctx* ctx, const void* const* dev, void* const* host, int count, size_t bytes,
                            int64_t* bytes_d2h, const Err& E) {
-  const size_t kPiece = size_t(32) << 20;
+  // (128 MB pieces: handing a piece to the worker pool costs a wake-up and a tail; at 32 MB that was a third of the
+  //  0.9 ms a piece took)
+  const size_t kPiece = size_t(128) << 20;
   const size_t piece = std::min(bytes, kPiece);
   int rc = TPG_OK;
   for (int b = 0; b < 2 && rc == TPG_OK; ++b)
