@@ -290,3 +290,26 @@ def test_wide_gram_kernel_whole_jobs(n_tot, rk, tpg_cfg):
     ref_a = O.snp_allele_sharing(raw, n_tot, m_tot, rows, None, block_size_=500)
     a, num, den = tpg.snp_allele_sharing_counts(X, rows, None, block_size=500)
     assert np.array_equal(num, ref_a["num"]) and np.array_equal(den, ref_a["denom"]) and same(a, ref_a["as"])
+
+
+@pytest.mark.parametrize("shard", ["loci", "tiles"])
+def test_multi_gpu_large_result_comes_home_over_every_link(shard):
+    """tpg_pairwise_multi with a result of >= 256 MB: finished on the first device into device buffers, then
+    every device pulls its slab of columns over NVLink and sends it home over its own PCIe link; the count
+    matrices are summed block-wise (upper blocks of the symmetric products).  Identical to one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(91)
+    n, m = 6100, 2048
+    raw = random_bk(rng, n, m, 0.05)
+    X = fbm_of(raw, n, m)
+    devices = list(range(min(4, torch.cuda.device_count())))
+    ref = tpg.snp_king(X)
+    got = tpg.snp_king(X, devices=devices, shard=shard)
+    assert same(got, ref)
+    many1 = tpg.snp_pairwise_many(X, ("king", "ibs_raw", "allele_sharing"), block_size=500)
+    manyN = tpg.snp_pairwise_many(X, ("king", "ibs_raw", "allele_sharing"), block_size=500, devices=devices, shard=shard)
+    assert same(manyN["king"], many1["king"]) and same(manyN["allele_sharing"], many1["allele_sharing"])
+    assert np.array_equal(manyN["ibs_raw"]["ibs"], many1["ibs_raw"]["ibs"])
+    assert np.array_equal(manyN["ibs_raw"]["valid_n"], many1["ibs_raw"]["valid_n"])

@@ -1170,6 +1170,82 @@ static int finish_many(Ctx* c, const tpg_job* job, const int32_t* stats, int nst
   return rc;
 }
 
+// Multi-GPU hand-back of large results: every statistic is finished on the first device INTO device
+// buffers, then each device pulls its slab of columns over NVLink and sends it home over ITS OWN PCIe link
+// (own pinned bounce buffers; the copies into the caller's pageable matrix go through the shared worker pool).
+// One link carries a 20 GB matrix in ~0.4 s at best; eight carry it as fast as the host can take it.
+static int finish_many_multilink(const std::vector<Ctx*>& ctxs, const tpg_job* job, const int32_t* stats, int nstats,
+                                 const int32_t* d_counts, tpg_result* results, const Err& E) {
+  Ctx* c0 = ctxs[0];
+  const int ndev = int(ctxs.size());
+  const int64_t n = job->ind_row ? job->n : job->nrow_total;
+  const size_t bytes = sizeof(double) * size_t(n) * size_t(n);
+  for (int k = 0; k < nstats; ++k) {
+    tpg_job jk = *job;
+    jk.stat = stats[k];
+    double* host[4] = {results[k].out0, results[k].out1, results[k].aux0, results[k].aux1};
+    tpg_result rd = results[k];
+    double* dev0[4] = {nullptr, nullptr, nullptr, nullptr};
+    TPG_CUDA_OK(cudaSetDevice(c0->device), E);
+    for (int o = 0; o < 4; ++o) {
+      if (!host[o]) continue;
+      int rc = ensure_slot(&c0->d_out[o], bytes, false, "result matrix", E);
+      if (rc) return rc;
+      dev0[o] = static_cast<double*>(c0->d_out[o].p);
+    }
+    rd.out0 = dev0[0]; rd.out1 = dev0[1]; rd.aux0 = dev0[2]; rd.aux1 = dev0[3];
+    rd.out_on_device = 1;
+    int rc = finish_impl(c0, &jk, d_counts, &rd, E);   // device -> device: no D2H here
+    results[k].stats = rd.stats;
+    if (rc) return rc;
+    const double t0 = now_ms();
+    std::vector<int> rcs(ndev, TPG_OK);
+    std::vector<std::string> msgs(ndev);
+    std::vector<int64_t> moved(ndev, 0);
+    std::vector<std::thread> th;
+    for (int r = 0; r < ndev; ++r) {
+      th.emplace_back([&, r] {
+        char buf[512] = {0};
+        Err Er{buf, sizeof buf};
+        Ctx* c = ctxs[r];
+        int rcr = TPG_OK;
+        const int64_t j0 = n * r / ndev, j1 = n * (r + 1) / ndev;
+        const size_t off = size_t(j0) * size_t(n), len = sizeof(double) * size_t(j1 - j0) * size_t(n);
+        if (len == 0) return;
+        if (cudaSetDevice(c->device) != cudaSuccess) rcr = Er.fail(TPG_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+        for (int o = 0; o < 4 && rcr == TPG_OK; ++o) {
+          if (!host[o]) continue;
+          const void* src = dev0[o] + off;
+          if (r != 0 && c->device != c0->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(c0->device, 0);
+            if (e != cudaSuccess) cudaGetLastError();  // already enabled / not possible: the copy still works (staged)
+            rcr = ensure_slot(&c->d_out[o], len, false, "result slab", Er);
+            if (rcr) break;
+            e = cudaMemcpyPeerAsync(c->d_out[o].p, c->device, src, c0->device, len, c->s_compute);
+            if (e != cudaSuccess) { rcr = Er.fail(TPG_ERR_CUDA, "peer copy of a result slab failed: %s", cudaGetErrorString(e)); break; }
+            src = c->d_out[o].p;
+          }
+          const void* dv[1] = {src};
+          void* hv[1] = {host[o] + off};
+          c->ev_plain_used = 0;
+          rcr = results_to_host(c, dv, hv, 1, len, &moved[r], Er);
+          if (rcr == TPG_OK && cudaStreamSynchronize(c->s_compute) != cudaSuccess) rcr = Er.fail(TPG_ERR_CUDA, "D2H of a result slab failed");
+        }
+        rcs[r] = rcr;
+        msgs[r] = buf;
+      });
+    }
+    for (auto& t : th) t.join();
+    TPG_CUDA_OK(cudaSetDevice(c0->device), E);
+    for (int r = 0; r < ndev; ++r) {
+      if (rcs[r]) return E.fail(rcs[r], "device %d (rank %d): %s", ctxs[r]->device, r, msgs[r].c_str());
+      results[k].stats.bytes_d2h += moved[r];
+    }
+    results[k].stats.ms_d2h += now_ms() - t0;
+  }
+  return TPG_OK;
+}
+
 // In-process multi-GPU job (the R process is one process): one host thread per device
 // accumulates its shard (loci slice, or owned output blocks) into its own count matrices;
 // the int32 matrices are then summed onto the first device over NVLink (peer copies) and
@@ -1286,16 +1362,20 @@ static int pairwise_multi(const tpg_job* job, const int32_t* stats, int nstats, 
         if (rc) return rc;
         tmp = static_cast<int32_t*>(cr->d_out[3].p);
       }
-      for (int k = 0; k < TPG_NUM_COUNT_MATS; ++k) {
-        if (!(mask & (1 << k))) continue;
-        int32_t* mine = static_cast<int32_t*>(cr->d_counts.p) + k * ms;
-        const int32_t* theirs = static_cast<const int32_t*>(cp->d_counts.p) + k * ms;
-        if (!direct) {
-          TPG_CUDA_OK(cudaMemcpyPeerAsync(tmp, cr->device, theirs, cp->device, sizeof(int32_t) * size_t(ms), cr->s_compute), E);
-          theirs = tmp;
-        }
-        int rc = launch_add_counts(cr, mine, theirs, ms, cr->s_compute, E);
+      if (direct) {
+        // one launch: the blocks the job accumulated, read straight out of the peer's HBM
+        int rc = launch_add_counts_blocks(cr, static_cast<int32_t*>(cr->d_counts.p), static_cast<const int32_t*>(cp->d_counts.p),
+                                          n, mask, cr->s_compute, E);
         if (rc) return rc;
+      } else {
+        for (int k = 0; k < TPG_NUM_COUNT_MATS; ++k) {
+          if (!(mask & (1 << k))) continue;
+          int32_t* mine = static_cast<int32_t*>(cr->d_counts.p) + k * ms;
+          const int32_t* theirs = static_cast<const int32_t*>(cp->d_counts.p) + k * ms;
+          TPG_CUDA_OK(cudaMemcpyPeerAsync(tmp, cr->device, theirs, cp->device, sizeof(int32_t) * size_t(ms), cr->s_compute), E);
+          int rc = launch_add_counts(cr, mine, tmp, ms, cr->s_compute, E);
+          if (rc) return rc;
+        }
       }
     }
     for (int r : receivers) {  // the step is done when every pair is
@@ -1305,7 +1385,11 @@ static int pairwise_multi(const tpg_job* job, const int32_t* stats, int nstats, 
   }
   TPG_CUDA_OK(cudaSetDevice(c0->device), E);
   const double ms_reduce = now_ms() - t_red;
-  int rc = finish_many(c0, &j0, stats, nstats, static_cast<int32_t*>(c0->d_counts.p), results, E);
+  // large host-bound results go home over every device's PCIe link, small ones (or device-resident ones) from the first
+  bool multilink = ndev > 1 && sizeof(double) * size_t(n) * size_t(n) >= (size_t(256) << 20);
+  for (int k = 0; k < nstats; ++k) multilink = multilink && !results[k].out_on_device;
+  int rc = multilink ? finish_many_multilink(ctxs, &j0, stats, nstats, static_cast<int32_t*>(c0->d_counts.p), results, E)
+                     : finish_many(c0, &j0, stats, nstats, static_cast<int32_t*>(c0->d_counts.p), results, E);
   if (rc == TPG_OK && !key.empty()) { c0->counts_key = key; c0->counts_key_n = n; }
   // stats: stage times are the max over devices (they ran side by side); bytes and MACs add up
   tpg_stats& S = results[0].stats;

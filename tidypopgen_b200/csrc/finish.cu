@@ -263,6 +263,39 @@ int launch_add_counts(Ctx* ctx, int32_t* a, const int32_t* b, int64_t elems, cud
   return TPG_OK;
 }
 
+// Block-wise a += b over what a job accumulated: the matrices of prod_mask, and of the symmetric ones only the
+// 256-blocks on or above the diagonal — a third less NVLink traffic than whole matrices for KING (b is a
+// peer's buffer, read straight out of its HBM).  One CTA per (matrix, block).
+__global__ void __launch_bounds__(256)
+add_counts_blocks_kernel(int32_t* a, const int32_t* b, int64_t ld, int prod_mask) {
+  const int mat = blockIdx.z;
+  if (!(prod_mask & (1 << mat))) return;
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (mat != TPG_MAT_HN && bi > bj) return;
+  const int64_t off = int64_t(mat) * ld * ld + int64_t(bj) * 256 * ld + int64_t(bi) * 256;
+  int4* pa = reinterpret_cast<int4*>(a + off);
+  const int4* pb = reinterpret_cast<const int4*>(b + off);
+  const int64_t ld4 = ld / 4;
+  const int q = threadIdx.x & 63, c0 = threadIdx.x >> 6;
+#pragma unroll 4
+  for (int c = c0; c < 256; c += 4) {
+    int4 x = pa[int64_t(c) * ld4 + q];
+    const int4 y = pb[int64_t(c) * ld4 + q];
+    x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    pa[int64_t(c) * ld4 + q] = x;
+  }
+}
+
+int launch_add_counts_blocks(Ctx* ctx, int32_t* a, const int32_t* b, int64_t n, int prod_mask, cudaStream_t st, const Err& E) {
+  const int64_t ld = (n + 255) / 256 * 256;
+  const int nb = int(ld / 256);
+  if (nb > 65535) return E.fail(TPG_ERR_ARG, "add_counts: too many blocks");
+  add_counts_blocks_kernel<<<dim3(nb, nb, TPG_NUM_COUNT_MATS), 256, 0, st>>>(a, b, ld, prod_mask);
+  TPG_CUDA_OK(cudaGetLastError(), E);
+  ctx->launches++;
+  return TPG_OK;
+}
+
 // ------------------------------------------------------------------ zeroing the count matrices
 // A job's accumulators start at zero.  A plain memset of the whole buffer (16 n_pad^2 bytes: 40 GB at
 // n = 50,000) writes four full matrices; what the Gram epilogue and finish ever touch is less: only the

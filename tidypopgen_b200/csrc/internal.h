@@ -224,6 +224,8 @@ int run_wg17(Ctx* ctx, const double* as_in, bool on_device, int64_t n, const int
 
 int check_err_flag(Ctx* ctx, const Err& E);
 int launch_add_counts(Ctx* ctx, int32_t* a, const int32_t* b, int64_t elems, cudaStream_t st, const Err& E);
+// a += b over the 256-blocks a job accumulated (matrices of prod_mask, upper blocks of the symmetric ones); b may be a peer's buffer.
+int launch_add_counts_blocks(Ctx* ctx, int32_t* a, const int32_t* b, int64_t n, int prod_mask, cudaStream_t st, const Err& E);
 // Zeroes what a job will accumulate into: the matrices of prod_mask, upper 256-blocks of the symmetric ones,
 // owned blocks only when tile-sharded (finish.cu).
 int launch_zero_counts(Ctx* ctx, int32_t* counts, int64_t n, int prod_mask, int shard_rank, int shard_world,
