@@ -195,6 +195,10 @@ typedef struct tpg_config {
   int32_t gram_no_trim;       /* TPG_GRAM_NO_TRIM: 1 = do not trim the last tile column to the valid individuals */
   int32_t gram_wide;          /* TPG_GRAM_WIDE: 4-bit route, 256 x 480 tiles (one A stream feeds two B tiles: a quarter  *
                                * less L2 traffic per MAC). 0 = where tiles are plentiful (default), 1 = never, 2 = always */
+  int32_t gram_l2_rows;       /* TPG_GRAM_L2_ROWS / TPG_GRAM_L2_COLS: the L2 neighbourhood of the Gram work list, in 256-row and   *
+                               * 240- (int8: 256-) column tiles; 0 = 8 x 8 (2048 x 1920)                                          */
+  int32_t gram_l2_cols;
+  int32_t gram_order;         /* TPG_GRAM_ORDER: 0 = product-major inside a neighbourhood (default), 1 = tile-major (round 1)     */
   int32_t pack_mode;          /* TPG_PACK_MODE: 0 = hybrid (pack or raw DMA per chunk), 1 = never pack (TPG_NO_PACK), *
                                * 2 = always pack (TPG_NO_HYBRID) */
   int32_t pk2_i8;             /* TPG_PK2_I8: 1 = packed chunks take the int8 kernels */

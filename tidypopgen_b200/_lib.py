@@ -114,6 +114,9 @@ class Config(C.Structure):
         ("gram_clusters", C.c_int32),
         ("gram_no_trim", C.c_int32),
         ("gram_wide", C.c_int32),
+        ("gram_l2_rows", C.c_int32),
+        ("gram_l2_cols", C.c_int32),
+        ("gram_order", C.c_int32),
         ("pack_mode", C.c_int32),
         ("pk2_i8", C.c_int32),
         ("no_compact", C.c_int32),

@@ -46,6 +46,9 @@ void tpg_config_init(tpg_config* c) {
   c->gram_clusters = env_int("TPG_GRAM_CLUSTERS", 0);
   c->gram_no_trim = env_set("TPG_GRAM_NO_TRIM") ? 1 : 0;
   c->gram_wide = env_int("TPG_GRAM_WIDE", 0);
+  c->gram_l2_rows = env_int("TPG_GRAM_L2_ROWS", 0);
+  c->gram_l2_cols = env_int("TPG_GRAM_L2_COLS", 0);
+  c->gram_order = env_int("TPG_GRAM_ORDER", 0);
   c->pack_mode = env_int("TPG_PACK_MODE", 0);
   if (env_set("TPG_NO_PACK")) c->pack_mode = 1;
   else if (env_set("TPG_NO_HYBRID")) c->pack_mode = 2;
@@ -77,6 +80,8 @@ int tpg_config_set(const tpg_config* c, char* err, size_t errlen) {
   if (c->gram_route < 0 || c->gram_route > 1) return fail("gram_route must be 0 (4-bit where exact) or 1 (int8)");
   if (c->gram_ctas < 0 || c->gram_ctas > 2) return fail("gram_ctas must be 0, 1 or 2");
   if (c->gram_ksplit < 0 || c->gram_max_kblocks < 0 || c->gram_clusters < 0) return fail("gram_* must be >= 0");
+  if (c->gram_l2_rows < 0 || c->gram_l2_cols < 0 || c->gram_l2_rows > 4096 || c->gram_l2_cols > 4096) return fail("gram_l2_rows / gram_l2_cols out of range");
+  if (c->gram_order < 0 || c->gram_order > 1) return fail("gram_order must be 0 or 1");
   if (c->gram_wide < 0 || c->gram_wide > 2) return fail("gram_wide must be 0 (auto), 1 (never) or 2 (always)");
   if (c->pack_mode < 0 || c->pack_mode > 2) return fail("pack_mode must be 0 (hybrid), 1 (never) or 2 (always)");
   if (c->gather_smem_kb < 0 || c->gather_smem_kb > 200) return fail("gather_smem_kb must be in [0, 200]");

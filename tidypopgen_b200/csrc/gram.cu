@@ -906,13 +906,19 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   } else {
     for (const auto& c : cols) wcols.push_back({c.first, c.second, 0});
   }
-  const int64_t RI = 4;
-  // L2 neighbourhoods of about 1024 columns: 2 wide / 4 narrow tiles (5 where a 1024-column region ends in a 64-column one)
-  const size_t RJ = wide ? (tiles_per_region == 5 ? 3 : 2) : (tiles_per_region == 5 ? 5 : 4);
+  // L2 neighbourhoods (tpg_config.gram_l2_rows x gram_l2_cols, in 256-row / 240-column tiles; default 2048 x 1920)
+  // and, inside one, PRODUCT-major order: the CTA pairs resident together stream the panels of ONE pair of planes
+  // (2048 + 1920 rows x 16 KiB per 128-k-block item = 65 MB: L2-resident) instead of all three planes of a
+  // 1024 x 1024 neighbourhood (round 1's order; ncu at C4: 3.4 TB of DRAM reads for 37.6 GB of planes).
+  const int64_t RI = std::max<int64_t>(1, C.gram_l2_rows > 0 ? C.gram_l2_rows : 8);
+  const size_t rj240 = size_t(std::max(1, C.gram_l2_cols > 0 ? int(C.gram_l2_cols) : 8));
+  const size_t RJ = wide ? std::max<size_t>(1, rj240 / 2) : rj240;
+  const bool prod_major = C.gram_order == 0;
   struct T { int prod, ti, col0, n0, n1; };
   std::vector<T> tiles;
   for (size_t rj = 0; rj < wcols.size(); rj += RJ)
     for (int64_t ri = 0; ri < tiles_m; ri += RI)
+      for (int pp = 0; pp < (prod_major ? TPG_NUM_COUNT_MATS : 1); ++pp)
       for (size_t cj = rj; cj < std::min(rj + RJ, wcols.size()); ++cj)
         for (int64_t ti = ri; ti < std::min(ri + RI, tiles_m); ++ti) {
           if (kPairTileM * ti >= a.n) continue;  // rows of padding individuals only
@@ -920,8 +926,8 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
           const int c_end = c0 + (n1 ? kQTileN + n1 : n0);
           const bool upper = c_end - 1 >= kPairTileM * ti;
           if (!tile_wanted(a, kPairTileM * ti, kPairTileM * (ti + 1), c0, c_end)) continue;
-          const int64_t bi = ti, bj = c0 / 256;  // 256-blocks; ownership is per 1024 region, so any block of the tile will do
-          for (int prod = 0; prod < TPG_NUM_COUNT_MATS; ++prod) {
+          const int64_t bi = ti, bj = c0 / 256;  // 256-blocks; a tile never straddles an ownership region, so any block of it will do
+          for (int prod = prod_major ? pp : 0; prod < (prod_major ? pp + 1 : TPG_NUM_COUNT_MATS); ++prod) {
             if (!(a.prod_mask & (1 << prod))) continue;
             if (prod != TPG_MAT_HN && !upper) continue;
             if (!block_owned(std::min(bi, bj), std::max(bi, bj), nblocks, a.shard_rank, a.shard_world, a.owner)) continue;
@@ -947,8 +953,9 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
     *macs_out = cells * a.lc_pad;
   }
   char key[200];
-  snprintf(key, sizeof key, "q4%c/%lld/%lld/%lld/%d/%d/%d/%d/%llx", wide ? 'w' : 'p', (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad,
-           a.prod_mask, ks, a.shard_rank, a.shard_world, (unsigned long long)(a.group_sorted ? a.group_sig | 1u : 0u));
+  snprintf(key, sizeof key, "q4%c/%lld/%lld/%lld/%d/%d/%d/%d/%llx/%lld/%zu/%d", wide ? 'w' : 'p', (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad,
+           a.prod_mask, ks, a.shard_rank, a.shard_world, (unsigned long long)(a.group_sorted ? a.group_sig | 1u : 0u),
+           (long long)RI, RJ, int(prod_major));
   if (ctx->items_key != key) {
     std::vector<WorkItem>& items = ctx->h_items;
     items.clear();
@@ -1064,16 +1071,25 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   // ---- tile list in L2-friendly order: 1024x1024 regions, then tiles, then products
   struct T { int prod, ti, tj; };
   std::vector<T> tiles;
-  const int64_t RI = 1024 / tile_m, RJ = 4;
+  // L2 neighbourhoods (tpg_config.gram_l2_rows / gram_l2_cols, in 256-row / 256-column tiles; default 2048 x 2048)
+  // and, inside one, PRODUCT-major order: CTAs resident together then stream the panels of ONE pair of planes —
+  // 2 x 2048 rows x 16 KiB per 128-k-block item = 67 MB, which stays in the 126 MB L2 — instead of all three
+  // planes of a 1024 x 1024 neighbourhood at once (round 1's order: tile-major, products innermost; ncu at C4:
+  // 13 - 16 TB of DRAM reads for 75 GB of int8 planes, the kernel was HBM-bound at 5.4 - 6.3 TB/s).
+  const tpg_config C2 = cfg();
+  const int64_t RI = std::max<int64_t>(1, (C2.gram_l2_rows > 0 ? C2.gram_l2_rows : 8) * 256 / tile_m);
+  const int64_t RJ = std::max<int64_t>(1, C2.gram_l2_cols > 0 ? C2.gram_l2_cols : 8);
+  const bool prod_major = C2.gram_order == 0;
   for (int64_t rj = 0; rj < tiles_n; rj += RJ)
     for (int64_t ri = 0; ri < tiles_m; ri += RI)
+      for (int pp = 0; pp < (prod_major ? TPG_NUM_COUNT_MATS : 1); ++pp)
       for (int64_t tj = rj; tj < std::min(rj + RJ, tiles_n); ++tj)
         for (int64_t ti = ri; ti < std::min(ri + RI, tiles_m); ++ti) {
           const bool upper = kTileN * tj + (kTileN - 1) >= tile_m * ti;
           if (!tile_wanted(a, tile_m * ti, tile_m * (ti + 1), kTileN * tj, kTileN * (tj + 1))) continue;
           // 256x256 ownership block of the tile; lower blocks mirror
           const int64_t bi = ti * tile_m / 256, bj = tj;
-          for (int prod = 0; prod < TPG_NUM_COUNT_MATS; ++prod) {
+          for (int prod = prod_major ? pp : 0; prod < (prod_major ? pp + 1 : TPG_NUM_COUNT_MATS); ++prod) {
             if (!(a.prod_mask & (1 << prod))) continue;
             if (prod != TPG_MAT_HN && !upper) continue;
             const int64_t lo = std::min(bi, bj), hi = std::max(bi, bj);
@@ -1099,9 +1115,9 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
     *macs_out = cells * a.lc_pad;
   }
   char key[200];
-  snprintf(key, sizeof key, "%lld/%lld/%lld/%d/%d/%d/%d/%d/%d/%llx", (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad,
+  snprintf(key, sizeof key, "%lld/%lld/%lld/%d/%d/%d/%d/%d/%d/%llx/%lld/%lld/%d", (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad,
            a.prod_mask, a.shard_rank, a.shard_world, ks, tile_m, int(trim_n),
-           (unsigned long long)(a.group_sorted ? a.group_sig | 1u : 0u));
+           (unsigned long long)(a.group_sorted ? a.group_sig | 1u : 0u), (long long)RI, (long long)RJ, int(prod_major));
   if (ctx->items_key != key) {
     std::vector<WorkItem>& items = ctx->h_items;
     items.clear();
