@@ -156,13 +156,15 @@ def test_raw_counts_written_into_fbm_backing_files(tmp_path):
 
 # ------------------------------------------------------------------ gathered rows through shared memory
 
+@pytest.mark.parametrize("layout", [0, 1], ids=["transposed_t4", "column_major"])
 @pytest.mark.parametrize("source", ["file", "host", "pinned"])
 @pytest.mark.parametrize("rk", ["shuffle", "dup", "subset"])
-def test_host_sources_gathered_rows_cross_packed(source, rk):
+def test_host_sources_gathered_rows_cross_packed(source, rk, layout, tpg_cfg):
     """ind.row in arbitrary order on file / host / pinned sources: the row span is 2-bit packed while staging,
     crosses PCIe at 0.25 B per genotype and is gathered on the device (gather_pack_kernel<packed>) — every
     chunk packed, every statistic exact; the int8 route and the raw route agree."""
     import torch
+    tpg_cfg(gather_layout=layout)
     rng = np.random.default_rng(51)
     n_tot, m_tot = 1237, 3300
     raw = random_bk(rng, n_tot, m_tot, 0.08, codes=(0, 1, 2, 3, 4, 5, 6, 255))
@@ -209,11 +211,14 @@ def test_gathered_rows_of_long_columns(where):
     assert np.array_equal(K, ref["K"]) and np.array_equal(N, ref["N_Aa_i"]) and same(king, ref["king"])
 
 
-def test_gather_pack_kernel_edges():
+@pytest.mark.parametrize("layout", [0, 1], ids=["transposed_t4", "column_major"])
+def test_gather_pack_kernel_edges(layout, tpg_cfg):
     """Row spans that start / end at the first / last byte of the allocation, n not a multiple of 16,
-    duplicated rows, a single locus: dense result equals the oracle."""
+    duplicated rows, a single locus, loci counts that are not multiples of 4: dense result equals the oracle,
+    for both staging layouts of gather_pack."""
+    tpg_cfg(gather_layout=layout)
     rng = np.random.default_rng(53)
-    for n_tot, m_tot, n_sel in ((17, 1, 5), (64, 3, 64), (1000, 40, 999), (4099, 7, 33)):
+    for n_tot, m_tot, n_sel in ((17, 1, 5), (64, 3, 64), (1000, 40, 999), (4099, 7, 33), (10000, 1030, 7000)):
         raw = random_bk(rng, n_tot, m_tot, 0.1, codes=(0, 1, 2, 3, 7, 200))
         rows = rng.choice(np.arange(1, n_tot + 1), size=n_sel, replace=True).astype(np.int32)
         rows[0], rows[-1] = 1, n_tot

@@ -121,6 +121,7 @@ class Config(C.Structure):
         ("pk2_i8", C.c_int32),
         ("no_compact", C.c_int32),
         ("gather_smem_kb", C.c_int32),
+        ("gather_layout", C.c_int32),
         ("io_mode", C.c_int32),
         ("no_thp", C.c_int32),
         ("decode_k4_v1", C.c_int32),

@@ -55,6 +55,7 @@ void tpg_config_init(tpg_config* c) {
   c->pk2_i8 = env_set("TPG_PK2_I8") ? 1 : 0;
   c->no_compact = env_set("TPG_NO_COMPACT") ? 1 : 0;
   c->gather_smem_kb = env_int("TPG_GATHER_SMEM_KB", 0);
+  c->gather_layout = env_int("TPG_GATHER_LAYOUT", 0);
   c->io_mode = env_int("TPG_IO_MODE", 0);
   if (env_set("TPG_NO_PREAD")) c->io_mode = 2;
   c->no_thp = env_set("TPG_NO_THP") ? 1 : 0;
@@ -84,6 +85,7 @@ int tpg_config_set(const tpg_config* c, char* err, size_t errlen) {
   if (c->gram_order < 0 || c->gram_order > 1) return fail("gram_order must be 0 or 1");
   if (c->gram_wide < 0 || c->gram_wide > 2) return fail("gram_wide must be 0 (auto), 1 (never) or 2 (always)");
   if (c->pack_mode < 0 || c->pack_mode > 2) return fail("pack_mode must be 0 (hybrid), 1 (never) or 2 (always)");
+  if (c->gather_layout < 0 || c->gather_layout > 1) return fail("gather_layout must be 0 or 1");
   if (c->gather_smem_kb < 0 || c->gather_smem_kb > 200) return fail("gather_smem_kb must be in [0, 200]");
   if (c->io_mode < 0 || c->io_mode > 2) return fail("io_mode must be 0 (page cache), 1 (O_DIRECT) or 2 (mmap)");
   if (c->host_threads < 0 || c->host_threads > 1024) return fail("host_threads out of range");
