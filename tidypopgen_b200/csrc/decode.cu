@@ -1129,7 +1129,7 @@ scan_counts_kernel(const DecodeParams p, const ScanParams sp) {
 // Contiguous rows and loci only (launch_scan routes everything else to scan_counts_kernel); same outputs,
 // bit for bit.
 template <bool kImpute>
-__global__ void __launch_bounds__(kDecThreads)
+__global__ void __launch_bounds__(kDecThreads, 4)
 scan_counts_fast_kernel(const DecodeParams p, const ScanParams sp) {
   __shared__ uint32_t part[kDecThreads / 32][16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

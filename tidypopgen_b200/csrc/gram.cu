@@ -909,7 +909,9 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   // L2 neighbourhoods (tpg_config.gram_l2_rows x gram_l2_cols, in 256-row / 240-column tiles; default 2048 x 1920)
   // and, inside one, PRODUCT-major order: the CTA pairs resident together stream the panels of ONE pair of planes
   // (2048 + 1920 rows x 16 KiB per 128-k-block item = 65 MB: L2-resident) instead of all three planes of a
-  // 1024 x 1024 neighbourhood (round 1's order; ncu at C4: 3.4 TB of DRAM reads for 37.6 GB of planes).
+  // 1024 x 1024 neighbourhood (round 1's order; ncu at C4: 3.4 TB of DRAM reads for 37.6 GB of planes).  For this
+  // kernel the order turned out not to matter (scripts/order_sweep.py: 798 - 806 ms for every variant at C4): it is
+  // bound by the L2 -> shared-memory stream and the power cap, not by HBM.
   const int64_t RI = std::max<int64_t>(1, C.gram_l2_rows > 0 ? C.gram_l2_rows : 8);
   const size_t rj240 = size_t(std::max(1, C.gram_l2_cols > 0 ? int(C.gram_l2_cols) : 8));
   const size_t RJ = wide ? std::max<size_t>(1, rj240 / 2) : rj240;
@@ -1071,14 +1073,15 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   // ---- tile list in L2-friendly order: 1024x1024 regions, then tiles, then products
   struct T { int prod, ti, tj; };
   std::vector<T> tiles;
-  // L2 neighbourhoods (tpg_config.gram_l2_rows / gram_l2_cols, in 256-row / 256-column tiles; default 2048 x 2048)
+  // L2 neighbourhoods (tpg_config.gram_l2_rows / gram_l2_cols, in 256-row / 256-column tiles; default 1024 x 1024)
   // and, inside one, PRODUCT-major order: CTAs resident together then stream the panels of ONE pair of planes —
-  // 2 x 2048 rows x 16 KiB per 128-k-block item = 67 MB, which stays in the 126 MB L2 — instead of all three
-  // planes of a 1024 x 1024 neighbourhood at once (round 1's order: tile-major, products innermost; ncu at C4:
-  // 13 - 16 TB of DRAM reads for 75 GB of int8 planes, the kernel was HBM-bound at 5.4 - 6.3 TB/s).
+  // 2 x 1024 rows x 16 KiB per 128-k-block item = 33 MB, L2-resident — instead of all three planes of the
+  // neighbourhood at once (round 1's order: tile-major, products innermost; ncu at C4: 13 - 16 TB of DRAM reads for
+  // 75 GB of int8 planes, the kernel ran at 5.4 - 6.3 TB/s of HBM).  Measured at C4 (scripts/order_sweep.py,
+  // profiles/r02_order_sweep.jsonl): 2174 -> 1939 ms; larger neighbourhoods are slower again (2048 x 2048: 2302 ms).
   const tpg_config C2 = cfg();
-  const int64_t RI = std::max<int64_t>(1, (C2.gram_l2_rows > 0 ? C2.gram_l2_rows : 8) * 256 / tile_m);
-  const int64_t RJ = std::max<int64_t>(1, C2.gram_l2_cols > 0 ? C2.gram_l2_cols : 8);
+  const int64_t RI = std::max<int64_t>(1, (C2.gram_l2_rows > 0 ? C2.gram_l2_rows : 4) * 256 / tile_m);
+  const int64_t RJ = std::max<int64_t>(1, C2.gram_l2_cols > 0 ? C2.gram_l2_cols : 4);
   const bool prod_major = C2.gram_order == 0;
   for (int64_t rj = 0; rj < tiles_n; rj += RJ)
     for (int64_t ri = 0; ri < tiles_m; ri += RI)
