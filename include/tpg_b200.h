@@ -204,8 +204,8 @@ typedef struct tpg_config {
   int32_t pk2_i8;             /* TPG_PK2_I8: 1 = packed chunks take the int8 kernels */
   int32_t no_compact;         /* TPG_NO_COMPACT: 1 = gathered rows are gathered inside the decode kernel */
   int32_t gather_smem_kb;     /* TPG_GATHER_SMEM_KB: shared memory per gather_pack CTA, 0 = 52 (four CTAs per SM) */
-  int32_t gather_layout;      /* TPG_GATHER_LAYOUT: 0 = transposed staging, four loci per shared-memory word (default), *
-                               * 1 = column-major staging (the first build; also what very long columns fall back to)  */
+  int32_t gather_layout;      /* TPG_GATHER_LAYOUT: 0 = column-major staging (default), 1 = transposed staging, four loci *
+                               * per shared-memory word (fewer bank conflicts, but measured slower: DESIGN.md section 4)   */
   int32_t io_mode;            /* TPG_IO_MODE: file sources. 0 = auto (pread through the page cache), 1 = O_DIRECT *
                                * (cold files, bypasses the page cache), 2 = mmap (TPG_NO_PREAD) */
   int32_t no_thp;             /* TPG_NO_THP: 1 = no MADV_HUGEPAGE on result matrices */

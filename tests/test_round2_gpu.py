@@ -156,7 +156,7 @@ def test_raw_counts_written_into_fbm_backing_files(tmp_path):
 
 # ------------------------------------------------------------------ gathered rows through shared memory
 
-@pytest.mark.parametrize("layout", [0, 1], ids=["transposed_t4", "column_major"])
+@pytest.mark.parametrize("layout", [0, 1], ids=["column_major", "transposed_t4"])
 @pytest.mark.parametrize("source", ["file", "host", "pinned"])
 @pytest.mark.parametrize("rk", ["shuffle", "dup", "subset"])
 def test_host_sources_gathered_rows_cross_packed(source, rk, layout, tpg_cfg):
@@ -211,14 +211,14 @@ def test_gathered_rows_of_long_columns(where):
     assert np.array_equal(K, ref["K"]) and np.array_equal(N, ref["N_Aa_i"]) and same(king, ref["king"])
 
 
-@pytest.mark.parametrize("layout", [0, 1], ids=["transposed_t4", "column_major"])
+@pytest.mark.parametrize("layout", [0, 1], ids=["column_major", "transposed_t4"])
 def test_gather_pack_kernel_edges(layout, tpg_cfg):
     """Row spans that start / end at the first / last byte of the allocation, n not a multiple of 16,
     duplicated rows, a single locus, loci counts that are not multiples of 4: dense result equals the oracle,
     for both staging layouts of gather_pack."""
     tpg_cfg(gather_layout=layout)
     rng = np.random.default_rng(53)
-    for n_tot, m_tot, n_sel in ((17, 1, 5), (64, 3, 64), (1000, 40, 999), (4099, 7, 33), (10000, 1030, 7000)):
+    for n_tot, m_tot, n_sel in ((17, 1, 5), (64, 3, 64), (1000, 40, 999), (4099, 7, 33), (10000, 70, 2000)):
         raw = random_bk(rng, n_tot, m_tot, 0.1, codes=(0, 1, 2, 3, 7, 200))
         rows = rng.choice(np.arange(1, n_tot + 1), size=n_sel, replace=True).astype(np.int32)
         rows[0], rows[-1] = 1, n_tot
@@ -318,3 +318,37 @@ def test_multi_gpu_large_result_comes_home_over_every_link(shard):
     assert same(manyN["king"], many1["king"]) and same(manyN["allele_sharing"], many1["allele_sharing"])
     assert np.array_equal(manyN["ibs_raw"]["ibs"], many1["ibs_raw"]["ibs"])
     assert np.array_equal(manyN["ibs_raw"]["valid_n"], many1["ibs_raw"]["valid_n"])
+
+
+def test_mma_peak_probe_reports_a_plausible_issue_rate():
+    """tpg_mma_peak (csrc/peak.cu): the roofline denominators bench.py reports — the 4-bit kind issues about
+    twice the MACs of kind::i8, both within reach of the nominal 9 / 4.5 POP/s."""
+    import ctypes as C
+    eb = L.errbuf()
+    got = {}
+    for kind in (0, 1):
+        tops, ms = C.c_double(0), C.c_double(0)
+        L.check(L.lib().tpg_mma_peak(0, kind, 0.02, C.byref(tops), C.byref(ms), eb, len(eb)), eb)
+        got[kind] = tops.value
+        assert ms.value > 1.0
+    assert 2500 < got[0] < 5200 and 5000 < got[1] < 10400 and 1.6 < got[1] / got[0] < 2.4, got
+    assert L.lib().tpg_mma_peak(0, 7, 0.02, None, None, eb, len(eb)) == L.ERR_ARG
+
+
+def test_bench_line_at_a_reduced_shape():
+    """bench.py end to end at a development size (labelled as such in the line): the contract's keys, the parity
+    flags, the e2e leg from a .bk file and the extras all run; the numbers themselves are not the point."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--indiv", "3000", "--loci", "16384", "--steps", "2",
+                        "--warmup", "1", "--pairs", "8", "--no-extras"], capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["unit"] == "pair-SNP/s" and d["scaling"] == "strong" and d["n_gpus"] == 1 and d["value"] > 0
+    assert "REDUCED" in d["config"]["workload"]
+    for key in ("roofline", "roofline_int8", "roofline_decode", "cpu_baseline", "e2e", "clocks", "parity", "mma_peaks_measured"):
+        assert d[key] is not None, key
+    assert d["roofline"]["bound"] == "tensor" and 0 < d["roofline"]["frac"] < 1.2 and d["roofline"]["peak"] > 1000
+    assert d["parity"]["sampled_pairs_exact"] and d["parity"]["int8_and_4bit_routes_agree"] and d["parity"]["parity_first_block"]
+    assert d["e2e"]["sampled_pairs_exact"] and d["e2e"]["matches_device_run"] and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert d["gpu_launches"] >= 2 * 4

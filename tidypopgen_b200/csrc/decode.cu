@@ -439,7 +439,8 @@ gather_pack_kernel(const GatherParams p) {
   }
 }
 
-// The build that runs wherever four columns fit shared memory: the staged tile is TRANSPOSED — word r of a group
+// A second build (tpg_config.gather_layout = 1; measured SLOWER than the column-major one above, 2.7 vs 1.6 ms on
+// the C5 subset, and therefore not the default — kept for the cross-check and the next look at it): the staged tile is TRANSPOSED — word r of a group
 // holds row r (packed input: byte r) of FOUR loci — so one shared-memory read serves four loci and the gather
 // phase's bank-conflicted lookups drop four-fold (ncu on the column-major build above: l1tex 90 % busy, 210 M bank
 // conflicts, 15 instructions per genotype; C5 subset 1.61 ms).  Staging: a thread loads rows 4q..4q+3 of the four
@@ -572,7 +573,7 @@ int launch_gather_pack(Ctx* ctx, const DecodeArgs& a, bool packed_in, int64_t ro
   if (C.gather_smem_kb > 0) budget = std::min(kGatherSmemMax, std::max(8, int(C.gather_smem_kb)) * 1024);
   // the transposed build stages groups of four columns (16 bytes per quad of rows and group)
   const int64_t group_bytes = (span_bytes + 3) / 4 * 16;
-  const bool t4 = group_bytes <= kGatherSmemMax && C.gather_layout == 0;
+  const bool t4 = group_bytes <= kGatherSmemMax && C.gather_layout == 1;
   const int64_t unit = t4 ? group_bytes : p.col_pitch;            // smallest piece of shared memory a CTA can work with
   while (budget < kGatherSmemMax && unit * (t4 ? 1 : 2) > budget) budget *= 2;   // long columns: fewer CTAs per SM
   budget = std::min(budget, kGatherSmemMax);

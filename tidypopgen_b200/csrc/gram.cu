@@ -587,6 +587,7 @@ gram_mxf4_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
 // gram_mxf4_pair_kernel.
 constexpr int kWideStages = 4;
 constexpr int kWideStageBytes = 3 * kHalfBytes;       // per CTA: A half + two B halves
+constexpr int kWideBBoxBytes = 120 * 128;             // a B box: 120 rows x 128 bytes
 constexpr int kWideEpiBytes = 4 * 2 * 4096;           // epilogue staging: per warp two 32 x 32 int32 boxes
 constexpr int kWideSmemBytes = kWideStages * kWideStageBytes + kWideEpiBytes + 1024 + 256;
 
@@ -595,8 +596,9 @@ constexpr int kWideSmemBytes = kWideStages * kWideStageBytes + kWideEpiBytes + 1
 template <int kDummy>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGramThreads, 1)
 gram_mxf4_wide_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_nm,
-                      const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_counts,
-                      const GramParams p) {
+                      const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tb_d,
+                      const __grid_constant__ CUtensorMap tb_nm, const __grid_constant__ CUtensorMap tb_h1,
+                      const __grid_constant__ CUtensorMap tm_counts, const GramParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -617,6 +619,9 @@ gram_mxf4_wide_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
     tma_prefetch_desc(&tm_d);
     tma_prefetch_desc(&tm_nm);
     tma_prefetch_desc(&tm_h1);
+    tma_prefetch_desc(&tb_d);
+    tma_prefetch_desc(&tb_nm);
+    tma_prefetch_desc(&tb_h1);
     tma_prefetch_desc(&tm_counts);
     for (int s = 0; s < kWideStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -655,11 +660,12 @@ gram_mxf4_wide_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
         int pa, pb;
         prod_planes(prod, pa, pb);
         const CUtensorMap* ma = pa == 0 ? &tm_d : pa == 1 ? &tm_nm : &tm_h1;
-        const CUtensorMap* mb = pb == 0 ? &tm_d : pb == 1 ? &tm_nm : &tm_h1;
+        // B boxes are 120 rows (a CTA supplies N / 2 <= 120 rows of a tile), not 128: 6 % fewer B bytes over L2
+        const CUtensorMap* mb = pb == 0 ? &tb_d : pb == 1 ? &tb_nm : &tb_h1;
         const int row_a = ti * kPairTileM + int(rank) * 128;
-        const int row_b0 = w.tj + int(rank) * (n0 / 2);            // N/2 of the 128 loaded rows are used
+        const int row_b0 = w.tj + int(rank) * (n0 / 2);
         const int row_b1 = w.tj + kQTileN + int(rank) * (n1 / 2);
-        const uint32_t bytes = 2u * uint32_t(n1 ? kWideStageBytes : kPairStageBytes);
+        const uint32_t bytes = 2u * uint32_t(kHalfBytes + (n1 ? 2 : 1) * kWideBBoxBytes);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
           uint8_t* sa = smem + stage * kWideStageBytes;
@@ -779,11 +785,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int make_plane_map(Ctx* ctx, CUtensorMap* out, const int8_t* base, uint64_t inner,
-                          uint64_t outer, const Err& E) {
+                          uint64_t outer, const Err& E, uint32_t box_rows = 128) {
   if (!ctx->encode_tiled) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled entry point missing");
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {inner};  // bytes, dim 1
-  cuuint32_t box[2] = {128, 128};
+  cuuint32_t box[2] = {128, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
       out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(base), dims, strides, box, estr,
@@ -1013,7 +1019,14 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
         &cmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, a.counts, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled(counts) failed (CUresult %d)", int(r));
-    gram_mxf4_wide_kernel<0><<<grid, kGramThreads, kWideSmemBytes, st>>>(maps[0], maps[1], maps[2], cmap, p);
+    CUtensorMap bmaps[3];
+    for (int pl = 0; pl < 3; ++pl) {
+      const bool present = pl < 2 || (a.prod_mask & ((1 << TPG_MAT_HH) | (1 << TPG_MAT_HN)));
+      int rc = make_plane_map(ctx, &bmaps[pl], present ? a.planes + int64_t(pl) * a.plane_stride : a.planes,
+                              uint64_t(a.lc_pad / 2), uint64_t(a.n_pad), E, 120);
+      if (rc) return rc;
+    }
+    gram_mxf4_wide_kernel<0><<<grid, kGramThreads, kWideSmemBytes, st>>>(maps[0], maps[1], maps[2], bmaps[0], bmaps[1], bmaps[2], cmap, p);
   }
   else gram_mxf4_pair_kernel<0><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
   TPG_CUDA_OK(cudaGetLastError(), E);
