@@ -149,7 +149,8 @@ CPU_SAMPLE_INDIV = 12_500   # a quarter of the individuals = 1/16 of the pairs
 def cpu_sample_desc(n_s, sample, n, m, bs, cores):
     return (f"loci block 1 of R's block loop ({sample} of {m} loci, block.size {bs} = bigstatsr::block_size({n})) on the first "
             f"{n_s} of {n} individuals; numpy decode into FP64 indicator planes + FP64 dgemm (MKL) on {cores} threads, "
-            "K / N accumulators and finish as the reference; the rate is per pair-SNP and FP64 GEMM at this size is "
+            "K / N accumulators and finish as the reference (g1 g1' goes through dgemm where Armadillo emits dsyrk: 8 flop per "
+            "pair-SNP against the reference's 7, i.e. up to ~12 % pessimistic for the CPU); the rate is per pair-SNP and FP64 GEMM at this size is "
             "compute bound, so it extrapolates to the full 187-block, 50,000-individual job (which needs 60 GB of FP64 "
             "temporaries and ~2 h of these cores)")
 

@@ -800,7 +800,7 @@ static int make_plane_map(Ctx* ctx, CUtensorMap* out, const int8_t* base, uint64
 }
 
 // Chooses how many k-splits a tile gets so that the persistent CTAs finish together.
-static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms) {
+static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms, int default_max_kblocks = 128) {
   const tpg_config C = cfg();
   if (C.gram_ksplit > 0) return int(std::max<int64_t>(1, std::min<int64_t>(kblocks, int64_t(C.gram_ksplit))));
   // Large problems: every CTA runs many items, balance is not the issue — L2 is.  CTAs that
@@ -810,7 +810,7 @@ static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms) {
   // n = 50,000 x 500,000: 256 k-blocks 3.25 s, 128 k-blocks 1.71 s).  With items of 128 k-blocks
   // (16,384 loci) the operand panels of a whole 1024 x 1024 tile region (~100 MB) fit in the
   // 126 MB L2, so the reuse no longer depends on the CTAs staying in lock step.
-  const int max_per = C.gram_max_kblocks > 0 ? std::max(8, int(C.gram_max_kblocks)) : 128;
+  const int max_per = C.gram_max_kblocks > 0 ? std::max(8, int(C.gram_max_kblocks)) : default_max_kblocks;
   const int ks_l2 = int((kblocks + max_per - 1) / max_per);
   if (n_tile_items >= int64_t(8) * sms) return std::max(1, ks_l2);
   int best = 1;
@@ -943,7 +943,9 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
           }
         }
   if (tiles.empty()) { if (macs_out) *macs_out = 0; return TPG_OK; }
-  int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units);
+  // (the wide kernel's epilogue is exposed, so its items are longer: 256 k-blocks = 65,536 loci; C4 sweep,
+  //  profiles/r02_gram_sweep.jsonl: 96 -> 810 ms, 128 -> 789, 192 -> 780, 256 -> 772, 384 -> 769)
+  int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units, wide ? 256 : 128);
   // EXACTNESS GUARD.  The FP32 accumulator of kind::mxf4 holds integer sums exactly only below 2^24
   // (gram_mxf4_pair_kernel): one work item = one accumulation chain never runs more than
   // TPG_MXF4_MAX_CHAIN_LOCI (2^23) loci, whatever the chunk size, the auto heuristic or a gram_ksplit
