@@ -196,9 +196,11 @@ typedef struct tpg_config {
   int32_t gram_wide;          /* TPG_GRAM_WIDE: 4-bit route, 256 x 480 tiles (one A stream feeds two B tiles: a quarter  *
                                * less L2 traffic per MAC). 0 = where tiles are plentiful (default), 1 = never, 2 = always */
   int32_t gram_l2_rows;       /* TPG_GRAM_L2_ROWS / TPG_GRAM_L2_COLS: the L2 neighbourhood of the Gram work list, in 256-row and   *
-                               * 240- (int8: 256-) column tiles; 0 = 8 x 8 (2048 x 1920) for the 4-bit kernels, 4 x 4 for int8    */
+                               * 240- (int8: 256-) column tiles; 0 = auto: 8 x 8 (2048 x 1920) for biobank-sized 4-bit jobs, else 4 x 4 */
   int32_t gram_l2_cols;
-  int32_t gram_order;         /* TPG_GRAM_ORDER: 0 = product-major inside a neighbourhood (default), 1 = tile-major (round 1)     */
+  int32_t gram_order;         /* TPG_GRAM_ORDER: work-list order inside a neighbourhood. 0 = auto (product-major for the int8     *
+                               * kernels and for biobank-sized 4-bit jobs, tile-major for mid-sized 4-bit jobs), 1 = product-major, *
+                               * 2 = tile-major (round 1's order)                                                                  */
   int32_t pack_mode;          /* TPG_PACK_MODE: 0 = hybrid (pack or raw DMA per chunk), 1 = never pack (TPG_NO_PACK), *
                                * 2 = always pack (TPG_NO_HYBRID) */
   int32_t pk2_i8;             /* TPG_PK2_I8: 1 = packed chunks take the int8 kernels */

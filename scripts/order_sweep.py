@@ -29,9 +29,9 @@ def run(flags, steps):
     return best
 
 
-variants = [(1, 4, 4), (0, 4, 4), (0, 4, 8), (0, 8, 8), (0, 8, 16), (0, 16, 8), (0, 16, 16), (0, 8, 32), (0, 32, 8)]
+variants = [(2, 4, 4), (1, 4, 4), (1, 4, 8), (1, 8, 8), (1, 8, 16), (1, 16, 8), (1, 16, 16), (1, 8, 32), (1, 32, 8)]
 for route, flags, steps in (("mxf4", 0, 3), ("int8", L.FLAG_GRAM_I8, 2)):
     for order, r, c in variants:
         tpg.config(gram_order=order, gram_l2_rows=r, gram_l2_cols=c)
-        print(json.dumps({"route": route, "order": "product-major" if order == 0 else "tile-major (round 1)", "l2_rows": r * 256,
+        print(json.dumps({"route": route, "order": "product-major" if order == 1 else "tile-major (round 1)", "l2_rows": r * 256,
                           "l2_cols": c * (240 if route == "mxf4" else 256), "gram_ms_best": run(flags, steps)}), flush=True)

@@ -82,7 +82,7 @@ int tpg_config_set(const tpg_config* c, char* err, size_t errlen) {
   if (c->gram_ctas < 0 || c->gram_ctas > 2) return fail("gram_ctas must be 0, 1 or 2");
   if (c->gram_ksplit < 0 || c->gram_max_kblocks < 0 || c->gram_clusters < 0) return fail("gram_* must be >= 0");
   if (c->gram_l2_rows < 0 || c->gram_l2_cols < 0 || c->gram_l2_rows > 4096 || c->gram_l2_cols > 4096) return fail("gram_l2_rows / gram_l2_cols out of range");
-  if (c->gram_order < 0 || c->gram_order > 1) return fail("gram_order must be 0 or 1");
+  if (c->gram_order < 0 || c->gram_order > 2) return fail("gram_order must be 0 (auto), 1 (product-major) or 2 (tile-major)");
   if (c->gram_wide < 0 || c->gram_wide > 2) return fail("gram_wide must be 0 (auto), 1 (never) or 2 (always)");
   if (c->pack_mode < 0 || c->pack_mode > 2) return fail("pack_mode must be 0 (hybrid), 1 (never) or 2 (always)");
   if (c->gather_layout < 0 || c->gather_layout > 1) return fail("gather_layout must be 0 or 1");

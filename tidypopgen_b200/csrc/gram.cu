@@ -918,10 +918,19 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   // 1024 x 1024 neighbourhood (round 1's order; ncu at C4: 3.4 TB of DRAM reads for 37.6 GB of planes).  For this
   // kernel the order turned out not to matter (scripts/order_sweep.py: 798 - 806 ms for every variant at C4): it is
   // bound by the L2 -> shared-memory stream and the power cap, not by HBM.
-  const int64_t RI = std::max<int64_t>(1, C.gram_l2_rows > 0 ? C.gram_l2_rows : 8);
-  const size_t rj240 = size_t(std::max(1, C.gram_l2_cols > 0 ? int(C.gram_l2_cols) : 8));
+  // Two regimes, told apart by how many waves of work items one k-split is (estimated before the list is built):
+  // a biobank-sized matrix (C4: ~550 waves per k-split) runs best product-major in 2048 x 1920 neighbourhoods with
+  // long items (256 k-blocks: the wide kernel's exposed epilogue is amortised; 803 -> 749 ms), a mid-sized one (C5,
+  // 10,000 individuals: ~18 waves) with round 1's tile-major 1024 x 960 neighbourhoods and 128 k-blocks (46 vs 51 - 53
+  // ms) — scripts/gram_sweep_c5.py, profiles/r02_gram_sweep_c5.jsonl.
+  int nprod = 0;
+  for (int prod = 0; prod < TPG_NUM_COUNT_MATS; ++prod) nprod += ((a.prod_mask >> prod) & 1) * (prod == TPG_MAT_HN ? 2 : 1);
+  const int64_t waves_est = count_tiles(wide) * nprod / std::max(1, a.shard_world) / std::max(1, units);
+  const bool big = waves_est >= 50;
+  const int64_t RI = std::max<int64_t>(1, C.gram_l2_rows > 0 ? C.gram_l2_rows : (big ? 8 : 4));
+  const size_t rj240 = size_t(std::max(1, C.gram_l2_cols > 0 ? int(C.gram_l2_cols) : (big ? 8 : 4)));
   const size_t RJ = wide ? std::max<size_t>(1, rj240 / 2) : rj240;
-  const bool prod_major = C.gram_order == 0;
+  const bool prod_major = C.gram_order == 0 ? big : C.gram_order == 1;
   struct T { int prod, ti, col0, n0, n1; };
   std::vector<T> tiles;
   for (size_t rj = 0; rj < wcols.size(); rj += RJ)
@@ -945,7 +954,7 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   if (tiles.empty()) { if (macs_out) *macs_out = 0; return TPG_OK; }
   // (the wide kernel's epilogue is exposed, so its items are longer: 256 k-blocks = 65,536 loci; C4 sweep,
   //  profiles/r02_gram_sweep.jsonl: 96 -> 810 ms, 128 -> 789, 192 -> 780, 256 -> 772, 384 -> 769)
-  int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units, wide ? 256 : 128);
+  int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units, (wide && big) ? 256 : 128);
   // EXACTNESS GUARD.  The FP32 accumulator of kind::mxf4 holds integer sums exactly only below 2^24
   // (gram_mxf4_pair_kernel): one work item = one accumulation chain never runs more than
   // TPG_MXF4_MAX_CHAIN_LOCI (2^23) loci, whatever the chunk size, the auto heuristic or a gram_ksplit
@@ -1097,7 +1106,7 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   const tpg_config C2 = cfg();
   const int64_t RI = std::max<int64_t>(1, (C2.gram_l2_rows > 0 ? C2.gram_l2_rows : 4) * 256 / tile_m);
   const int64_t RJ = std::max<int64_t>(1, C2.gram_l2_cols > 0 ? C2.gram_l2_cols : 4);
-  const bool prod_major = C2.gram_order == 0;
+  const bool prod_major = C2.gram_order != 2;
   for (int64_t rj = 0; rj < tiles_n; rj += RJ)
     for (int64_t ri = 0; ri < tiles_m; ri += RI)
       for (int pp = 0; pp < (prod_major ? TPG_NUM_COUNT_MATS : 1); ++pp)
