@@ -336,11 +336,16 @@ def test_decode_planes_kernel(k_major, gather):
     assert np.array_equal(got, ref)
 
 
-@pytest.mark.parametrize("ctas", [2, 1])
+@pytest.mark.parametrize("ctas", [2, 1, "wide"])
 @pytest.mark.parametrize("k_major", [False, True])
 @pytest.mark.parametrize("shape", [(256, 128), (512, 1152), (1024, 4096), (2560, 2048)])
-def test_gram_kernel(k_major, shape, ctas):
+def test_gram_kernel(k_major, shape, ctas, tpg_cfg):
+    """The int8 -> s32 Gram kernels: CTA pairs (256 x 256 ping-pong), single CTA, and the wide 256 x 512 kernel with the
+    TMA-reduction epilogue; MN-major and K-major planes."""
     import torch
+    if ctas == "wide":
+        tpg_cfg(gram_wide=2)
+        ctas = 2
     n_pad, lc_pad = shape
     ctx = L.Context(0)
     rng = np.random.default_rng(2)

@@ -274,10 +274,12 @@ def test_grm_mb_is_the_double_double_mean():
     assert mbs[0] == mb
 
 
+@pytest.mark.parametrize("route", [0, L.FLAG_GRAM_I8, L.FLAG_GRAM_I8 | L.FLAG_PLANES_K_MAJOR], ids=["mxf4", "i8", "i8_kmajor"])
 @pytest.mark.parametrize("n_tot,rk", [(389, "all"), (929, "shuffle"), (1300, "subset")])
-def test_wide_gram_kernel_whole_jobs(n_tot, rk, tpg_cfg):
-    """gram_mxf4_wide_kernel forced on small matrices (ragged last tiles: 240 + 149, 480 + 449, ...): every
-    statistic equals the oracle, for one chunk and several, with and without a row gather."""
+def test_wide_gram_kernel_whole_jobs(n_tot, rk, route, tpg_cfg):
+    """gram_mxf4_wide_kernel (256 x 480 tiles) and gram_i8_wide_kernel (256 x 512) forced on small matrices (ragged
+    last tiles: 240 + 149, 480 + 449, 256 + 133, ...): every statistic equals the oracle, for one chunk and several,
+    with and without a row gather."""
     rng = np.random.default_rng(n_tot)
     m_tot = 2100
     raw = random_bk(rng, n_tot, m_tot, 0.08, codes=(0, 1, 2, 3, 4, 5, 6, 255))
@@ -286,14 +288,14 @@ def test_wide_gram_kernel_whole_jobs(n_tot, rk, tpg_cfg):
     tpg_cfg(gram_wide=2)
     ref_k = O.snp_king(raw, n_tot, m_tot, rows, None)
     for chunk in (0, 512):
-        king, K, N = tpg.snp_king_counts(X, rows, None, gpu_chunk_loci=chunk)
-        assert tpg.snp.last_stats["n_mxf4_chunks"] >= 1
+        king, K, N = tpg.snp_king_counts(X, rows, None, gpu_chunk_loci=chunk, flags=route)
+        assert (tpg.snp.last_stats["n_mxf4_chunks"] >= 1) == (route == 0)
         assert np.array_equal(K, ref_k["K"]) and np.array_equal(N, ref_k["N_Aa_i"]) and same(king, ref_k["king"])
     ref_i = O.snp_ibs(raw, n_tot, m_tot, rows, None, type="raw_counts")
-    got = tpg.snp_ibs(X, rows, None, type="raw_counts")
+    got = tpg.snp_ibs(X, rows, None, type="raw_counts", flags=route)
     assert np.array_equal(got["ibs"][:], ref_i["ibs"]) and np.array_equal(got["valid_n"][:], ref_i["valid_n"])
     ref_a = O.snp_allele_sharing(raw, n_tot, m_tot, rows, None, block_size_=500)
-    a, num, den = tpg.snp_allele_sharing_counts(X, rows, None, block_size=500)
+    a, num, den = tpg.snp_allele_sharing_counts(X, rows, None, block_size=500, flags=route)
     assert np.array_equal(num, ref_a["num"]) and np.array_equal(den, ref_a["denom"]) and same(a, ref_a["as"])
 
 

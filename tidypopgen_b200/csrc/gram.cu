@@ -777,6 +777,187 @@ gram_mxf4_wide_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------ int8 variant, wide tiles
+// The int8 -> s32 twin of gram_mxf4_wide_kernel (north_star's literal route): a work item is a 256 x 512 tile — both
+// 256-column s32 accumulators of the CTA pair's TMEM — so one A stage feeds two B stages (48 KiB per 128 loci and CTA
+// for twice the MACs), and the epilogue adds 32 x 32 int32 boxes with TMA reductions.  The ping-pong pair kernel reads
+// 10.9 TB from DRAM per C4 launch (5.6 TB/s: HBM-bound, ncu); per MAC this kernel moves a quarter less.
+// work item: prod [0,4) | (n0 / 16 - 1) [4,8) | (n1 / 16) [8,13) | ti [13,32); tj = first 256-column tile;
+// half 0 = columns [256 tj, 256 tj + n0), half 1 = columns [256 (tj + 1), 256 (tj + 1) + n1) (n1 = 0: absent)
+template <bool kMajorK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGramThreads, 1)
+gram_i8_wide_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_nm,
+                    const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_counts,
+                    const GramParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* epi = smem + kWideStages * kWideStageBytes;  // [4 warps][2][32 x 32 int32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + kWideEpiBytes);
+  uint64_t* full_bar = bars;                          // [kWideStages] used in the leader only
+  uint64_t* empty_bar = bars + kWideStages;           // [kWideStages] in each CTA
+  uint64_t* tfull_bar = bars + 2 * kWideStages;       // [1] in each CTA
+  uint64_t* tempty_bar = bars + 2 * kWideStages + 1;  // [1] used in the leader only (8 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWideStages + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_d);
+    tma_prefetch_desc(&tm_nm);
+    tma_prefetch_desc(&tm_h1);
+    tma_prefetch_desc(&tm_counts);
+    for (int s = 0; s < kWideStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = cluster; it < p.n_items; it += n_clusters) {
+        const WorkItem w = p.items[it];
+        const int prod = w.prod_ti & 15, ti = int(uint32_t(w.prod_ti) >> 13), tj = w.tj;
+        const int n0 = (((w.prod_ti >> 4) & 15) + 1) * 16, n1 = ((w.prod_ti >> 8) & 31) * 16;
+        int pa, pb;
+        prod_planes(prod, pa, pb);
+        const CUtensorMap* ma = pa == 0 ? &tm_d : pa == 1 ? &tm_nm : &tm_h1;
+        const CUtensorMap* mb = pb == 0 ? &tm_d : pb == 1 ? &tm_nm : &tm_h1;
+        const int row_a = ti * kPairTileM + int(rank) * 128;
+        const int row_b0 = tj * kTileN + int(rank) * (n0 / 2);          // N/2 of the 128 loaded rows are used
+        const int row_b1 = (tj + 1) * kTileN + int(rank) * (n1 / 2);
+        const uint32_t bytes = 2u * uint32_t(n1 ? kWideStageBytes : kPairStageBytes);
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+          uint8_t* sa = smem + stage * kWideStageBytes;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          const uint32_t bar0 = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (kMajorK) {
+            tma_load_2d_pair(sa, ma, bar0, kb * kTileK, row_a);
+            tma_load_2d_pair(sa + kHalfBytes, mb, bar0, kb * kTileK, row_b0);
+            if (n1) tma_load_2d_pair(sa + 2 * kHalfBytes, mb, bar0, kb * kTileK, row_b1);
+          } else {
+            tma_load_2d_pair(sa, ma, bar0, row_a, kb * kTileK);
+            tma_load_2d_pair(sa + kHalfBytes, mb, bar0, row_b0, kb * kTileK);
+            if (n1) tma_load_2d_pair(sa + 2 * kHalfBytes, mb, bar0, row_b1, kb * kTileK);
+          }
+          if (++stage == kWideStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc0 = make_idesc_i8(kPairTileM, 0, !kMajorK);
+      constexpr uint32_t lbo = kMajorK ? 16u : uint32_t(kHalfBytes);
+      constexpr uint32_t sbo = 1024u;
+      constexpr uint32_t kstep = kMajorK ? (32u >> 4) : (4096u >> 4);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int it = cluster; it < p.n_items; it += n_clusters) {
+        const WorkItem w = p.items[it];
+        const uint32_t n0 = (((uint32_t(w.prod_ti) >> 4) & 15u) + 1u) * 16u, n1 = ((uint32_t(w.prod_ti) >> 8) & 31u) * 16u;
+        const uint32_t idesc_a = idesc0 | ((n0 >> 3) << 17), idesc_b = idesc0 | ((n1 >> 3) << 17);
+        mbar_wait(tempty_bar, acc_phase ^ 1, p.err_flag, 2);   // both accumulators drained by the previous item
+        tc_fence_after();
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kWideStageBytes);
+          const uint64_t da = make_smem_desc_sw128(sa, lbo, sbo);
+          const uint64_t db0 = make_smem_desc_sw128(sa + kHalfBytes, lbo, sbo);
+          const uint64_t db1 = make_smem_desc_sw128(sa + 2 * kHalfBytes, lbo, sbo);
+          const uint32_t accum0 = kb > w.kb0 ? 1u : 0u;
+#pragma unroll
+          for (int k = 0; k < kTileK / 32; ++k) {
+            umma_i8_pair(tmem_base, da + uint64_t(k * kstep), db0 + uint64_t(k * kstep), idesc_a, (accum0 | uint32_t(k)) ? 1u : 0u);
+            if (n1) umma_i8_pair(tmem_base + 256u, da + uint64_t(k * kstep), db1 + uint64_t(k * kstep), idesc_b, (accum0 | uint32_t(k)) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (++stage == kWideStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(tfull_bar, 3);
+        acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue (warps 2..5, both CTAs)
+    const int q = warp & 3;
+    uint32_t acc_phase = 0;
+    int buf = 0;
+    uint8_t* ebase = epi + q * 2 * 4096;
+    for (int it = cluster; it < p.n_items; it += n_clusters) {
+      const WorkItem w = p.items[it];
+      const int prod = w.prod_ti & 15, ti = int(uint32_t(w.prod_ti) >> 13);
+      const int n0 = (((w.prod_ti >> 4) & 15) + 1) * 16, n1 = ((w.prod_ti >> 8) & 31) * 16;   // multiples of 32 (host)
+      mbar_wait(tfull_bar, acc_phase, p.err_flag, 4);
+      tc_fence_after();
+      const int i0 = ti * kPairTileM + int(rank) * 128 + q * 32;       // this warp's 32 rows
+      const int jmat = prod * int(p.ld);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int ncols = half ? n1 : n0;
+        if (ncols == 0) break;
+        const int j0 = (w.tj + half) * kTileN;
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(half * 256);
+        const bool last_half = half == 1 || n1 == 0;
+#pragma unroll 1
+        for (int c = 0; c < ncols; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + uint32_t(c), v);
+          tmem_ld_wait();
+          if (c + 32 == ncols && last_half) {  // both accumulators drained: hand them back (to the leader's barrier)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(tempty_bar), 0));
+          }
+          if (lane == 0) bulk_wait_group_read<1>();   // the staging box used two chunks ago has been read
+          __syncwarp();
+          int32_t* box = reinterpret_cast<int32_t*>(ebase + buf * 4096);   // [32 columns][32 rows]
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) box[jj * 32 + lane] = int32_t(v[jj]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tm_counts, box, i0, jmat + j0 + c);
+            bulk_commit_group();
+          }
+          buf ^= 1;
+        }
+      }
+      acc_phase ^= 1;
+    }
+    if (lane == 0) bulk_wait_group<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -1094,8 +1275,36 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   // schedulable units: SMs (one CTA each) or resident CTA pairs
   const int units = pair ? ctx->pair_clusters : ctx->num_sms;
 
-  // ---- tile list in L2-friendly order: 1024x1024 regions, then tiles, then products
-  struct T { int prod, ti, tj; };
+  // ---- tile list in L2-friendly order: neighbourhoods, then products, then tiles
+  const tpg_config C2 = cfg();
+  const bool trim_n = pair && !C2.gram_no_trim;
+  // N of a tile's MMAs: the pair kernels trim the last tile column to its valid columns (multiple of 32)
+  auto tile_ncols = [&](int64_t tj) {
+    if (!trim_n) return int(kTileN);
+    const int64_t valid = std::min<int64_t>(kTileN, a.n - tj * kTileN);
+    return int(std::max<int64_t>(32, (valid + 31) / 32 * 32));
+  };
+  // Wide items (gram_i8_wide_kernel): two neighbouring 256-column tiles of one ownership region share an A stream.
+  // Where tiles are plentiful, as for the 4-bit route (tpg_config.gram_wide: 0 auto, 1 never, 2 always).
+  const int64_t upper_tiles = tiles_m * (tiles_n + 1) / 2;
+  const bool wide = pair && (C2.gram_wide == 2 || (C2.gram_wide == 0 && upper_tiles >= int64_t(4) * units));
+  if (wide && !ctx->i8wide_attr_set) {
+    TPG_CUDA_OK(cudaFuncSetAttribute(gram_i8_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideSmemBytes), E);
+    TPG_CUDA_OK(cudaFuncSetAttribute(gram_i8_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideSmemBytes), E);
+    ctx->i8wide_attr_set = true;
+  }
+  struct JC { int tj, n0, n1; };   // column item: tile tj (n0 columns) and, when paired, tile tj + 1 (n1 columns)
+  std::vector<JC> jcs;
+  {
+    const int64_t region = a.shard_world > 1 ? shard_region_blocks(tiles_n, a.shard_world) : tiles_n;
+    for (int64_t tj = 0; tj < tiles_n;) {
+      const bool pair2 = wide && tj + 1 < tiles_n && tj / region == (tj + 1) / region && tile_ncols(tj) == kTileN &&
+                         kTileN * (tj + 1) < a.n;
+      jcs.push_back({int(tj), tile_ncols(tj), pair2 ? tile_ncols(tj + 1) : 0});
+      tj += pair2 ? 2 : 1;
+    }
+  }
+  struct T { int prod, ti, tj, n0, n1; };
   std::vector<T> tiles;
   // L2 neighbourhoods (tpg_config.gram_l2_rows / gram_l2_cols, in 256-row / 256-column tiles; default 1024 x 1024)
   // and, inside one, PRODUCT-major order: CTAs resident together then stream the panels of ONE pair of planes —
@@ -1103,25 +1312,28 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   // neighbourhood at once (round 1's order: tile-major, products innermost; ncu at C4: 13 - 16 TB of DRAM reads for
   // 75 GB of int8 planes, the kernel ran at 5.4 - 6.3 TB/s of HBM).  Measured at C4 (scripts/order_sweep.py,
   // profiles/r02_order_sweep.jsonl): 2174 -> 1939 ms; larger neighbourhoods are slower again (2048 x 2048: 2302 ms).
-  const tpg_config C2 = cfg();
   const int64_t RI = std::max<int64_t>(1, (C2.gram_l2_rows > 0 ? C2.gram_l2_rows : 4) * 256 / tile_m);
-  const int64_t RJ = std::max<int64_t>(1, C2.gram_l2_cols > 0 ? C2.gram_l2_cols : 4);
+  const int64_t rj256 = std::max<int64_t>(1, C2.gram_l2_cols > 0 ? C2.gram_l2_cols : 4);
+  const size_t RJ = size_t(wide ? std::max<int64_t>(1, rj256 / 2) : rj256);
   const bool prod_major = C2.gram_order != 2;
-  for (int64_t rj = 0; rj < tiles_n; rj += RJ)
+  for (size_t rj = 0; rj < jcs.size(); rj += RJ)
     for (int64_t ri = 0; ri < tiles_m; ri += RI)
       for (int pp = 0; pp < (prod_major ? TPG_NUM_COUNT_MATS : 1); ++pp)
-      for (int64_t tj = rj; tj < std::min(rj + RJ, tiles_n); ++tj)
+      for (size_t cj = rj; cj < std::min(rj + RJ, jcs.size()); ++cj)
         for (int64_t ti = ri; ti < std::min(ri + RI, tiles_m); ++ti) {
-          const bool upper = kTileN * tj + (kTileN - 1) >= tile_m * ti;
-          if (!tile_wanted(a, tile_m * ti, tile_m * (ti + 1), kTileN * tj, kTileN * (tj + 1))) continue;
-          // 256x256 ownership block of the tile; lower blocks mirror
+          const JC& jc = jcs[cj];
+          const int64_t tj = jc.tj;
+          const int64_t c_end = jc.n1 ? kTileN * (tj + 1) + jc.n1 : kTileN * tj + kTileN;
+          const bool upper = c_end - 1 >= tile_m * ti;
+          if (!tile_wanted(a, tile_m * ti, tile_m * (ti + 1), kTileN * tj, c_end)) continue;
+          // 256x256 ownership block of the tile (a pair lies inside one region); lower blocks mirror
           const int64_t bi = ti * tile_m / 256, bj = tj;
           for (int prod = prod_major ? pp : 0; prod < (prod_major ? pp + 1 : TPG_NUM_COUNT_MATS); ++prod) {
             if (!(a.prod_mask & (1 << prod))) continue;
             if (prod != TPG_MAT_HN && !upper) continue;
             const int64_t lo = std::min(bi, bj), hi = std::max(bi, bj);
             if (!block_owned(lo, hi, tiles_n, a.shard_rank, a.shard_world, a.owner)) continue;
-            tiles.push_back({prod, int(ti), int(tj)});
+            tiles.push_back({prod, int(ti), int(tj), jc.n0, jc.n1});
           }
         }
   if (tiles.empty()) { if (macs_out) *macs_out = 0; return TPG_OK; }
@@ -1129,22 +1341,15 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   const int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units);
 
   // The work list only depends on the geometry; chunks of equal size reuse the upload.
-  const bool trim_n = pair && !cfg().gram_no_trim;
-  // N of a tile's MMAs: the pair kernel trims the last tile column to its valid columns (multiple of 32)
-  auto tile_ncols = [&](int tj) {
-    if (!trim_n) return int(kTileN);
-    const int64_t valid = std::min<int64_t>(kTileN, a.n - int64_t(tj) * kTileN);
-    return int(std::max<int64_t>(32, (valid + 31) / 32 * 32));
-  };
   if (macs_out) {
     int64_t cells = 0;
-    for (const T& t : tiles) cells += int64_t(tile_m) * tile_ncols(t.tj);
+    for (const T& t : tiles) cells += int64_t(tile_m) * (pair ? t.n0 + t.n1 : kTileN);
     *macs_out = cells * a.lc_pad;
   }
   char key[200];
-  snprintf(key, sizeof key, "%lld/%lld/%lld/%d/%d/%d/%d/%d/%d/%llx/%lld/%lld/%d", (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad,
+  snprintf(key, sizeof key, "%lld/%lld/%lld/%d/%d/%d/%d/%d/%d/%llx/%lld/%zu/%d/%d", (long long)a.n, (long long)a.n_pad, (long long)a.lc_pad,
            a.prod_mask, a.shard_rank, a.shard_world, ks, tile_m, int(trim_n),
-           (unsigned long long)(a.group_sorted ? a.group_sig | 1u : 0u), (long long)RI, (long long)RJ, int(prod_major));
+           (unsigned long long)(a.group_sorted ? a.group_sig | 1u : 0u), (long long)RI, RJ, int(prod_major), int(wide));
   if (ctx->items_key != key) {
     std::vector<WorkItem>& items = ctx->h_items;
     items.clear();
@@ -1154,9 +1359,12 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
       if (kb1 <= kb0) continue;
       for (const T& t : tiles) {
         if (!pair) { items.push_back({int32_t(t.prod | (t.ti << 4)), t.tj, kb0, kb1}); continue; }
+        if (wide) {
+          items.push_back({int32_t(uint32_t(t.prod) | (uint32_t(t.n0 / 16 - 1) << 4) | (uint32_t(t.n1 / 16) << 8) | (uint32_t(t.ti) << 13)), t.tj, kb0, kb1});
+          continue;
+        }
         // pair kernel: N of the MMAs trimmed to the valid columns of the last tile column (multiple of 32)
-        const int ncols = tile_ncols(t.tj);
-        items.push_back({int32_t(t.prod | ((ncols / 16 - 1) << 4) | (t.ti << 8)), t.tj, kb0, kb1});
+        items.push_back({int32_t(t.prod | ((t.n0 / 16 - 1) << 4) | (t.ti << 8)), t.tj, kb0, kb1});
       }
     }
     if (items.size() > ctx->d_items_cap) {
@@ -1195,7 +1403,21 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   p.n = int(a.n);
   p.err_flag = ctx->d_err_flag;
 
-  if (pair) {
+  if (pair && wide) {
+    if (!ctx->encode_tiled) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled entry point missing");
+    CUtensorMap cmap;   // the count matrices as one 2-D int32 tensor: the epilogue's TMA reductions add 32 x 32 boxes into it
+    cuuint64_t dims[2] = {cuuint64_t(a.ld), cuuint64_t(a.ld) * TPG_NUM_COUNT_MATS};
+    cuuint64_t strides[1] = {cuuint64_t(a.ld) * sizeof(int32_t)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+        &cmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, a.counts, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled(counts) failed (CUresult %d)", int(r));
+    const int grid = 2 * int(std::min<size_t>(n_items, size_t(units)));
+    if (a.k_major) gram_i8_wide_kernel<true><<<grid, kGramThreads, kWideSmemBytes, st>>>(maps[0], maps[1], maps[2], cmap, p);
+    else gram_i8_wide_kernel<false><<<grid, kGramThreads, kWideSmemBytes, st>>>(maps[0], maps[1], maps[2], cmap, p);
+  } else if (pair) {
     const int grid = 2 * int(std::min<size_t>(n_items, size_t(units)));  // cluster dims are compiled in
     if (a.k_major) gram_i8_pair_kernel<true><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
     else gram_i8_pair_kernel<false><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], p);

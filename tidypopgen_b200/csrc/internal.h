@@ -43,6 +43,7 @@ struct Ctx {
   int64_t launches = 0;
   bool gram_attr_set = false;
   bool mxf4_attr_set = false;
+  bool i8wide_attr_set = false;
   bool gather_attr_set = false;
   int pair_clusters = 0;           // CTA pairs resident at once (cudaOccupancyMaxActiveClusters)
   // Grow-only buffer cache, reused across jobs (cudaMalloc / cudaMallocHost / cudaFree are
