@@ -313,7 +313,7 @@ def run_b200(args, rank, world, local):
 
     def run_steps(the_job, steps, warmup):
         agg = {"ms_decode": 0.0, "ms_gram": 0.0, "ms_finish": 0.0, "launches": 0, "chunks": 0, "macs": 0, "q4": 0,
-               "i8": 0, "chain": 0}
+               "i8": 0, "chain": 0, "wide": 0}
         for _ in range(warmup):
             L.check(lib.tpg_pairwise_ctx(eng.ctx.handle, C.byref(the_job), C.byref(res), eb, len(eb)), eb)
         barrier()
@@ -331,6 +331,7 @@ def run_b200(args, rank, world, local):
             agg["macs"] += st.mma_macs
             agg["q4"] += st.n_mxf4_chunks
             agg["i8"] += st.n_i8_chunks
+            agg["wide"] += st.n_wide_launches
             agg["chain"] = max(agg["chain"], st.max_chain_loci)
         e1.record(eng.stream)
         barrier()
@@ -489,8 +490,15 @@ def run_b200(args, rank, world, local):
         issued = 2 * a["macs"] / (ms_total * 1e-3) / 1e12
         tag = "mxf4" if route == "q4" else "i8"
         peak = mma.get(f"{tag}_sustained_tops") or ((4.0 if route == "q4" else 2.0) * pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
-        kern = ("gram_mxf4_pair_kernel (tcgen05.mma.cta_group::2.kind::mxf4.block_scale, E2M1 x E2M1 -> f32, exact integer sums)"
-                if route == "q4" else "gram_i8_pair_kernel (tcgen05.mma.cta_group::2.kind::i8, int8 x int8 -> s32)")
+        wide = a["wide"] > 0   # tpg_stats.n_wide_launches: the wide-tile kernels (TMA-reduction epilogue) ran
+        if route == "q4":
+            kern = (("gram_mxf4_wide_kernel: 256 x 480 tiles, cp.reduce.async.bulk.tensor epilogue" if wide else
+                     "gram_mxf4_pair_kernel: 256 x 240 tiles, ping-pong accumulators") +
+                    " (tcgen05.mma.cta_group::2.kind::mxf4.block_scale, E2M1 x E2M1 -> f32, exact integer sums)")
+        else:
+            kern = (("gram_i8_wide_kernel: 256 x 512 tiles, cp.reduce.async.bulk.tensor epilogue" if wide else
+                     "gram_i8_pair_kernel: 256 x 256 tiles, ping-pong accumulators") +
+                    " (tcgen05.mma.cta_group::2.kind::i8, int8 x int8 -> s32)")
         return {"kernel": kern, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic_from_profile().get("gram_mxf4_c4_dram_bytes_per_launch" if route == "q4" else "gram_i8_c4_dram_bytes_per_launch"),
                 "per_gpu": True, "avg_launch_ms": t_launch, "launches_per_step": launches // max(1, nsteps),

@@ -144,6 +144,8 @@ typedef struct tpg_stats {
   int64_t n_direct_io;     /* chunks read with O_DIRECT (page cache bypassed)              */
   int64_t n_cached_jobs;   /* 1 if the count matrices came from the context's cache       */
   double ms_reduce;        /* multi-GPU: summing the count matrices over NVLink            */
+  int64_t n_wide_launches; /* Gram launches that ran a wide-tile kernel (256 x 480 4-bit / 256 x 512 int8, *
+                            * TMA-reduction epilogue) rather than a ping-pong pair kernel                */
 } tpg_stats;
 
 /* Longest accumulation chain a 4-bit (kind::mxf4, FP32 accumulator) work item may run. */

@@ -83,6 +83,7 @@ class Stats(C.Structure):
         ("n_direct_io", C.c_int64),
         ("n_cached_jobs", C.c_int64),
         ("ms_reduce", C.c_double),
+        ("n_wide_launches", C.c_int64),
     ]
 
     def as_dict(self) -> dict:

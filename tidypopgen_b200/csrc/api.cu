@@ -603,7 +603,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   TPG_CUDA_OK(cudaStreamWaitEvent(s_dec, ev_start, 0), E);
   std::vector<Ctx::ChunkEv>& tm = ctx->pend_ev;
   tm.assign(n_chunks, Ctx::ChunkEv{});
-  int64_t macs = 0, max_chain = 0;
+  int64_t macs = 0, max_chain = 0, n_wide = 0;
   double ms_read = 0;
   // hybrid link/core scheduling state (see the chunk loop)
   cudaEvent_t ev_pin_free[2] = {B.ev(false), B.ev(false)};
@@ -928,6 +928,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     ga.counts = d_counts;
     ga.ld = pl.n_pad;
     ga.max_chain_out = &max_chain;
+    ga.wide_out = &n_wide;
     ga.group_sorted = group_sorted;
     ga.group_sig = group_sig;
     int64_t mm = 0;
@@ -950,6 +951,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   st->n_packed_chunks += n_packed;
   st->n_mxf4_chunks += n_q4;
   st->n_i8_chunks += n_i8;
+  st->n_wide_launches += n_wide;
   st->max_chain_loci = std::max(st->max_chain_loci, max_chain);
   st->bytes_file += file_bytes.load();
   st->n_direct_io += n_dio;
@@ -1405,6 +1407,7 @@ static int pairwise_multi(const tpg_job* job, const int32_t* stats, int nstats, 
     S.n_packed_chunks += sts[r].n_packed_chunks;
     S.n_mxf4_chunks += sts[r].n_mxf4_chunks;
     S.n_i8_chunks += sts[r].n_i8_chunks;
+    S.n_wide_launches += sts[r].n_wide_launches;
     S.n_direct_io += sts[r].n_direct_io;
     S.mma_macs += sts[r].mma_macs;
     S.n_launches += sts[r].n_launches;

@@ -1198,6 +1198,7 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   p.n = int(a.n);
   p.err_flag = ctx->d_err_flag;
   const int grid = 2 * int(std::min<size_t>(n_items, size_t(units)));
+  if (wide && a.wide_out) ++*a.wide_out;
   if (wide) {
     // the count matrices as one 2-D int32 tensor (rows i fastest, the four matrices stacked along j): the
     // epilogue's TMA reductions add 32 x 32 boxes into it
@@ -1403,6 +1404,7 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   p.n = int(a.n);
   p.err_flag = ctx->d_err_flag;
 
+  if (pair && wide && a.wide_out) ++*a.wide_out;
   if (pair && wide) {
     if (!ctx->encode_tiled) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled entry point missing");
     CUtensorMap cmap;   // the count matrices as one 2-D int32 tensor: the epilogue's TMA reductions add 32 x 32 boxes into it

@@ -142,6 +142,7 @@ struct GramArgs {
   int32_t* counts;
   int64_t ld;
   int64_t* max_chain_out = nullptr;  // 4-bit route: longest accumulation chain (loci) of the launch
+  int64_t* wide_out = nullptr;       // incremented when the launch ran a wide-tile kernel
   // Block-diagonal jobs (one KING per group, individuals sorted by group): host array of n non-decreasing
   // group ids; only tiles that hold at least one same-group pair are computed.  nullptr = every tile.
   const int32_t* group_sorted = nullptr;
