@@ -980,6 +980,23 @@ static int make_plane_map(Ctx* ctx, CUtensorMap* out, const int8_t* base, uint64
   return TPG_OK;
 }
 
+// The persistent CTA pairs take work items round-robin (item = pair index + k * pairs), and they share operand panels
+// through L2 only while they walk the list side by side.  Items of unequal cost break that: a pair that drew a few
+// narrow items runs ahead, the resident items spread over more neighbourhoods than L2 holds.  (Measured, int8 wide
+// kernel at C4, one of 2 tile-sharded ranks: a 3840-column region is 7 items of 512 columns + 1 of 256, and the rank
+// ran 28 % slower per MAC than the unsharded job, whose items are all alike.)  So the list is cut into runs of equal
+// cost: all full-width items first, in their L2 order, then the narrower ones by width — within a run every pair
+// finishes its item at the same time again.
+template <class T>
+static void equal_cost_runs(std::vector<T>& tiles) {
+  int full = 0;
+  for (const T& t : tiles) full = std::max(full, t.n0 + t.n1);
+  std::stable_sort(tiles.begin(), tiles.end(), [full](const T& x, const T& y) {
+    const int wx = x.n0 + x.n1, wy = y.n0 + y.n1;
+    return (wx == full) != (wy == full) ? wx == full : wx > wy;
+  });
+}
+
 // Chooses how many k-splits a tile gets so that the persistent CTAs finish together.
 static int choose_ksplit(int64_t n_tile_items, int64_t kblocks, int sms, int default_max_kblocks = 128) {
   const tpg_config C = cfg();
@@ -1133,6 +1150,7 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
           }
         }
   if (tiles.empty()) { if (macs_out) *macs_out = 0; return TPG_OK; }
+  if (wide) equal_cost_runs(tiles);
   // (the wide kernel's epilogue is exposed, so its items are longer: 256 k-blocks = 65,536 loci; C4 sweep,
   //  profiles/r02_gram_sweep.jsonl: 96 -> 810 ms, 128 -> 789, 192 -> 780, 256 -> 772, 384 -> 769)
   int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units, (wide && big) ? 256 : 128);
@@ -1338,6 +1356,7 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
           }
         }
   if (tiles.empty()) { if (macs_out) *macs_out = 0; return TPG_OK; }
+  if (wide) equal_cost_runs(tiles);
 
   const int ks = choose_ksplit(int64_t(tiles.size()), kblocks, units);
 
