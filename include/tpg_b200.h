@@ -215,9 +215,10 @@ typedef struct tpg_config {
   int32_t no_thp;             /* TPG_NO_THP: 1 = no MADV_HUGEPAGE on result matrices */
   int32_t decode_k4_v1;       /* TPG_DECODE_K4_V1: 1 = first build of the 4-bit decode kernel (cross-check) */
   int32_t host_threads;       /* TPG_HOST_THREADS: staging worker threads, 0 = cores / local ranks (max 32) */
-  int32_t scan_loci_per_cta;  /* TPG_SCAN_LOCI: 0 = 256 */
+  int32_t scan_loci_per_cta;  /* TPG_SCAN_LOCI: 0 = auto */
   int32_t scan_no_indiv;      /* TPG_SCAN_NO_INDIV: debugging */
-  int32_t scan_table;         /* TPG_SCAN_TABLE: 1 = always the table-lookup scan kernel (cross-check) */
+  int32_t scan_table;         /* TPG_SCAN_TABLE: scan kernel, 0 = auto, 1 = lookup table (any code table), 2 = table-free, *
+                               * 16-locus rounds, 3 = table-free, warp per locus (auto: n >= 512)                        */
   int32_t cache_counts;       /* TPG_CACHE_COUNTS: 1 = a file-sourced job computes all four count matrices and keeps *
                                * them in the context; the next job on the same file (size, mtime), ind.row and     *
                                * ind.col finishes from them without touching the genotypes (pairwise_king, then    *

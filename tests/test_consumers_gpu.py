@@ -187,12 +187,14 @@ def test_scans_example(example_gt):
 
 
 @pytest.mark.parametrize("case", [(929, 3000, "all", "all"), (300, 2000, "shuffle", "shuffle"), (1500, 700, "window", "every3"),
-                                  (64, 5000, "dup", "all"), (2500, 513, "subset", "subset")])
+                                  (64, 5000, "dup", "all"), (2500, 513, "subset", "subset"),
+                                  (1027, 801, "window", "all"), (4102, 333, "all", "all")])
 @pytest.mark.parametrize("src_kind", ["file", "device", "pinned"])
-@pytest.mark.parametrize("table_kernel", [0, 1], ids=["table_free", "lut"])
+@pytest.mark.parametrize("table_kernel", [0, 1, 2, 3], ids=["auto", "lut", "rounds", "warp"])
 def test_scans_random_parity(case, src_kind, table_kernel, tpg_cfg):
-    """Every case on both scan kernels: the table-free build (standard code tables, contiguous rows and
-    loci — the other cases fall back by themselves) and the lookup-table one (tpg_config.scan_table)."""
+    """Every case on every scan kernel (tpg_config.scan_table): the two table-free builds (standard code tables,
+    contiguous rows and loci — warp per locus from 512 individuals on, 16-locus rounds below; the other cases
+    fall back by themselves) and the lookup-table one."""
     import torch
     from test_parity_gpu import pick
 

@@ -63,7 +63,7 @@ void tpg_config_init(tpg_config* c) {
   c->host_threads = env_int("TPG_HOST_THREADS", 0);
   c->scan_loci_per_cta = env_int("TPG_SCAN_LOCI", 0);
   c->scan_no_indiv = env_set("TPG_SCAN_NO_INDIV") ? 1 : 0;
-  c->scan_table = env_set("TPG_SCAN_TABLE") ? 1 : 0;
+  c->scan_table = env_int("TPG_SCAN_TABLE", 0);
   c->cache_counts = env_set("TPG_CACHE_COUNTS") ? 1 : 0;
   c->device_chunk_loci = env_ll("TPG_DEVICE_CHUNK_LOCI", 0);
   c->host_chunk_mb = env_ll("TPG_HOST_CHUNK_MB", 0);
@@ -90,6 +90,7 @@ int tpg_config_set(const tpg_config* c, char* err, size_t errlen) {
   if (c->io_mode < 0 || c->io_mode > 2) return fail("io_mode must be 0 (page cache), 1 (O_DIRECT) or 2 (mmap)");
   if (c->host_threads < 0 || c->host_threads > 1024) return fail("host_threads out of range");
   if (c->scan_loci_per_cta < 0) return fail("scan_loci_per_cta must be >= 0");
+  if (c->scan_table < 0 || c->scan_table > 3) return fail("scan_table must be 0 (auto), 1 (lookup table), 2 (16-locus rounds) or 3 (warp per locus)");
   if (c->device_chunk_loci < 0 || c->host_chunk_mb < 0) return fail("chunk sizes must be >= 0");
   if (c->link_gbps < 0 || c->hybrid_factor < 0) return fail("link_gbps / hybrid_factor must be >= 0");
   std::lock_guard<std::mutex> lk(g_mu);

@@ -1231,6 +1231,136 @@ scan_counts_fast_kernel(const DecodeParams p, const ScanParams sp) {
       }
 }
 
+// Warp-per-locus build of the table-free scan.  scan_counts_fast_kernel spends 45 instructions per word of four
+// genotypes (ncu: 0.36 warp instructions per byte, issue-bound at 0.29 of the HBM figure): every word pays for its own
+// horizontal reduction (three dp4a, packing, one REDUX) and for two loads and a funnel shift, and every round of
+// 16 loci for two block barriers.  Here a WARP owns a locus: a lane takes 8 words of it (32 individuals), adds their
+// contributions vertically — the dp4a accumulates — and the warp reduces once per locus (two REDUX for 256 words).
+// The words are the ALIGNED words of the buffer: a locus that starts at byte `a` (mod 4) of its first word simply has
+// its individuals shifted by `a` byte lanes, and since the 8 warps of a CTA take every 8th locus, `a` is the same for
+// all loci of a warp (8 x stride = 0 mod 4) — the lane's weights, ploidies and per-individual counters are laid out
+// once for that shift.  Byte lanes outside the locus (the neighbours' genotypes in the first and last word, the
+// over-read of the last word block) carry weight 0 and their counters are dropped, so nothing is masked in the
+// loop; only words that would leave the buffer take a byte-wise loader.  No shared memory, no block barrier.
+// ~17 instructions per word.  Contiguous rows and loci (launch_scan); outputs bit for bit those of the other builds.
+constexpr int kScanWarpWords = 8;                        // words per lane and locus
+constexpr int kScanWordsPerCta = 32 * kScanWarpWords;   // 256 words = 1 KiB of a locus per CTA
+
+__device__ __forceinline__ uint32_t scan_word_checked(const uint8_t* q, const uint8_t* lo, const uint8_t* hi) {
+  uint32_t g = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) g |= uint32_t((q + b >= lo && q + b < hi) ? q[b] : 0xFFu) << (8 * b);
+  return g;
+}
+
+template <bool kImpute>
+__global__ void __launch_bounds__(kDecThreads, 3)
+scan_counts_warp_kernel(const DecodeParams p, const ScanParams sp) {
+  constexpr int R = kScanWarpWords;
+  constexpr int kWarps = kDecThreads / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwb = ((p.n + 6) / 4 + kScanWordsPerCta - 1) / kScanWordsPerCta;  // a locus touches <= ceil((3 + n) / 4) words
+  const int wb = blockIdx.x % nwb, lb = blockIdx.x / nwb;
+  __shared__ int32_t tot_s[2][4 * kScanWordsPerCta + 8];  // per-individual totals of the CTA: [het | missing][4 (j - first word) - a + b + 4]
+  const int lend = min((lb + 1) * sp.loci_per_cta, p.lc);
+  int l = lb * sp.loci_per_cta + warp;
+  for (int k = threadIdx.x; k < 2 * (4 * kScanWordsPerCta + 8); k += kDecThreads) (&tot_s[0][0])[k] = 0;
+  __syncthreads();
+  const uint8_t* col = p.raw + (p.col0 + l) * p.raw_stride + p.row0;
+  const int a = int(reinterpret_cast<uintptr_t>(col) & 3u);
+  const int j0 = wb * kScanWordsPerCta + lane;           // word r of this lane: j0 + 32 r; individuals 4 j - a + b
+  uint32_t w4[R], f4[R], het4[R], na4[R];
+  uint32_t pl_lane = 0;                                  // sum of ploidy over this lane's individuals
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    w4[r] = f4[r] = het4[r] = na4[r] = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int ind = 4 * (j0 + 32 * r) - a + b;
+      if (ind >= 0 && ind < p.n) {
+        const uint32_t pl = sp.ploidy[ind];
+        w4[r] |= uint32_t(sp.weight[ind]) << (8 * b);
+        f4[r] |= (1u + 64u * pl) << (8 * b);             // one dp4a: missing count + 64 x missing ploidy
+        pl_lane += pl;
+      }
+    }
+  }
+  const uint8_t* wp = col - a + 4 * int64_t(j0);         // this lane's first (aligned) word of the locus
+  const int64_t step = int64_t(kWarps) * p.raw_stride;
+  auto load = [&](const uint8_t* q, uint32_t (&g)[R]) {
+    const uint8_t* q0 = q - 4 * lane;                    // the warp's first byte (uniform)
+    if (q0 >= p.raw && q0 + 4 * kScanWordsPerCta <= p.raw_end) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) g[r] = __ldg(reinterpret_cast<const uint32_t*>(q + 128 * r));
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) g[r] = scan_word_checked(q + 128 * r, p.raw, p.raw_end);
+    }
+  };
+  auto consume = [&](const uint32_t (&gin)[R], int locus) {
+    uint32_t alt = 0, nn = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      uint32_t g = gin[r];
+      uint32_t t = (g & 0x7F7F7F7Fu) + 0x7D7D7D7Du;      // bit 7 set iff (byte & 127) >= 3
+      uint32_t m7 = (t | g) & 0x80808080u;               // bit 7 set iff byte > 2
+      if (kImpute) {                                     // 4 / 5 / 6 -> 0 / 1 / 2, then classify again
+        g ^= m7 >> 5;
+        t = (g & 0x7F7F7F7Fu) + 0x7D7D7D7Du;
+        m7 = (t | g) & 0x80808080u;
+      }
+      const uint32_t na01 = m7 >> 7;
+      const uint32_t dos = g & ~((m7 - na01) | m7);      // missing bytes -> 0; the typed ones are their dosage
+      alt = __dp4a(dos, w4[r], alt);                     // x weight
+      nn = __dp4a(na01, f4[r], nn);
+      het4[r] += dos & 0x01010101u;                      // dosage 1
+      na4[r] += na01;
+    }
+    // per lane: nn & 63 = missing individuals (<= 32), nn >> 6 = their ploidy (<= 64)
+    const uint32_t alt_t = __reduce_add_sync(0xFFFFFFFFu, alt);
+    const uint32_t t2 = __reduce_add_sync(0xFFFFFFFFu, (nn & 63u) | ((pl_lane - (nn >> 6)) << 16));
+    if (lane == 0) {
+      const int32_t val = int32_t(t2 >> 16), nal = int32_t(t2 & 0xFFFFu);
+      // reductions, also where this warp is the only writer (nwb == 1): a load - add - store would stall it three times
+      atomicAdd(sp.alt2 + locus, int32_t(alt_t)); atomicAdd(sp.valid + locus, val); atomicAdd(sp.na_l + locus, nal);
+    }
+  };
+  // two loci in flight per warp: 16 independent loads per lane
+  for (; l < lend; l += 2 * kWarps, wp += 2 * step) {
+    uint32_t g0[R], g1[R];
+    const bool two = l + kWarps < lend;
+    load(wp, g0);
+    if (two) load(wp + step, g1);
+    consume(g0, l);
+    if (two) consume(g1, l + kWarps);
+  }
+  // per-individual counters: summed over the CTA's warps in shared memory (the warps' byte lanes are shifted against
+  // each other by their `a`), then one global reduction per individual and CTA — with every warp reducing for itself
+  // the 929 counters of C2 took 14.5 M same-address atomics and the kernel 0.57 ms
+  if (!(sp.flags & 1)) {
+    if (lb * sp.loci_per_cta + warp < lend) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int k = 4 * (lane + 32 * r) - a + b + 4;
+          const int h = int((het4[r] >> (8 * b)) & 0xFFu), m = int((na4[r] >> (8 * b)) & 0xFFu);
+          if (h) atomicAdd(&tot_s[0][k], h);
+          if (m) atomicAdd(&tot_s[1][k], m);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 4 * kScanWordsPerCta + 8; k += kDecThreads) {
+      const int ind = 4 * wb * kScanWordsPerCta + k - 4;
+      if (ind >= 0 && ind < p.n) {
+        const int h = tot_s[0][k], m = tot_s[1][k];
+        if (h) atomicAdd(sp.het_n + ind, h);
+        if (m) atomicAdd(sp.na_n + ind, m);
+      }
+    }
+  }
+}
+
 int launch_scan(Ctx* ctx, const DecodeArgs& a, const ScanArgs& s, cudaStream_t st, const Err& E) {
   if (a.n <= 0 || a.lc <= 0 || a.n > INT32_MAX / 2 || a.lc > INT32_MAX / 2)
     return E.fail(TPG_ERR_ARG, "scan: bad geometry n=%lld lc=%lld", (long long)a.n, (long long)a.lc);
@@ -1260,8 +1390,29 @@ int launch_scan(Ctx* ctx, const DecodeArgs& a, const ScanArgs& s, cudaStream_t s
   if (blocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "scan: chunk too large for one launch");
   // the table-free build: a standard code table, contiguous rows and loci, a stride the 32-bit address
   // arithmetic of the fast loads can take
-  const bool fast = s.std_table != 0 && !C.scan_table && !a.row_idx && !a.col_idx && !a.packed &&
-                    a.raw_stride < (int64_t(1) << 27);
+  // tpg_config.scan_table: 0 = auto, 1 = the lookup-table kernel, 2 = the 16-locus-round kernel, 3 = the warp-per-locus kernel
+  const bool contiguous = s.std_table != 0 && C.scan_table != 1 && !a.row_idx && !a.col_idx && !a.packed;
+  // warp per locus: worth it once a locus fills most of a CTA's 256 words (n >= 512); its byte counters hold 255 loci per warp
+  if (contiguous && (C.scan_table == 3 || (C.scan_table == 0 && a.n >= 512))) {
+    const int64_t nwb = ((a.n + 6) / 4 + kScanWordsPerCta - 1) / kScanWordsPerCta;
+    int lpc;
+    if (C.scan_loci_per_cta > 0) lpc = std::min(2032, std::max(8, C.scan_loci_per_cta / 8 * 8));
+    else {  // whole waves of 3 CTAs per SM, at most 1024 loci per CTA (the per-individual atomics are paid once per CTA)
+      const int64_t slots = int64_t(ctx->num_sms) * 3;
+      const int64_t waves = std::max<int64_t>(1, (nwb * a.lc + 1024 * slots - 1) / (1024 * slots));
+      const int64_t groups = std::max<int64_t>(1, waves * slots / nwb);
+      lpc = int(std::min<int64_t>(2032, std::max<int64_t>(64, ((a.lc + groups - 1) / groups + 7) / 8 * 8)));
+    }
+    sp.loci_per_cta = lpc;
+    const int64_t wblocks = nwb * ((a.lc + lpc - 1) / lpc);
+    if (wblocks > INT32_MAX) return E.fail(TPG_ERR_ARG, "scan: chunk too large for one launch");
+    if (s.std_table == 2) scan_counts_warp_kernel<true><<<unsigned(wblocks), kDecThreads, 0, st>>>(p, sp);
+    else scan_counts_warp_kernel<false><<<unsigned(wblocks), kDecThreads, 0, st>>>(p, sp);
+    TPG_CUDA_OK(cudaGetLastError(), E);
+    ctx->launches++;
+    return TPG_OK;
+  }
+  const bool fast = contiguous && a.raw_stride < (int64_t(1) << 27);
   if (fast && s.std_table == 2) scan_counts_fast_kernel<true><<<unsigned(blocks), kDecThreads, 0, st>>>(p, sp);
   else if (fast) scan_counts_fast_kernel<false><<<unsigned(blocks), kDecThreads, 0, st>>>(p, sp);
   else scan_counts_kernel<<<unsigned(blocks), kDecThreads, 0, st>>>(p, sp);
