@@ -578,6 +578,26 @@ def test_hgdp_shape_properties():
     assert np.array_equal(sub[1], ref["K"]) and np.array_equal(sub[2], ref["N_Aa_i"]) and same(sub[0], ref["king"])
 
 
+def test_hgdp_shape_full_size_against_the_blas_port():
+    """C2 at FULL size (929 x 650,000, 2 % missing), every locus: the KING numerator, N_Aa_i and the finished
+    matrix equal, bit for bit, the reference's block loop restated over a threaded FP64 BLAS
+    (oracle/blas_baseline.py — pinned to oracle.c by tests/test_cpu_baseline.py) — on the default 4-bit route
+    and on the int8 route.  ~20 s of CPU dgemm."""
+    from oracle import blas_baseline as B
+    n, m = 929, 650_000
+    host = np.zeros(n * m, np.uint8)
+    L.lib().tpg_synth_fill_host(host.ctypes.data, n, m, 0, 20260002, 0.02, 0)
+    Kr, Nr, done, _ = B.king_blocks(host.reshape(m, n), n, m, O.block_size(n))
+    assert done == m
+    ref = B.king_finish(Kr, Nr)
+    X = tpg.FBMCode256.__new__(tpg.FBMCode256)
+    X.backingfile, X.nrow, X.ncol, X.code256 = "<host>", n, m, None
+    for flags in (0, L.FLAG_GRAM_I8):
+        king, K, N = tpg.snp_king_counts(X, src=(L.SRC_HOST, host.ctypes.data, host), flags=flags)
+        assert np.array_equal(K, Kr) and np.array_equal(N, Nr), flags
+        assert same(king, ref), flags
+
+
 # ------------------------------------------------------------------ sharding (staged C-ABI), ranks emulated on one GPU
 
 def _staged(engine, X, stat, bs, mode, rank, world, counts=None, finish=True, **kw):
