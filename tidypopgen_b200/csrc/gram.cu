@@ -221,16 +221,19 @@ constexpr int kPairStages = 6;
 constexpr int kPairTileM = 256;
 constexpr int kHalfBytes = 128 * kTileK;              // one 128 x 128 box, 16 KiB
 constexpr int kPairStageBytes = 2 * kHalfBytes;       // per CTA: A half + B half
-constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + 1024 + 256;
+constexpr int kPairEpiBytes = 4 * 2 * 4096;             // epilogue staging: per warp two 32 x 32 int32 boxes (TMA reductions)
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kPairEpiBytes + 1024 + 256;
 
 template <bool kMajorK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGramThreads, 1)
 gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_nm,
-                    const __grid_constant__ CUtensorMap tm_h1, const GramParams p) {
+                    const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_counts,
+                    const GramParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes);
+  uint8_t* epi = smem + kPairStages * kPairStageBytes;   // [4 warps][2][32 x 32 int32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + kPairEpiBytes);
   uint64_t* full_bar = bars;                          // [kPairStages] used in the leader only
   uint64_t* empty_bar = bars + kPairStages;           // [kPairStages] in each CTA
   uint64_t* tfull_bar = bars + 2 * kPairStages;       // [2] in each CTA
@@ -246,6 +249,7 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_const
     tma_prefetch_desc(&tm_d);
     tma_prefetch_desc(&tm_nm);
     tma_prefetch_desc(&tm_h1);
+    tma_prefetch_desc(&tm_counts);
     for (int s = 0; s < kPairStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -340,19 +344,23 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_const
     __syncwarp();
   } else {
     // ===================================================== epilogue (warps 2..5, both CTAs)
+    // 32 x 32 boxes go through a staging buffer in shared memory and ONE TMA reduction each (as in the wide kernels):
+    // with red.global — ~1.3 cycles per lane and value — draining a 128 x 256 accumulator took longer than the MMAs of a
+    // short item (C2: 69 k-blocks), and the ping-pong hid nothing.  Whole boxes are added: entries below the diagonal of
+    // the symmetric products receive values too (nothing reads them), padding rows / columns add zeros.
     const int q = warp & 3;
-    int acc = 0;
+    int acc = 0, buf = 0;
     uint32_t acc_phase = 0;
+    uint8_t* ebase = epi + q * 2 * 4096;
     for (int it = cluster; it < p.n_items; it += n_clusters) {
       const WorkItem w = p.items[it];
       const int prod = w.prod_ti & 15, ti = w.prod_ti >> 8, tj = w.tj;
       const int ncols = (((w.prod_ti >> 4) & 15) + 1) * 16;   // multiple of 32 (host)
-      const bool sym = prod != TPG_MAT_HN;
       mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
       tc_fence_after();
-      const int i = ti * kPairTileM + int(rank) * 128 + q * 32 + lane;
+      const int i0 = ti * kPairTileM + int(rank) * 128 + q * 32;   // this warp's 32 rows
       const int j0 = tj * kTileN;
-      int32_t* cbase = p.counts + int64_t(prod) * p.mat_stride + i;
+      const int jmat = prod * int(p.ld);                           // the count matrices are stacked along j
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kTileN);
 #pragma unroll 1
       for (int c = 0; c < ncols; c += 32) {
@@ -364,17 +372,26 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
         }
-        if (j0 + c < p.n && i < p.n) {
+        if (j0 + c < p.n && i0 < p.n) {                            // warp-uniform
+          if (lane == 0) bulk_wait_group_read<1>();                // the staging box used two chunks ago has been read
+          __syncwarp();
+          int32_t* box = reinterpret_cast<int32_t*>(ebase + buf * 4096);   // [32 columns][32 rows]
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const int j = j0 + c + jj;
-            if (j < p.n && (!sym || i <= j)) atomicAdd(cbase + int64_t(j) * p.ld, int32_t(v[jj]));
+          for (int jj = 0; jj < 32; ++jj) box[jj * 32 + lane] = int32_t(v[jj]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tm_counts, box, i0, jmat + j0 + c);
+            bulk_commit_group();
           }
+          buf ^= 1;
         }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) bulk_wait_group<0>();   // every reduction of this warp has landed before the CTA exits
+    __syncwarp();
   }
 
   // No CTA may leave while its partner can still signal its barriers or read its smem.
@@ -403,11 +420,13 @@ constexpr int kQStageLoci = 256;
 template <int kDummy>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGramThreads, 1)
 gram_mxf4_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_nm,
-                      const __grid_constant__ CUtensorMap tm_h1, const GramParams p) {
+                      const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_counts,
+                      const GramParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes);
+  uint8_t* epi = smem + kPairStages * kPairStageBytes;   // [4 warps][2][32 x 32 int32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + kPairEpiBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kPairStages;
   uint64_t* tfull_bar = bars + 2 * kPairStages;
@@ -423,6 +442,7 @@ gram_mxf4_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
     tma_prefetch_desc(&tm_d);
     tma_prefetch_desc(&tm_nm);
     tma_prefetch_desc(&tm_h1);
+    tma_prefetch_desc(&tm_counts);
     for (int s = 0; s < kPairStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -516,19 +536,20 @@ gram_mxf4_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
     __syncwarp();
   } else {
     // ===================================================== epilogue (warps 2..5, both CTAs)
+    // TMA reductions of 32 x 32 boxes, as in gram_i8_pair_kernel (the values are converted to int32 first)
     const int q = warp & 3;
-    int acc = 0;
+    int acc = 0, buf = 0;
     uint32_t acc_phase = 0;
+    uint8_t* ebase = epi + q * 2 * 4096;
     for (int it = cluster; it < p.n_items; it += n_clusters) {
       const WorkItem w = p.items[it];
       const int prod = w.prod_ti & 15, ti = w.prod_ti >> 8;
       const int ncols = (((w.prod_ti >> 4) & 15) + 1) * 16;   // >= 32
-      const bool sym = prod != TPG_MAT_HN;
       mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
       tc_fence_after();
-      const int i = ti * kPairTileM + int(rank) * 128 + q * 32 + lane;
+      const int i0 = ti * kPairTileM + int(rank) * 128 + q * 32;   // this warp's 32 rows
       const int j0 = w.tj;
-      int32_t* cbase = p.counts + int64_t(prod) * p.mat_stride + i;
+      const int jmat = prod * int(p.ld);
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * 256);
 #pragma unroll 1
       for (int c = 0; c < ncols; c += 32) {
@@ -543,18 +564,27 @@ gram_mxf4_pair_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
         }
-        if (j0 + cc < p.n && i < p.n) {
+        if (j0 + cc < p.n && i0 < p.n) {                           // warp-uniform
+          if (lane == 0) bulk_wait_group_read<1>();
+          __syncwarp();
+          int32_t* box = reinterpret_cast<int32_t*>(ebase + buf * 4096);   // [32 columns][32 rows]
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const int j = j0 + cc + jj;
-            if (jj >= first && j < p.n && (!sym || i <= j))
-              atomicAdd(cbase + int64_t(j) * p.ld, __float2int_rn(__uint_as_float(v[jj])));
+          for (int jj = 0; jj < 32; ++jj)   // columns already added by the previous (overlapping) chunk add zero
+            box[jj * 32 + lane] = jj >= first ? __float2int_rn(__uint_as_float(v[jj])) : 0;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tm_counts, box, i0, jmat + j0 + cc);
+            bulk_commit_group();
           }
+          buf ^= 1;
         }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) bulk_wait_group<0>();
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -980,6 +1010,21 @@ static int make_plane_map(Ctx* ctx, CUtensorMap* out, const int8_t* base, uint64
   return TPG_OK;
 }
 
+// The count matrices as one 2-D int32 tensor (rows i fastest, the four matrices stacked along j): the epilogues' TMA
+// reductions add 32 x 32 boxes into it.
+static int make_counts_map(Ctx* ctx, CUtensorMap* out, int32_t* counts, int64_t ld, const Err& E) {
+  if (!ctx->encode_tiled) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled entry point missing");
+  cuuint64_t dims[2] = {cuuint64_t(ld), cuuint64_t(ld) * TPG_NUM_COUNT_MATS};
+  cuuint64_t strides[1] = {cuuint64_t(ld) * sizeof(int32_t)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      out, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, counts, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled(counts) failed (CUresult %d)", int(r));
+  return TPG_OK;
+}
+
 // The persistent CTA pairs take work items round-robin (item = pair index + k * pairs), and they share operand panels
 // through L2 only while they walk the list side by side.  Items of unequal cost break that: a pair that drew a few
 // narrow items runs ahead, the resident items spread over more neighbourhoods than L2 holds.  (Measured, int8 wide
@@ -1217,19 +1262,9 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
   p.err_flag = ctx->d_err_flag;
   const int grid = 2 * int(std::min<size_t>(n_items, size_t(units)));
   if (wide && a.wide_out) ++*a.wide_out;
+  CUtensorMap cmap;
+  if (int rc = make_counts_map(ctx, &cmap, a.counts, a.ld, E)) return rc;
   if (wide) {
-    // the count matrices as one 2-D int32 tensor (rows i fastest, the four matrices stacked along j): the
-    // epilogue's TMA reductions add 32 x 32 boxes into it
-    if (!ctx->encode_tiled) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled entry point missing");
-    CUtensorMap cmap;
-    cuuint64_t dims[2] = {cuuint64_t(a.ld), cuuint64_t(a.ld) * TPG_NUM_COUNT_MATS};
-    cuuint64_t strides[1] = {cuuint64_t(a.ld) * sizeof(int32_t)};
-    cuuint32_t box[2] = {32, 32};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-        &cmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, a.counts, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled(counts) failed (CUresult %d)", int(r));
     CUtensorMap bmaps[3];
     for (int pl = 0; pl < 3; ++pl) {
       const bool present = pl < 2 || (a.prod_mask & ((1 << TPG_MAT_HH) | (1 << TPG_MAT_HN)));
@@ -1239,7 +1274,7 @@ static int launch_gram_mxf4(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_
     }
     gram_mxf4_wide_kernel<0><<<grid, kGramThreads, kWideSmemBytes, st>>>(maps[0], maps[1], maps[2], bmaps[0], bmaps[1], bmaps[2], cmap, p);
   }
-  else gram_mxf4_pair_kernel<0><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
+  else gram_mxf4_pair_kernel<0><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], cmap, p);
   TPG_CUDA_OK(cudaGetLastError(), E);
   ctx->launches++;
   return TPG_OK;
@@ -1424,24 +1459,16 @@ int launch_gram(Ctx* ctx, const GramArgs& a, cudaStream_t st, int64_t* macs_out,
   p.err_flag = ctx->d_err_flag;
 
   if (pair && wide && a.wide_out) ++*a.wide_out;
+  CUtensorMap cmap;
+  if (pair) if (int rc = make_counts_map(ctx, &cmap, a.counts, a.ld, E)) return rc;
   if (pair && wide) {
-    if (!ctx->encode_tiled) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled entry point missing");
-    CUtensorMap cmap;   // the count matrices as one 2-D int32 tensor: the epilogue's TMA reductions add 32 x 32 boxes into it
-    cuuint64_t dims[2] = {cuuint64_t(a.ld), cuuint64_t(a.ld) * TPG_NUM_COUNT_MATS};
-    cuuint64_t strides[1] = {cuuint64_t(a.ld) * sizeof(int32_t)};
-    cuuint32_t box[2] = {32, 32};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-        &cmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, a.counts, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return E.fail(TPG_ERR_CUDA, "cuTensorMapEncodeTiled(counts) failed (CUresult %d)", int(r));
     const int grid = 2 * int(std::min<size_t>(n_items, size_t(units)));
     if (a.k_major) gram_i8_wide_kernel<true><<<grid, kGramThreads, kWideSmemBytes, st>>>(maps[0], maps[1], maps[2], cmap, p);
     else gram_i8_wide_kernel<false><<<grid, kGramThreads, kWideSmemBytes, st>>>(maps[0], maps[1], maps[2], cmap, p);
   } else if (pair) {
     const int grid = 2 * int(std::min<size_t>(n_items, size_t(units)));  // cluster dims are compiled in
-    if (a.k_major) gram_i8_pair_kernel<true><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
-    else gram_i8_pair_kernel<false><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
+    if (a.k_major) gram_i8_pair_kernel<true><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], cmap, p);
+    else gram_i8_pair_kernel<false><<<grid, kGramThreads, kPairSmemBytes, st>>>(maps[0], maps[1], maps[2], cmap, p);
   } else {
     const int grid = int(std::min<size_t>(n_items, size_t(units)));
     if (a.k_major) gram_i8_kernel<true><<<grid, kGramThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], p);
