@@ -567,6 +567,61 @@ def traffic_from_profile():
 
 # ---------------------------------------------------------------------------- extras: the other named shapes
 
+def c2_file_jobs(args, tpg, L, lib, eb, eng, dev, local):
+    """configs[1] (929 x 650,000) from a .bk FILE to host matrices, wall clock per call: streamed (pread + 2-bit pack
+    + H2D, as every first job runs), and with tpg_config.cache_genotypes — the first whole-file job leaves the packed
+    image in HBM (155 MB) and the jobs an R session runs next (another statistic, a QC'd subset of individuals, a
+    thinned set of loci) gather from it on the device."""
+    import torch
+    n, m = 929, 650_000
+    raw = torch.empty(n * m + 64, dtype=torch.uint8, device=dev)
+    L.check(lib.tpg_synth_fill(eng.ctx.handle, raw.data_ptr(), n, m, 0, 20260002, 0.02, 0, eb, len(eb)), eb)
+    path = os.path.join(args.tmpdir, f"tpg_bench_c2_{os.getpid()}.bk")
+    write_bk_file(path, raw, n * m)
+    del raw
+    rng = np.random.default_rng(2)
+    rows = (np.sort(rng.permutation(n)[:800]) + 1).astype(np.int32)          # 800 of the 929 individuals kept by a QC step
+    cols = (np.arange(0, m, 5) + 1).astype(np.int32)                          # every 5th locus
+    out = {}
+    try:
+        X = tpg.FBMCode256(path, n, m)
+
+        def wall(f, reps=5):
+            f()
+            best = 1e30
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                f()
+                best = min(best, time.perf_counter() - t0)
+            return best * 1e3, dict(tpg.snp.last_stats)
+
+        jobs = {"king_all": lambda: tpg.snp_king(X, device=local),
+                "ibs_all": lambda: tpg.snp_ibs(X, device=local),
+                "king_800_rows": lambda: tpg.snp_king(X, rows, device=local),
+                "king_every_5th_locus": lambda: tpg.snp_king(X, None, cols, device=local)}
+        L.config(cache_genotypes=0)
+        ref = {k: f() for k, f in jobs.items()}
+        for k, f in jobs.items():
+            ms, st = wall(f)
+            out[k] = {"streamed_ms": ms, "h2d_bytes": st["bytes_h2d"]}
+        L.config(cache_genotypes=1)
+        jobs["king_all"]()                                                    # fills the cache while it streams
+        for k, f in jobs.items():
+            same = bool(np.array_equal(f(), ref[k], equal_nan=True))
+            ms, st = wall(f)
+            out[k].update(from_genotype_cache_ms=ms, cached=int(st["n_geno_cached"]), h2d_bytes_cached=st["bytes_h2d"], same_result=same)
+        out["note"] = "wall clock per call, host matrix included; best of 5"
+    finally:
+        L.config(cache_genotypes=0)
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+        lib.tpg_ctx_trim(eng.ctx.handle)
+        lib.tpg_release(local)
+    return out
+
+
 def run_extras(args, rank, world, local, eng, gloo):
     """C2 / C3 / C5 of BASELINE.json on the same GPUs.  N = 1: one tpg_pairwise_ctx call per step.  N > 1:
     loci-sharded STRONG scaling — every rank decodes and multiplies its slice of the loci, ONE NCCL all-reduce
@@ -671,6 +726,8 @@ def run_extras(args, rank, world, local, eng, gloo):
                    "wall clock per call; value counts the pair-SNPs once")
         timed("C2_ibs_929x650k", 929, 650_000, 20260002, 0.02, 0, L.STAT_IBS_PROPORTION, 3, steps=10)
         timed("C2_allele_sharing_929x650k", 929, 650_000, 20260002, 0.02, 0, L.STAT_AS, 2, steps=10)
+    if world == 1 and not args.no_e2e:
+        out["C2_file_jobs"] = c2_file_jobs(args, tpg, L, lib, eb, eng, dev, local)
     # C3: 1000G shape, imputed bytes, GRM (configs[2])
     timed("C3_grm_2504x1M_imputed", 2504, 1_000_000, 20260003, 0.01, 1, L.STAT_GRM, 2, steps=5)
     # C5: mixed ploidy, 10 % missing, row / column subsets (configs[4])

@@ -144,6 +144,7 @@ typedef struct tpg_stats {
   int64_t n_direct_io;     /* chunks read with O_DIRECT (page cache bypassed)              */
   int64_t n_cached_jobs;   /* 1 if the count matrices came from the context's cache       */
   double ms_reduce;        /* multi-GPU: summing the count matrices over NVLink            */
+  int64_t n_geno_cached;   /* 1 if the genotypes came from the on-device 2-bit cache (tpg_config.cache_genotypes) */
   int64_t n_wide_launches; /* Gram launches that ran a wide-tile kernel (256 x 480 4-bit / 256 x 512 int8, *
                             * TMA-reduction epilogue) rather than a ping-pong pair kernel                */
 } tpg_stats;
@@ -223,6 +224,10 @@ typedef struct tpg_config {
                                * them in the context; the next job on the same file (size, mtime), ind.row and     *
                                * ind.col finishes from them without touching the genotypes (pairwise_king, then    *
                                * pairwise_ibs, then pairwise_allele_sharing on one gen_tibble = one pass)           */
+  int32_t cache_genotypes;    /* TPG_CACHE_GENOTYPES: 1 = a file-sourced job that reads the WHOLE .bk (all rows, all   *
+                               * loci) leaves its 2-bit packed image in HBM (nrow x ncol / 4 bytes); later jobs on  *
+                               * that file (same size, mtime) — any ind.row / ind.col, any statistic — gather from *
+                               * it on the device: no disk read, no host packing, no PCIe (tpg_stats.n_geno_cached) */
   int64_t device_chunk_loci;  /* TPG_DEVICE_CHUNK_LOCI: loci per chunk of a device-resident source, 0 = 2^20 */
   int64_t host_chunk_mb;      /* TPG_HOST_CHUNK_MB: raw MB per chunk of a host / file source, 0 = 48 */
   double link_gbps;           /* TPG_LINK_GBPS: PCIe model of the hybrid schedule, 0 = 45 */

@@ -10,4 +10,7 @@ print('roofline', d['roofline']['kernel'][:60], {k: d['roofline'][k] for k in ('
 r8 = d['roofline_int8']
 print('int8', r8['kernel'][:60], {k: r8[k] for k in ('achieved', 'peak', 'frac', 'ms_per_step', 'frac_of_nominal_int8_peak')})
 for k, v in d.get('extras', {}).items():
-    print(k, round(v['ms_per_step'], 3), '%.3e' % v['value'])
+    if 'ms_per_step' in v:
+        print(k, round(v['ms_per_step'], 3), '%.3e' % v['value'])
+    else:
+        print(k, json.dumps(v)[:600])

@@ -123,6 +123,47 @@ def test_counts_cache_serves_the_next_statistic(tpg_cfg, tmp_path):
     assert same(k2, O.snp_king(raw2, n, m, rows)["king"])
 
 
+@pytest.mark.parametrize("n,m", [(300, 4000), (1031, 2500)])
+def test_genotype_cache_serves_other_subsets_and_statistics(n, m, tpg_cfg, tmp_path):
+    """tpg_config.cache_genotypes: a whole-file job leaves the 2-bit packed .bk in HBM; later jobs on that file —
+    any ind.row / ind.col (all, windows, shuffles, duplicates, gathered loci), any statistic — are gathered from
+    it on the device (no chunk crosses PCIe) and equal the oracle; subset jobs do not fill the cache; a rewritten
+    file misses and refills."""
+    rng = np.random.default_rng(n + m)
+    raw = random_bk(rng, n, m, 0.07)
+    X = tpg.FBMCode256.from_bytes(raw, n, m, backingfile=tmp_path / "geno.bk")
+    tpg_cfg(cache_genotypes=1)
+    rows_sub = pick("shuffle", n, rng)
+    i0 = tpg.snp_ibs(X, rows_sub)                                 # a subset job first: streams, does not fill
+    assert tpg.snp.last_stats["n_geno_cached"] == 0 and same(i0, O.snp_ibs(raw, n, m, rows_sub)["out"])
+    k_all = tpg.snp_king(X, gpu_chunk_loci=1024)                  # the whole file, in several chunks: streams AND fills
+    st = dict(tpg.snp.last_stats)
+    assert st["n_geno_cached"] == 0 and st["bytes_h2d"] > 0 and st["n_chunks"] > 1
+    assert same(k_all, O.snp_king(raw, n, m)["king"])
+    for rk, ck in (("all", "all"), ("shuffle", "all"), ("window", "every3"), ("dup", "subset"), ("subset", "shuffle")):
+        rows, cols = pick(rk, n, rng), pick(ck, m, rng)
+        k = tpg.snp_king(X, rows, cols)
+        st = dict(tpg.snp.last_stats)
+        assert st["n_geno_cached"] == 1 and st["bytes_h2d"] == 0 and st["bytes_file"] == 0, (rk, ck, st)
+        assert same(k, O.snp_king(raw, n, m, rows, cols)["king"]), (rk, ck)
+        a = tpg.snp_allele_sharing(X, rows, cols, block_size=257)
+        assert tpg.snp.last_stats["n_geno_cached"] == 1
+        assert same(a, O.snp_allele_sharing(raw, n, m, rows, cols, block_size_=257)["as"]), (rk, ck)
+    rows = pick("subset", n, rng)
+    i8 = tpg.snp_ibs(X, rows, flags=L.FLAG_GRAM_I8)              # int8 route from the cache
+    assert tpg.snp.last_stats["n_geno_cached"] == 1 and same(i8, O.snp_ibs(raw, n, m, rows)["out"])
+    # the file changes under the same name: the stale image is not used, the next whole-file job refills
+    raw2 = random_bk(np.random.default_rng(5), n, m, 0.07)
+    os.utime(X.backingfile, ns=(1, 1))
+    np.ascontiguousarray(raw2).tofile(X.backingfile)
+    rows = pick("window", n, rng)
+    k2 = tpg.snp_king(X, rows)
+    assert tpg.snp.last_stats["n_geno_cached"] == 0 and same(k2, O.snp_king(raw2, n, m, rows)["king"])
+    tpg.snp_king(X)
+    k3 = tpg.snp_king(X, rows)
+    assert tpg.snp.last_stats["n_geno_cached"] == 1 and same(k3, k2)
+
+
 # ------------------------------------------------------------------ file-backed results (raw_counts)
 
 def test_raw_counts_written_into_fbm_backing_files(tmp_path):

@@ -205,9 +205,10 @@ void trim_ctx(Ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   c->counts_key.clear();
+  c->geno_key.clear();
   c->owner_key.clear();
   c->h_owner.clear();
-  Ctx::Slot* dev[] = {&c->d_owner, &c->d_raw[0], &c->d_raw[1], &c->d_gat[0], &c->d_gat[1], &c->d_planes[0], &c->d_planes[1], &c->d_rows,
+  Ctx::Slot* dev[] = {&c->d_geno, &c->d_owner, &c->d_raw[0], &c->d_raw[1], &c->d_gat[0], &c->d_gat[1], &c->d_planes[0], &c->d_planes[1], &c->d_rows,
                       &c->d_cols, &c->d_counts, &c->d_out[0], &c->d_out[1], &c->d_out[2],
                       &c->d_out[3], &c->d_red};
   for (Ctx::Slot* s : dev) { if (s->p) cudaFree(s->p); s->p = nullptr; s->cap = 0; }
@@ -418,6 +419,19 @@ static int collect_accumulate(Ctx* ctx, tpg_stats* st, const Err& E) {
 // per-locus arrays of *scan are indexed by the job's locus position.
 // prod_mask_override != 0: compute these products instead of the ones job->stat needs (one pass
 // for several statistics: tpg_pairwise_many, the count-matrix cache).
+// Identity of a .bk for the on-device genotype cache (tpg_config.cache_genotypes): device, inode, size,
+// mtime and the matrix shape.  Empty = not cacheable.
+static std::string geno_cache_key(const tpg_job* job) {
+  if (!cfg().cache_genotypes || job->src_kind != TPG_SRC_FILE || !job->bk_path) return std::string();
+  struct stat sb;
+  if (stat(job->bk_path, &sb) != 0) return std::string();
+  char key[256];
+  snprintf(key, sizeof key, "%llu:%llu:%lld:%lld.%09ld|%lldx%lld", (unsigned long long)sb.st_dev,
+           (unsigned long long)sb.st_ino, (long long)sb.st_size, (long long)sb.st_mtim.tv_sec,
+           (long)sb.st_mtim.tv_nsec, (long long)job->nrow_total, (long long)job->ncol_total);
+  return std::string(key);
+}
+
 static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_stats* st,
                            const Err& E, bool defer = false, const ScanArgs* scan = nullptr,
                            int prod_mask_override = 0, const int32_t* group_sorted = nullptr, uint64_t group_sig = 0) {
@@ -436,17 +450,38 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   rc = open_source(job, &src, C.io_mode, E);
   if (rc) return rc;
 
-  const bool on_device = job->src_kind == TPG_SRC_DEVICE;
+  bool on_device = job->src_kind == TPG_SRC_DEVICE;
   const bool k_major = !scan && (job->flags & TPG_FLAG_PLANES_K_MAJOR) != 0;
   const bool no_overlap = (job->flags & TPG_FLAG_NO_OVERLAP) != 0;
   const int64_t nrow = job->nrow_total;
-  const bool rows_g = !pl.rows_contig;
+  bool rows_g = !pl.rows_contig;
 
   // Rows actually needed from each raw column: [rlo, rhi).  Staging copies only that span.
   int64_t rlo = pl.row0, rhi = pl.row0 + pl.n;
   if (rows_g) {
     rlo = nrow; rhi = 0;
     for (int32_t r : pl.rows0) { rlo = std::min<int64_t>(rlo, r); rhi = std::max<int64_t>(rhi, r + 1); }
+  }
+  // ---- on-device genotype cache (tpg_config.cache_genotypes).  A hit turns the job into a device-resident one
+  // whose source is the 2-bit packed image: every chunk is gathered from it (gather_pack_kernel, packed input;
+  // ind.row — or the identity — and ind.col are applied there) and decoded as any packed chunk.
+  const std::string geno_key = (scan || k_major || C.no_compact) ? std::string() : geno_cache_key(job);
+  const uint8_t* dev_base = src.base;   // device-resident source: bytes, extent, column stride
+  int64_t dev_bytes = int64_t(src.bytes), dev_stride = nrow;
+  bool from_cache = false;
+  if (!geno_key.empty() && ctx->geno_key == geno_key && ctx->d_geno.p && gather_pack_fits((rhi - (rlo & ~int64_t(3)) + 3) / 4)) {
+    from_cache = true;
+    on_device = true;
+    dev_base = static_cast<const uint8_t*>(ctx->d_geno.p);
+    dev_stride = ctx->geno_stride;
+    dev_bytes = dev_stride * job->ncol_total;
+    if (!rows_g) {                       // contiguous rows: the gather takes the identity index
+      pl.rows0.resize(size_t(pl.n));
+      for (int64_t i = 0; i < pl.n; ++i) pl.rows0[size_t(i)] = int32_t(pl.row0 + i);
+      rows_g = true;
+    }
+    rlo &= ~int64_t(3);                  // packed input: the staged span starts at a whole byte
+    st->n_geno_cached = 1;
   }
   int64_t span = on_device ? nrow : rhi - rlo;  // bytes per staged column
   // Gathered rows (ind.row in arbitrary order): the chunk is first compacted by gather_pack_kernel
@@ -481,12 +516,32 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   if (direct_only) { span = nrow; rlo = 0; }
   const int64_t g_span = rhi - rlo;            // rows a gather has to stage (relative row index 0 = raw row rlo)
   const bool gp_staged = gp_base && !on_device && !pack_ok && gather_pack_fits(g_span);  // raw chunks of a host source
-  const bool gp_dev = on_device && gp_raw_fits;
+  const bool gp_dev = on_device && (from_cache || gp_raw_fits);
   const bool gp_any = gp_dev || gp_staged || (rows_g && pack_ok);
   // device-resident gathered chunk whose span is too long for shared memory: compact through L2 instead
   const bool compact_gather = on_device && rows_g && !gp_dev && !scan && !C.no_compact;
   const int64_t pk_stride = pk2_stride(span);
   const int64_t g_stride = pk2_stride(pl.n);  // bytes per locus of a gathered (dense, packed) chunk
+  // A whole-file job (all rows, all loci, in order) whose chunks cross PCIe packed fills the cache as it goes: one
+  // device-to-device copy per chunk behind its H2D.  Only where HBM has room to spare (a quarter of what is free).
+  bool fill_cache = false;
+  if (!geno_key.empty() && !from_cache && pack_ok && !rows_g && rlo == 0 && span == nrow && pl.cols_contig && pl.col0 == 0 &&
+      pl.m_shard == job->ncol_total && !direct_ok && gather_pack_fits((nrow + 3) / 4)) {
+    const size_t need = size_t(pk_stride) * size_t(job->ncol_total) + 16;
+    bool room = ctx->d_geno.cap >= need;
+    if (!room) {
+      size_t free_b = 0, total_b = 0;
+      TPG_CUDA_OK(cudaMemGetInfo(&free_b, &total_b), E);
+      room = double(need) <= 0.25 * double(free_b + ctx->d_geno.cap);
+    }
+    if (room) {
+      ctx->geno_key.clear();             // being rewritten: not valid until this job has enqueued every chunk
+      rc = ensure_slot(&ctx->d_geno, need, false, "genotype cache", E);
+      if (rc) return rc;
+      ctx->geno_stride = pk_stride;
+      fill_cache = true;
+    }
+  }
 
   // ---- chunk size (loci per GPU chunk), decoupled from R's block.size
   int64_t lc = job->gpu_chunk_loci;
@@ -601,6 +656,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   // the step pays no cross-stream event hops
   cudaStream_t s_dec = (n_chunks == 1 && on_device) ? ctx->s_compute : ctx->s_decode;
   TPG_CUDA_OK(cudaStreamWaitEvent(s_dec, ev_start, 0), E);
+  if (from_cache && ctx->ev_geno) TPG_CUDA_OK(cudaStreamWaitEvent(s_dec, ctx->ev_geno, 0), E);
   std::vector<Ctx::ChunkEv>& tm = ctx->pend_ev;
   tm.assign(n_chunks, Ctx::ChunkEv{});
   int64_t macs = 0, max_chain = 0, n_wide = 0;
@@ -808,13 +864,14 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     bool gather_packed_in = false;
     int64_t gather_row_lo = 0;
     if (on_device) {
-      da.raw = src.base;
-      da.raw_bytes = int64_t(src.bytes);
-      da.raw_stride = nrow;
+      da.raw = dev_base;
+      da.raw_bytes = dev_bytes;
+      da.raw_stride = dev_stride;
       da.row0 = pl.row0;
       da.col_idx = pl.cols_contig ? nullptr : B.d_cols + k0;
       da.col0 = pl.col0 + k0;
       gather_now = gp_dev;
+      gather_packed_in = from_cache;
       gather_row_lo = rlo;
       TPG_CUDA_OK(cudaEventRecord(tm[c].c0, ctx->s_copy), E);
       TPG_CUDA_OK(cudaEventRecord(tm[c].c1, ctx->s_copy), E);
@@ -831,6 +888,10 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       TPG_CUDA_OK(cudaEventRecord(tm[c].c0, ctx->s_copy), E);
       TPG_CUDA_OK(cudaMemcpyAsync(B.d_raw[b], hp, size_t(h2d_bytes), cudaMemcpyHostToDevice, ctx->s_copy), E);
       TPG_CUDA_OK(cudaEventRecord(tm[c].c1, ctx->s_copy), E);
+      if (fill_cache && packed && col_stride == ctx->geno_stride)
+        TPG_CUDA_OK(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->d_geno.p) + k0 * col_stride, B.d_raw[b], size_t(h2d_bytes),
+                                    cudaMemcpyDeviceToDevice, ctx->s_copy), E);
+      else fill_cache = false;           // (never for a file source; a chunk that crossed raw would leave a hole)
       TPG_CUDA_OK(cudaEventRecord(ev_h2d_done[b], ctx->s_copy), E);
       if (!use_direct) TPG_CUDA_OK(cudaEventRecord(ev_pin_free[S.sb], ctx->s_copy), E);
       TPG_CUDA_OK(cudaStreamWaitEvent(s_dec, ev_h2d_done[b], 0), E);
@@ -939,6 +1000,11 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     TPG_CUDA_OK(cudaEventRecord(tm[c].g1, ctx->s_compute), E);
     TPG_CUDA_OK(cudaEventRecord(ev_gram_done[b], ctx->s_compute), E);
     if (no_overlap) TPG_CUDA_OK(cudaStreamSynchronize(ctx->s_compute), E);
+  }
+  if (fill_cache) {                      // every chunk is on its way: the image is valid once s_copy gets here
+    if (!ctx->ev_geno) TPG_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_geno, cudaEventDisableTiming), E);
+    TPG_CUDA_OK(cudaEventRecord(ctx->ev_geno, ctx->s_copy), E);
+    ctx->geno_key = geno_key;
   }
   drain.armed = false;
   ctx->pending = true;

@@ -65,6 +65,7 @@ void tpg_config_init(tpg_config* c) {
   c->scan_no_indiv = env_set("TPG_SCAN_NO_INDIV") ? 1 : 0;
   c->scan_table = env_int("TPG_SCAN_TABLE", 0);
   c->cache_counts = env_set("TPG_CACHE_COUNTS") ? 1 : 0;
+  c->cache_genotypes = env_set("TPG_CACHE_GENOTYPES") ? 1 : 0;
   c->device_chunk_loci = env_ll("TPG_DEVICE_CHUNK_LOCI", 0);
   c->host_chunk_mb = env_ll("TPG_HOST_CHUNK_MB", 0);
   c->link_gbps = env_f("TPG_LINK_GBPS", 0.0);

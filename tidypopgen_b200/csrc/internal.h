@@ -56,6 +56,12 @@ struct Ctx {
   // described by counts_key (file identity + indices); empty = nothing cached
   std::string counts_key;
   int64_t counts_key_n = 0;
+  // genotype cache (tpg_config.cache_genotypes): the whole .bk of geno_key (file identity), 2-bit packed,
+  // column k at k * geno_stride (pk2 layout of pack.cpp over all nrow_total rows); ev_geno = its last write
+  Slot d_geno;
+  std::string geno_key;
+  int64_t geno_stride = 0;
+  cudaEvent_t ev_geno = nullptr;
   std::vector<cudaEvent_t> ev_timing, ev_plain;
   // accumulate enqueued but not yet collected (tpg_pairwise defers the sync to the end of finish)
   struct ChunkEv { cudaEvent_t c0, c1, d0, d1, g0, g1; };
