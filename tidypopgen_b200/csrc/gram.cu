@@ -10,13 +10,19 @@
 //   DD = d d'   NN = NM NM'   HH = H1 H1'   (symmetric: upper-triangle tiles only)
 //   HN = H1 NM'                              (full)
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
-//   warp 0   TMA producer       (one lane)    global planes -> 4-stage smem ring
-//   warp 1   MMA issuer         (one lane)    4 x tcgen05.mma (M128 N256 K32) per stage
-//   warps 2-5 epilogue          TMEM -> registers -> red.global.add.s32 (coalesced, exact)
-// TMEM holds two 128x256 s32 accumulators, so the epilogue of one work item overlaps the
-// MMAs of the next.  A work item is (product, tile, k-block range); the host orders the
-// list so that CTAs running at the same time share operand panels in L2.
+// Five kernels share one skeleton — persistent CTAs, 192 threads, warp-specialised:
+//   warp 0   TMA producer       (one lane)    global planes -> shared-memory ring
+//   warp 1   MMA issuer         (one lane)    tcgen05.mma per stage, accumulators in TMEM
+//   warps 2-5 epilogue          TMEM -> registers -> the int32 count matrices (exact, order-independent adds)
+// and one host scheduler (launch_gram / launch_gram_mxf4: work lists ordered so that CTAs running at the same
+// time share operand panels in L2, cut into runs of equal-cost items):
+//   gram_i8_kernel          one CTA per SM, kind::i8 M128 x N256, red.global epilogue (round 1's first kernel; cross-check)
+//   gram_i8_pair_kernel     CTA pairs (cta_group::2), kind::i8 256 x 256 tiles, two accumulators ping-pong
+//   gram_i8_wide_kernel     CTA pairs, kind::i8 256 x 512 items (one A stage feeds two B stages)
+//   gram_mxf4_pair_kernel   CTA pairs, kind::mxf4 on 4-bit E2M1 planes, 256 x 240 tiles ping-pong (the default route)
+//   gram_mxf4_wide_kernel   CTA pairs, kind::mxf4 256 x 480 items (the default for large matrices)
+// The pair and wide kernels' epilogues stage 32 x 32 boxes in shared memory and add them with TMA reductions
+// (cp.reduce.async.bulk.tensor).  A work item is (product, tile, k-block range).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
