@@ -447,6 +447,10 @@ def run_b200(args, rank, world, local):
                            "(loci-sharded, int32 counts summed over NVLink by peer-reading add kernels, finished once)",
                    "stage_ms": {k: st[k] for k in ("ms_read", "ms_h2d", "ms_decode", "ms_gram", "ms_reduce", "ms_finish", "ms_d2h")},
                    "chunks": int(st["n_chunks"]), "packed_chunks": int(st["n_packed_chunks"]),
+                   "result_shells": int(st["n_result_shells"]),
+                   "result_shells_note": "tpg_config.result_shells (default): the matrix is computed and handed back in nested shells, "
+                                         "the D2H of one beside the products of the next; stage_ms.ms_d2h is then the host time of the "
+                                         "hand-back loops, most of it overlapped" if st["n_result_shells"] else None,
                    "host_threads": L.config()["host_threads"],
                    "sampled_pairs_exact": bool(ok_pairs), "matches_device_run": ok_fp, "bk_write_s": t_write}
             # disk -> HBM streaming, reported separately from the kernels (north_star): the same call on a COLD

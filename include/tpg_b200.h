@@ -145,6 +145,7 @@ typedef struct tpg_stats {
   int64_t n_cached_jobs;   /* 1 if the count matrices came from the context's cache       */
   double ms_reduce;        /* multi-GPU: summing the count matrices over NVLink            */
   int64_t n_geno_cached;   /* 1 if the genotypes came from the on-device 2-bit cache (tpg_config.cache_genotypes) */
+  int64_t n_result_shells; /* shells the result came home in (tpg_config.result_shells), 0 = one piece            */
   int64_t n_wide_launches; /* Gram launches that ran a wide-tile kernel (256 x 480 4-bit / 256 x 512 int8, *
                             * TMA-reduction epilogue) rather than a ping-pong pair kernel                */
 } tpg_stats;
@@ -228,6 +229,10 @@ typedef struct tpg_config {
                                * loci) leaves its 2-bit packed image in HBM (nrow x ncol / 4 bytes); later jobs on  *
                                * that file (same size, mtime) — any ind.row / ind.col, any statistic — gather from *
                                * it on the device: no disk read, no host packing, no PCIe (tpg_stats.n_geno_cached) */
+  int32_t result_shells;      /* TPG_RESULT_SHELLS: whole-file jobs with >= ~27,000 individuals compute and hand back  *
+                               * the result in nested shells (top-left square first, then L-shaped rims), so the D2H *
+                               * of one shell overlaps the products of the next: 0 = auto (6, 4 or 3 shells), 1 = off, *
+                               * 2..8 = that many shells                                                            */
   int64_t device_chunk_loci;  /* TPG_DEVICE_CHUNK_LOCI: loci per chunk of a device-resident source, 0 = 2^20 */
   int64_t host_chunk_mb;      /* TPG_HOST_CHUNK_MB: raw MB per chunk of a host / file source, 0 = 48 */
   double link_gbps;           /* TPG_LINK_GBPS: PCIe model of the hybrid schedule, 0 = 45 */

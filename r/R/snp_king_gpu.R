@@ -16,7 +16,7 @@ tpg_gpu_devices <- function() {
 tpg_gpu_config <- function() {
   fields <- c("gram_route", "gram_ctas", "gram_ksplit", "gram_max_kblocks", "gram_clusters",
               "gram_no_trim", "gram_wide", "gram_l2_rows", "gram_l2_cols", "gram_order", "pack_mode", "pk2_i8", "no_compact", "gather_smem_kb", "gather_layout", "io_mode", "no_thp", "decode_k4_v1",
-              "host_threads", "scan_loci_per_cta", "scan_no_indiv", "scan_table", "cache_counts", "cache_genotypes",
+              "host_threads", "scan_loci_per_cta", "scan_no_indiv", "scan_table", "cache_counts", "cache_genotypes", "result_shells",
               "device_chunk_loci", "host_chunk_mb", "link_gbps", "hybrid_factor")
   opts <- lapply(stats::setNames(fields, fields), function(f) getOption(paste0("tidypopgen.gpu.", f)))
   gpu_set_config(opts[!vapply(opts, is.null, logical(1))])

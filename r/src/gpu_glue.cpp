@@ -75,7 +75,7 @@ void gpu_set_config(List opts) {
   TPG_OPT_I(gram_route) TPG_OPT_I(gram_ctas) TPG_OPT_I(gram_ksplit) TPG_OPT_I(gram_max_kblocks)
   TPG_OPT_I(gram_clusters) TPG_OPT_I(gram_no_trim) TPG_OPT_I(gram_wide) TPG_OPT_I(gram_l2_rows) TPG_OPT_I(gram_l2_cols) TPG_OPT_I(gram_order) TPG_OPT_I(pack_mode) TPG_OPT_I(pk2_i8) TPG_OPT_I(no_compact) TPG_OPT_I(gather_smem_kb) TPG_OPT_I(gather_layout)
   TPG_OPT_I(io_mode) TPG_OPT_I(no_thp) TPG_OPT_I(decode_k4_v1) TPG_OPT_I(host_threads)
-  TPG_OPT_I(scan_loci_per_cta) TPG_OPT_I(scan_no_indiv) TPG_OPT_I(scan_table) TPG_OPT_I(cache_counts) TPG_OPT_I(cache_genotypes)
+  TPG_OPT_I(scan_loci_per_cta) TPG_OPT_I(scan_no_indiv) TPG_OPT_I(scan_table) TPG_OPT_I(cache_counts) TPG_OPT_I(cache_genotypes) TPG_OPT_I(result_shells)
   TPG_OPT_D(link_gbps) TPG_OPT_D(hybrid_factor)
   if (opts.containsElementNamed("device_chunk_loci")) c.device_chunk_loci = static_cast<int64_t>(as<double>(opts["device_chunk_loci"]));
   if (opts.containsElementNamed("host_chunk_mb")) c.host_chunk_mb = static_cast<int64_t>(as<double>(opts["host_chunk_mb"]));

@@ -164,6 +164,46 @@ def test_genotype_cache_serves_other_subsets_and_statistics(n, m, tpg_cfg, tmp_p
     assert tpg.snp.last_stats["n_geno_cached"] == 1 and same(k3, k2)
 
 
+def test_result_shells_equal_the_one_piece_path(tpg_cfg, tmp_path):
+    """tpg_config.result_shells: a whole-file job with >= 27,136 individuals computes and hands back its matrix in
+    nested shells (products of shell k+1 beside the D2H of shell k, shells 1.. from the packed image shell 0's
+    streaming pass left in HBM).  Every statistic equals the one-piece path bit for bit — all outputs, every shell
+    count — and the oracle on individuals sampled from every shell."""
+    n, m = 27_136 + 77, 2_000
+    rng = np.random.default_rng(77)
+    raw = np.zeros(n * m, np.uint8)
+    L.lib().tpg_synth_fill_host(raw.ctypes.data, n, m, 0, 977, 0.03, 0)
+    X = tpg.FBMCode256.from_bytes(raw, n, m, backingfile=tmp_path / "shells.bk")
+    tpg_cfg(result_shells=1)
+    king1, K1, N1 = tpg.snp_king_counts(X)
+    assert tpg.snp.last_stats["n_result_shells"] == 0
+    for shells in (0, 3):
+        tpg_cfg(result_shells=shells)
+        king, K, N = tpg.snp_king_counts(X, gpu_chunk_loci=512)
+        st = dict(tpg.snp.last_stats)
+        assert st["n_result_shells"] == (shells or 4) and st["n_chunks"] >= 4 + (shells or 4) - 1, st   # (8 regions: auto = 4)
+        assert same(king, king1) and np.array_equal(K, K1) and np.array_equal(N, N1), shells
+        del king, K, N
+    pick_rows = np.sort(rng.choice(n, 240, replace=False)).astype(np.int32) + 1     # spans every shell
+    ref = O.snp_king(raw, n, m, pick_rows)
+    ix = np.ix_(pick_rows - 1, pick_rows - 1)
+    assert same(king1[ix], ref["king"]) and np.array_equal(K1[ix], ref["K"]) and np.array_equal(N1[ix], ref["N_Aa_i"])
+    del king1, K1, N1
+    tpg_cfg(result_shells=1)
+    a1 = tpg.snp_allele_sharing(X, block_size=333)
+    r1 = tpg.snp_ibs(X, type="raw_counts")
+    i1, v1 = r1["ibs"][:].copy(), r1["valid_n"][:].copy()
+    tpg_cfg(result_shells=0)
+    a = tpg.snp_allele_sharing(X, block_size=333)                                 # pad quirk constant in every shell
+    assert tpg.snp.last_stats["n_result_shells"] == 4 and same(a, a1)
+    del a, a1
+    r = tpg.snp_ibs(X, type="raw_counts")                                          # two file-backed outputs
+    assert tpg.snp.last_stats["n_result_shells"] == 4
+    assert np.array_equal(r["ibs"][:], i1) and np.array_equal(r["valid_n"][:], v1)
+    g = tpg.snp_ibs(X, pick_rows)                                                  # a subset job: the one-piece path
+    assert tpg.snp.last_stats["n_result_shells"] == 0 and same(g, O.snp_ibs(raw, n, m, pick_rows)["out"])
+
+
 # ------------------------------------------------------------------ file-backed results (raw_counts)
 
 def test_raw_counts_written_into_fbm_backing_files(tmp_path):

@@ -84,6 +84,7 @@ class Stats(C.Structure):
         ("n_cached_jobs", C.c_int64),
         ("ms_reduce", C.c_double),
         ("n_geno_cached", C.c_int64),
+        ("n_result_shells", C.c_int64),
         ("n_wide_launches", C.c_int64),
     ]
 
@@ -133,6 +134,7 @@ class Config(C.Structure):
         ("scan_table", C.c_int32),
         ("cache_counts", C.c_int32),
         ("cache_genotypes", C.c_int32),
+        ("result_shells", C.c_int32),
         ("device_chunk_loci", C.c_int64),
         ("host_chunk_mb", C.c_int64),
         ("link_gbps", C.c_double),

@@ -176,15 +176,42 @@ void build_owner_table(int64_t nblocks, int world, std::vector<uint8_t>* out) {
   }
 }
 
+// Result shells (pairwise_shells): the regions are cut into `shells` nested groups — the first one a top-left square
+// holding `first_frac` of the area, the others L-shaped rims of equal area — and a block belongs to the shell of
+// max(region of its row, region of its column).  Same table layout as build_owner_table.
+static void build_shell_table(int64_t nblocks, int shells, double first_frac, std::vector<uint8_t>* out, std::vector<int64_t>* bounds) {
+  out->clear();
+  bounds->clear();
+  const int64_t r = 15, nr = (nblocks + r - 1) / r;
+  if (shells < 2 || shells > nr) return;
+  bounds->push_back(0);
+  const double a0 = first_frac * double(nr) * double(nr);
+  for (int k = 1; k < shells; ++k) {
+    const double area = a0 + (double(nr) * double(nr) - a0) * double(k - 1) / double(shells - 1);
+    int64_t b = int64_t(std::llround(std::sqrt(area)));
+    b = std::max<int64_t>(bounds->back() + 1, std::min<int64_t>(b, nr - (shells - k)));
+    bounds->push_back(b);
+  }
+  bounds->push_back(nr);
+  out->assign(size_t(nr * (nr + 1) / 2), 0);
+  for (int64_t ri = 0; ri < nr; ++ri)
+    for (int64_t rj = ri; rj < nr; ++rj) {
+      int k = 0;
+      while (rj >= (*bounds)[size_t(k) + 1]) ++k;
+      (*out)[size_t(ri * nr - ri * (ri - 1) / 2 + (rj - ri))] = uint8_t(k);
+    }
+}
+
 int owner_table(Ctx* ctx, int64_t n_pad, int world, const uint8_t** host, const uint8_t** dev, const Err& E) {
   *host = nullptr;
   *dev = nullptr;
   if (world <= 1) return TPG_OK;
   const int64_t nblocks = n_pad / 256;
   char key[64];
-  snprintf(key, sizeof key, "%lld/%d", (long long)nblocks, world);
+  snprintf(key, sizeof key, "%s%lld/%d", ctx->owner_shells > 0 ? "shells:" : "", (long long)nblocks, world);
   if (ctx->owner_key != key) {
-    build_owner_table(nblocks, world, &ctx->h_owner);
+    if (ctx->owner_shells > 0) build_shell_table(nblocks, world, 0.45, &ctx->h_owner, &ctx->shell_bounds);
+    else build_owner_table(nblocks, world, &ctx->h_owner);
     if (!ctx->h_owner.empty()) {
       int rc = ensure_slot(&ctx->d_owner, ctx->h_owner.size(), false, "owner table", E);
       if (rc) return rc;
@@ -206,6 +233,7 @@ void trim_ctx(Ctx* c) {
   cudaDeviceSynchronize();
   c->counts_key.clear();
   c->geno_key.clear();
+  c->planes_key.clear();
   c->owner_key.clear();
   c->h_owner.clear();
   Ctx::Slot* dev[] = {&c->d_geno, &c->d_owner, &c->d_raw[0], &c->d_raw[1], &c->d_gat[0], &c->d_gat[1], &c->d_planes[0], &c->d_planes[1], &c->d_rows,
@@ -419,10 +447,13 @@ static int collect_accumulate(Ctx* ctx, tpg_stats* st, const Err& E) {
 // per-locus arrays of *scan are indexed by the job's locus position.
 // prod_mask_override != 0: compute these products instead of the ones job->stat needs (one pass
 // for several statistics: tpg_pairwise_many, the count-matrix cache).
+constexpr uint64_t kFnvSeed = 1469598103934665603ull;
+static uint64_t fnv1a(const void* p, size_t bytes, uint64_t h);
+
 // Identity of a .bk for the on-device genotype cache (tpg_config.cache_genotypes): device, inode, size,
 // mtime and the matrix shape.  Empty = not cacheable.
-static std::string geno_cache_key(const tpg_job* job) {
-  if (!cfg().cache_genotypes || job->src_kind != TPG_SRC_FILE || !job->bk_path) return std::string();
+static std::string geno_cache_key(const tpg_job* job, bool force = false) {
+  if ((!cfg().cache_genotypes && !force) || job->src_kind != TPG_SRC_FILE || !job->bk_path) return std::string();
   struct stat sb;
   if (stat(job->bk_path, &sb) != 0) return std::string();
   char key[256];
@@ -434,7 +465,8 @@ static std::string geno_cache_key(const tpg_job* job) {
 
 static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_stats* st,
                            const Err& E, bool defer = false, const ScanArgs* scan = nullptr,
-                           int prod_mask_override = 0, const int32_t* group_sorted = nullptr, uint64_t group_sig = 0) {
+                           int prod_mask_override = 0, const int32_t* group_sorted = nullptr, uint64_t group_sig = 0,
+                           bool force_geno = false) {
   const double t_begin = now_ms();
   const tpg_config C = cfg();
   Plan pl;
@@ -465,7 +497,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   // ---- on-device genotype cache (tpg_config.cache_genotypes).  A hit turns the job into a device-resident one
   // whose source is the 2-bit packed image: every chunk is gathered from it (gather_pack_kernel, packed input;
   // ind.row — or the identity — and ind.col are applied there) and decoded as any packed chunk.
-  const std::string geno_key = (scan || k_major || C.no_compact) ? std::string() : geno_cache_key(job);
+  const std::string geno_key = (scan || k_major || C.no_compact) ? std::string() : geno_cache_key(job, force_geno);
   const uint8_t* dev_base = src.base;   // device-resident source: bytes, extent, column stride
   int64_t dev_bytes = int64_t(src.bytes), dev_stride = nrow;
   bool from_cache = false;
@@ -532,7 +564,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     if (!room) {
       size_t free_b = 0, total_b = 0;
       TPG_CUDA_OK(cudaMemGetInfo(&free_b, &total_b), E);
-      room = double(need) <= 0.25 * double(free_b + ctx->d_geno.cap);
+      room = double(need) <= (force_geno ? 0.9 : 0.25) * double(free_b + ctx->d_geno.cap);
     }
     if (room) {
       ctx->geno_key.clear();             // being rewritten: not valid until this job has enqueued every chunk
@@ -595,11 +627,24 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
   }
   const int64_t n_chunks = (pl.m_shard + lc - 1) / lc;
   const int64_t plane_stride = pl.n_pad * lc;
+  // One chunk out of the packed image: its planes stay valid in d_planes[0] until another job decodes there
+  // (result shells run the same rows and loci K - 1 times).
+  std::string planes_key;
+  if (from_cache && n_chunks == 1 && !scan) {
+    char pk[160];
+    snprintf(pk, sizeof pk, "|n%lld|m%lld|r%016llx|c%016llx|p%d|q%d|lc%lld", (long long)pl.n, (long long)pl.m_shard,
+             (unsigned long long)fnv1a(pl.rows0.data(), sizeof(int32_t) * pl.rows0.size(), kFnvSeed),
+             (unsigned long long)(pl.cols_contig ? uint64_t(pl.col0) : fnv1a(pl.cols0.data(), sizeof(int32_t) * pl.cols0.size(), kFnvSeed)),
+             pl.nplanes, int(q4_ok && !C.pk2_i8), (long long)lc);
+    planes_key = geno_key + pk;
+  }
+  const bool reuse_planes = !planes_key.empty() && ctx->planes_key == planes_key && ctx->d_planes[0].p;
+  if (!scan && !reuse_planes) ctx->planes_key.clear();
 
   struct { uint8_t* d_raw[2]; uint8_t* d_gat[2]; int8_t* d_planes[2]; uint8_t* h_pin[2]; int32_t* d_rows; int32_t* d_cols;
            Ctx* c; cudaEvent_t ev(bool t) { return pooled_event(c, t); } } B{};
   B.c = ctx;
-  ctx->ev_timing_used = ctx->ev_plain_used = 0;
+  if (!ctx->keep_events) ctx->ev_timing_used = ctx->ev_plain_used = 0;
   const int64_t stage_per_locus = pack_ok ? pk_stride : span;  // pinned staging bytes per locus
   for (int b = 0; b < 2 && b < n_chunks; ++b) {
     if (!scan) {
@@ -927,7 +972,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     // planes[b] (and the gathered copy b) were last read by the gram / decode of chunk c-2
     if (c >= 2) TPG_CUDA_OK(cudaStreamWaitEvent(s_dec, ev_gram_done[b], 0), E);
     TPG_CUDA_OK(cudaEventRecord(tm[c].d0, s_dec), E);
-    if (gather_now) {
+    if (gather_now && !reuse_planes) {
       // gathered rows: stage the row span in shared memory, gather there, write the dense chunk 2-bit
       // packed (decode.cu, "row gather through shared memory"); ind.col of a device source is applied too
       rc = launch_gather_pack(ctx, da, gather_packed_in, gather_row_lo, g_span, B.d_gat[b], g_stride, s_dec, E);
@@ -940,6 +985,8 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       da.row0 = 0;
       da.col_idx = nullptr;
       da.col0 = 0;
+    } else if (gather_now) {
+      da.packed = true;                   // planes reused: the same plane form as the gathered chunk got
     }
     // (2-bit packed chunks decode to 4-bit planes too; pk2_i8 keeps them on the int8 kernels)
     const bool use_q4 = q4_ok && !(da.packed && C.pk2_i8);
@@ -966,8 +1013,10 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
       da.col_idx = nullptr;
       da.col0 = 0;
     }
-    rc = launch_decode(ctx, da, s_dec, E);
-    if (rc) return rc;
+    if (!reuse_planes) {
+      rc = launch_decode(ctx, da, s_dec, E);
+      if (rc) return rc;
+    }
     TPG_CUDA_OK(cudaEventRecord(tm[c].d1, s_dec), E);
     TPG_CUDA_OK(cudaEventRecord(ev_dec_done[b], s_dec), E);
     TPG_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ev_dec_done[b], 0), E);
@@ -1001,6 +1050,7 @@ static int accumulate_impl(Ctx* ctx, const tpg_job* job, int32_t* d_counts, tpg_
     TPG_CUDA_OK(cudaEventRecord(ev_gram_done[b], ctx->s_compute), E);
     if (no_overlap) TPG_CUDA_OK(cudaStreamSynchronize(ctx->s_compute), E);
   }
+  if (!planes_key.empty()) ctx->planes_key = planes_key;
   if (fill_cache) {                      // every chunk is on its way: the image is valid once s_copy gets here
     if (!ctx->ev_geno) TPG_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_geno, cudaEventDisableTiming), E);
     TPG_CUDA_OK(cudaEventRecord(ctx->ev_geno, ctx->s_copy), E);
@@ -1199,7 +1249,7 @@ static int union_mask(const int32_t* stats, int nstats) {
 }
 static const int kAllProducts = (1 << TPG_MAT_DD) | (1 << TPG_MAT_NN) | (1 << TPG_MAT_HH) | (1 << TPG_MAT_HN);
 
-static uint64_t fnv1a(const void* p, size_t bytes, uint64_t h = 1469598103934665603ull) {
+static uint64_t fnv1a(const void* p, size_t bytes, uint64_t h) {
   const uint8_t* b = static_cast<const uint8_t*>(p);
   for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
   return h;
@@ -1214,8 +1264,8 @@ static std::string counts_cache_key(const tpg_job* job) {
   struct stat sb;
   if (stat(job->bk_path, &sb) != 0) return std::string();
   const int64_t n = job->ind_row ? job->n : job->nrow_total, m = job->ind_col ? job->m : job->ncol_total;
-  const uint64_t hr = job->ind_row ? fnv1a(job->ind_row, sizeof(int32_t) * size_t(n)) : 0;
-  const uint64_t hc = job->ind_col ? fnv1a(job->ind_col, sizeof(int32_t) * size_t(m)) : 0;
+  const uint64_t hr = job->ind_row ? fnv1a(job->ind_row, sizeof(int32_t) * size_t(n), kFnvSeed) : 0;
+  const uint64_t hc = job->ind_col ? fnv1a(job->ind_col, sizeof(int32_t) * size_t(m), kFnvSeed) : 0;
   char key[512];
   snprintf(key, sizeof key, "%llu:%llu:%lld:%lld.%09ld|%lldx%lld|r%lld:%016llx|c%lld:%016llx",
            (unsigned long long)sb.st_dev, (unsigned long long)sb.st_ino, (long long)sb.st_size,
@@ -1522,6 +1572,251 @@ struct ResultMaps {
   }
 };
 
+// ------------------------------------------------------------------ result shells
+// A large result takes as long to come home as a third of the products take (n = 50,000: 20 GB, 0.4 s over one PCIe
+// link against 0.75 s of Gram kernels), and a chunk-streamed job can finish nothing before its last chunk.  For a
+// whole-file job the matrix is therefore produced in nested shells — a top-left square, then L-shaped rims
+// (build_shell_table; tile sharding's machinery with the shells as "ranks" of one GPU):
+//   phase A   the file is streamed ONCE: every chunk adds the products of shell 0 and leaves its 2-bit packed image
+//             in HBM (the genotype cache's fill path) — as much Gram work as the host needs to read and pack the file;
+//   phase B   shells 1 .. K-1 run from the resident image (gather + decode + one Gram launch over all loci each);
+//   each shell is finished as soon as its products are done, and its D2H runs on the copy stream while the next
+//   shell's kernels run.
+// Exposed at the end: the last shell's hand-back only.
+
+// D2H of a rectangle [r0, r1) x [c0, c1) of column-major n x n double matrices (device `dev`, host `host`) on
+// `stream`: through the two pinned bounce buffers, columns copied into the caller's pageable matrix by the pool.
+static int rect_to_host(Ctx* ctx, cudaStream_t stream, const double* const* dev, double* const* host, int count, int64_t n,
+                        int64_t r0, int64_t r1, int64_t c0, int64_t c1, int64_t* bytes_d2h, const Err& E) {
+  if (r1 <= r0 || c1 <= c0) return TPG_OK;
+  const size_t kPiece = size_t(128) << 20;
+  const size_t w = size_t(r1 - r0) * sizeof(double);            // bytes per column of the rectangle
+  const int64_t cols_per_piece = std::max<int64_t>(1, int64_t(kPiece / w));
+  int rc = TPG_OK;
+  for (int b = 0; b < 2 && rc == TPG_OK; ++b)
+    rc = ensure_slot(&ctx->h_out[b], std::max(kPiece, w), true, "pinned result staging", E);
+  if (rc) return rc;
+  struct Piece { double* dst; const uint8_t* from; int64_t ncols; cudaEvent_t ev; };
+  Piece prev{nullptr, nullptr, 0, nullptr};
+  auto drain = [&](const Piece& q) {
+    if (!q.dst) return cudaSuccess;
+    cudaError_t e = cudaEventSynchronize(q.ev);
+    if (e != cudaSuccess) return e;
+    double* dst = q.dst;
+    const uint8_t* from = q.from;
+    const int64_t grain = std::max<int64_t>(1, int64_t((size_t(256) << 10) / w));
+    parallel_for(q.ncols, grain, [=](int64_t a, int64_t z) {
+      for (int64_t j = a; j < z; ++j) copy_streaming(dst + j * n, from + size_t(j) * w, w);
+    });
+    return cudaSuccess;
+  };
+  cudaEvent_t evp[2];
+  for (int b = 0; b < 2; ++b) TPG_CUDA_OK(cudaEventCreateWithFlags(&evp[b], cudaEventDisableTiming), E);
+  int64_t idx = 0;
+  cudaError_t e = cudaSuccess;
+  for (int o = 0; o < count && e == cudaSuccess; ++o) {
+    if (!host[o]) continue;
+    for (int64_t c = c0; c < c1 && e == cudaSuccess; c += cols_per_piece, ++idx) {
+      const int64_t nc = std::min(cols_per_piece, c1 - c);
+      const int b = int(idx & 1);
+      // bounce buffer b was last used two pieces ago: that piece has been drained (it was `prev` one step back)
+      e = cudaMemcpy2DAsync(ctx->h_out[b].p, w, dev[o] + c * n + r0, size_t(n) * sizeof(double), w, size_t(nc),
+                            cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess) e = cudaEventRecord(evp[b], stream);
+      if (e == cudaSuccess) e = drain(prev);
+      prev = Piece{host[o] + c * n + r0, static_cast<const uint8_t*>(ctx->h_out[b].p), nc, evp[b]};
+      *bytes_d2h += int64_t(w) * nc;
+    }
+  }
+  if (e == cudaSuccess) e = drain(prev);
+  for (int b = 0; b < 2; ++b) cudaEventDestroy(evp[b]);
+  if (e != cudaSuccess) return E.fail(TPG_ERR_CUDA, "result D2H failed: %s", cudaGetErrorString(e));
+  return TPG_OK;
+}
+
+// How many shells this job's result comes home in (0 = the ordinary path).
+static int shells_for(Ctx* c, const tpg_job* job, int stat, const tpg_result* res) {
+  const tpg_config C = cfg();
+  if (C.result_shells == 1) return 0;
+  if (job->src_kind != TPG_SRC_FILE || !job->bk_path || job->ind_row || job->ind_col) return 0;
+  if (job->shard_mode != TPG_SHARD_NONE && job->shard_world > 1) return 0;
+  if (stat == TPG_STAT_GRM || res->out_on_device) return 0;               // GRM's mean needs the whole matrix
+  if (job->flags & (TPG_FLAG_PLANES_K_MAJOR | TPG_FLAG_NO_PACK | TPG_FLAG_GRAM_1CTA | TPG_FLAG_NO_OVERLAP)) return 0;
+  if (C.pack_mode == 1 || C.no_compact || C.cache_counts || C.gram_ctas == 1) return 0;
+  const int64_t n = job->nrow_total, nblocks = round_up(n, kRowPad) / 256;
+  int K = 0;                                 // needs the 3840-wide ownership regions: as many shells as they allow
+  for (int cand : {6, 4, 3}) {
+    if (C.result_shells >= 2) cand = C.result_shells;
+    if (shard_region_blocks(nblocks, cand) == 15 && (nblocks + 14) / 15 >= cand) { K = cand; break; }
+    if (C.result_shells >= 2) break;
+  }
+  if (!K) return 0;
+  if (!gather_pack_fits((n + 3) / 4)) return 0;
+  // room for the packed image beside everything a phase-B shell holds at once
+  size_t free_b = 0, total_b = 0;
+  if (cudaSetDevice(c->device) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
+  const size_t held = c->d_geno.cap + c->d_counts.cap + c->d_out[0].cap + c->d_out[1].cap + c->d_out[2].cap + c->d_out[3].cap +
+                      c->d_planes[0].cap + c->d_planes[1].cap + c->d_gat[0].cap + c->d_gat[1].cap + c->d_raw[0].cap + c->d_raw[1].cap;
+  const int nout = 1 + (res->out1 ? 1 : 0) + (res->aux0 ? 1 : 0) + (res->aux1 ? 1 : 0);
+  const double n_pad = double(round_up(n, kRowPad)), m = double(job->ncol_total);
+  const double need = 16.0 * n_pad * n_pad + 8.0 * double(n) * double(n) * nout + double(pk2_stride(n)) * m * 2.0 +
+                      1.5 * n_pad * m + 2e9;   // counts, results, image + one gathered copy, 4-bit planes, staging
+  if (need > 0.92 * double(free_b + held)) return 0;
+  return K;
+}
+
+static int pairwise_shells(Ctx* c, const tpg_job* job, int stat, tpg_result* res, int K, const Err& E) {
+  const double t_begin = now_ms();
+  const int64_t l0 = c->launches;
+  const int64_t n = job->nrow_total, n_pad = round_up(n, kRowPad);
+  tpg_stats& st = res->stats;
+  int rc = ensure_slot(&c->d_counts, sizeof(int32_t) * size_t(tpg_counts_elems(n)), false, "count matrices", E);
+  if (rc) return rc;
+  int32_t* d_counts = static_cast<int32_t*>(c->d_counts.p);
+  double* host[4] = {res->out0, res->out1, res->aux0, res->aux1};
+  const double* dev[4] = {nullptr, nullptr, nullptr, nullptr};
+  const size_t bytes = sizeof(double) * size_t(n) * size_t(n);
+  for (int o = 0; o < 4; ++o) {
+    if (!host[o]) continue;
+    rc = ensure_slot(&c->d_out[o], bytes, false, "result matrix", E);
+    if (rc) return rc;
+    dev[o] = static_cast<const double*>(c->d_out[o].p);
+    if (bytes >= (size_t(8) << 20) && !cfg().no_thp) {   // a fresh result matrix: ask for huge pages (results_to_host)
+      const uintptr_t lo = (reinterpret_cast<uintptr_t>(host[o]) + (size_t(2) << 20) - 1) & ~((uintptr_t(2) << 20) - 1);
+      const uintptr_t hi = (reinterpret_cast<uintptr_t>(host[o]) + bytes) & ~((uintptr_t(2) << 20) - 1);
+      if (hi > lo) madvise(reinterpret_cast<void*>(lo), size_t(hi - lo), MADV_HUGEPAGE);
+    }
+  }
+  struct Mode {   // the shell table replaces the weighted owner table while this job runs
+    Ctx* c;
+    ~Mode() {
+      cudaStreamSynchronize(c->s_compute); cudaStreamSynchronize(c->s_decode); cudaStreamSynchronize(c->s_copy);
+      c->owner_shells = 0; c->keep_events = false; c->owner_key.clear(); c->pending = false;
+      if (!cfg().cache_genotypes) c->geno_key.clear();
+    }
+  } mode{c};
+  c->owner_shells = K;
+  c->keep_events = true;
+  c->counts_key.clear();
+  c->ev_timing_used = c->ev_plain_used = 0;
+  const uint8_t *owner_h = nullptr, *owner_d = nullptr;
+  rc = owner_table(c, n_pad, K, &owner_h, &owner_d, E);
+  if (rc) return rc;
+  if (!owner_d || int(c->shell_bounds.size()) != K + 1) return E.fail(TPG_ERR_ARG, "result shells: no shell table for this shape");
+  const int mask = prod_mask_for(stat);
+  rc = launch_zero_counts(c, d_counts, n, mask, 0, 1, nullptr, c->s_compute, E);   // every shell's blocks, once
+  if (rc) return rc;
+  tpg_job jk = *job;
+  jk.stat = stat;
+  jk.shard_mode = TPG_SHARD_TILES;
+  jk.shard_world = K;
+  FinishArgs fa;
+  fa.stat = stat;
+  fa.counts = d_counts;
+  fa.ld = n_pad;
+  fa.n = n;
+  fa.m = job->ncol_total;
+  fa.n_short = 0;
+  if (stat == TPG_STAT_AS && job->pad_quirk)
+    fa.n_short = as_pad_count(job->ncol_total, job->block_size > 0 ? job->block_size : block_size_default(job->nrow_total));
+  st.n_short = fa.n_short;
+  fa.shard_world = K;
+  fa.owner = owner_d;
+  fa.out0 = const_cast<double*>(dev[0]); fa.out1 = const_cast<double*>(dev[1]);
+  fa.aux0 = const_cast<double*>(dev[2]); fa.aux1 = const_cast<double*>(dev[3]);
+  std::vector<std::vector<Ctx::ChunkEv>> evs(static_cast<size_t>(K));
+  std::vector<cudaEvent_t> ev_fin(static_cast<size_t>(K)), ev_f0(static_cast<size_t>(K));
+  const std::string gkey = geno_cache_key(job, true);
+  for (int b = 0; b < 2; ++b) {           // the bounce buffers, before the hand-back thread needs them
+    rc = ensure_slot(&c->h_out[b], size_t(128) << 20, true, "pinned result staging", E);
+    if (rc) return rc;
+  }
+  // Hand-back of one shell at a time on a helper thread (DMA on the copy stream, the pool's copies into the caller's
+  // matrix), so that this thread can enqueue the next shells meanwhile; phase B stages nothing, the pool is free.
+  struct HandBack {
+    std::thread th;
+    int rc = TPG_OK;
+    char err[512] = {0};
+    int64_t bytes = 0;
+    double ms = 0;
+  } hb;
+  auto join_hand_back = [&]() -> int {
+    if (hb.th.joinable()) hb.th.join();
+    if (hb.rc != TPG_OK) { const int r = E.fail(hb.rc, "%s", hb.err); hb.rc = TPG_OK; return r; }
+    return TPG_OK;
+  };
+  struct Joiner { HandBack* h; ~Joiner() { if (h->th.joinable()) h->th.join(); } } joiner{&hb};
+  auto start_hand_back = [&](int k) -> int {   // shell k: columns [ca, cb) down to row cb, and rows [ca, cb) of the columns before
+    int r = join_hand_back();
+    if (r) return r;
+    const int64_t ca = std::min(n, c->shell_bounds[size_t(k)] * 15 * 256), cb = std::min(n, c->shell_bounds[size_t(k) + 1] * 15 * 256);
+    const cudaEvent_t ready = ev_fin[size_t(k)];
+    hb.th = std::thread([c, &hb, dev, host, n, ca, cb, ready]() {
+      Err Et{hb.err, sizeof hb.err};
+      const double t0 = now_ms();
+      if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamWaitEvent(c->s_copy, ready, 0) != cudaSuccess) {
+        hb.rc = Et.fail(TPG_ERR_CUDA, "result shells: the copy stream could not wait for the shell");
+        return;
+      }
+      int r2 = rect_to_host(c, c->s_copy, dev, host, 4, n, 0, cb, ca, cb, &hb.bytes, Et);
+      if (r2 == TPG_OK) r2 = rect_to_host(c, c->s_copy, dev, host, 4, n, ca, cb, 0, ca, &hb.bytes, Et);
+      hb.rc = r2;
+      hb.ms += now_ms() - t0;
+    });
+    return TPG_OK;
+  };
+  for (int k = 0; k < K && rc == TPG_OK; ++k) {
+    jk.shard_rank = k;
+    tpg_stats sk;
+    memset(&sk, 0, sizeof sk);
+    // shell 0 streams the file and must leave the packed image behind; the others read it (and, from the second
+    // one on, the planes the first of them decoded)
+    rc = accumulate_impl(c, &jk, d_counts, &sk, E, /*defer=*/true, nullptr, 0, nullptr, 0, /*force_geno=*/true);
+    if (rc) break;
+    if (k == 0 && c->geno_key != gkey) { rc = E.fail(TPG_ERR_NOMEM, "result shells: the packed genotype image did not fit"); break; }
+    if (k > 0 && !sk.n_geno_cached) { rc = E.fail(TPG_ERR_CUDA, "result shells: shell %d did not run from the packed image", k); break; }
+    evs[size_t(k)] = c->pend_ev;
+    c->pending = false;                   // collected below, after the last shell
+    st.ms_read += sk.ms_read; st.n_chunks += sk.n_chunks; st.n_packed_chunks += sk.n_packed_chunks; st.bytes_h2d += sk.bytes_h2d;
+    st.n_mxf4_chunks += sk.n_mxf4_chunks; st.n_i8_chunks += sk.n_i8_chunks; st.n_wide_launches += sk.n_wide_launches;
+    st.max_chain_loci = std::max(st.max_chain_loci, sk.max_chain_loci); st.bytes_file += sk.bytes_file;
+    st.n_direct_io += sk.n_direct_io; st.mma_macs += sk.mma_macs;
+    fa.shard_rank = k;
+    ev_f0[size_t(k)] = pooled_event(c, true);
+    ev_fin[size_t(k)] = pooled_event(c, true);
+    TPG_CUDA_OK(cudaEventRecord(ev_f0[size_t(k)], c->s_compute), E);
+    rc = launch_finish(c, fa, c->s_compute, E);
+    if (rc) break;
+    TPG_CUDA_OK(cudaEventRecord(ev_fin[size_t(k)], c->s_compute), E);
+    if (k > 0) rc = start_hand_back(k - 1);   // the previous shell comes home while this one's kernels run
+  }
+  if (rc == TPG_OK) rc = start_hand_back(K - 1);
+  { const int r = join_hand_back(); if (rc == TPG_OK) rc = r; }
+  st.bytes_d2h += hb.bytes;
+  const double ms_host_d2h = hb.ms;
+  cudaError_t e = cudaStreamSynchronize(c->s_compute);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_decode);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_copy);
+  if (rc == TPG_OK) rc = check_err_flag(c, E);
+  if (rc == TPG_OK && e != cudaSuccess) rc = E.fail(TPG_ERR_CUDA, "result shells failed on device: %s", cudaGetErrorString(e));
+  if (rc == TPG_OK) {
+    for (int k = 0; k < K; ++k) {
+      float ms = 0;
+      for (const Ctx::ChunkEv& t : evs[size_t(k)]) {
+        cudaEventElapsedTime(&ms, t.c0, t.c1); st.ms_h2d += ms;
+        cudaEventElapsedTime(&ms, t.d0, t.d1); st.ms_decode += ms;
+        cudaEventElapsedTime(&ms, t.g0, t.g1); st.ms_gram += ms;
+      }
+      cudaEventElapsedTime(&ms, ev_f0[size_t(k)], ev_fin[size_t(k)]); st.ms_finish += ms;
+    }
+    st.ms_d2h = ms_host_d2h;              // host time spent in the hand-back loops (most of it beside the next shell's kernels)
+    st.n_result_shells = K;
+  }
+  st.n_launches = c->launches - l0;
+  st.ms_total = now_ms() - t_begin;
+  return rc;
+}
+
 static int pairwise_many_on(Ctx* c, const tpg_job* job, const int32_t* stats, int nstats, tpg_result* results,
                             const Err& E, const int32_t* group_sorted = nullptr, uint64_t group_sig = 0) {
   if (job->shard_mode == TPG_SHARD_LOCI && job->shard_world > 1)
@@ -1538,6 +1833,9 @@ static int pairwise_many_on(Ctx* c, const tpg_job* job, const int32_t* stats, in
     memset(&results[k].stats, 0, sizeof results[k].stats);
   }
   TPG_CUDA_OK(cudaSetDevice(c->device), E);
+  if (nstats == 1 && !group_sorted) {
+    if (const int K = shells_for(c, job, stats[0], &results[0])) return pairwise_shells(c, job, stats[0], &results[0], K, E);
+  }
   const size_t cbytes = sizeof(int32_t) * size_t(tpg_counts_elems(n));
   const std::string key = group_sorted ? std::string() : counts_cache_key(job);
   int rc = TPG_OK;

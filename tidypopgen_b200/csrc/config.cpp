@@ -66,6 +66,7 @@ void tpg_config_init(tpg_config* c) {
   c->scan_table = env_int("TPG_SCAN_TABLE", 0);
   c->cache_counts = env_set("TPG_CACHE_COUNTS") ? 1 : 0;
   c->cache_genotypes = env_set("TPG_CACHE_GENOTYPES") ? 1 : 0;
+  c->result_shells = env_int("TPG_RESULT_SHELLS", 0);
   c->device_chunk_loci = env_ll("TPG_DEVICE_CHUNK_LOCI", 0);
   c->host_chunk_mb = env_ll("TPG_HOST_CHUNK_MB", 0);
   c->link_gbps = env_f("TPG_LINK_GBPS", 0.0);
@@ -91,6 +92,7 @@ int tpg_config_set(const tpg_config* c, char* err, size_t errlen) {
   if (c->io_mode < 0 || c->io_mode > 2) return fail("io_mode must be 0 (page cache), 1 (O_DIRECT) or 2 (mmap)");
   if (c->host_threads < 0 || c->host_threads > 1024) return fail("host_threads out of range");
   if (c->scan_loci_per_cta < 0) return fail("scan_loci_per_cta must be >= 0");
+  if (c->result_shells < 0 || c->result_shells > 8) return fail("result_shells must be 0 (auto), 1 (off) or 2..8");
   if (c->scan_table < 0 || c->scan_table > 3) return fail("scan_table must be 0 (auto), 1 (lookup table), 2 (16-locus rounds) or 3 (warp per locus)");
   if (c->device_chunk_loci < 0 || c->host_chunk_mb < 0) return fail("chunk sizes must be >= 0");
   if (c->link_gbps < 0 || c->hybrid_factor < 0) return fail("link_gbps / hybrid_factor must be >= 0");

@@ -52,6 +52,14 @@ struct Ctx {
   Slot d_raw[2], d_gat[2], d_planes[2], h_pin[2], h_out[2], d_rows, d_cols, d_counts, d_out[4], d_red, d_owner;
   std::vector<uint8_t> h_owner;    // tile-sharding owner table of owner_key = "nblocks/world" (internal.h)
   std::string owner_key;
+  // result shells (api.cu, pairwise_shells): > 0 makes owner_table() build the shell table — owner = the shell of
+  // max(region of the block row, region of the block column) — instead of the weighted one; bounds in regions
+  int owner_shells = 0;
+  std::vector<int64_t> shell_bounds;
+  bool keep_events = false;        // accumulate_impl appends to the event pools instead of recycling them
+  // d_planes[0] still holds the decoded planes of planes_key (packed image + rows + loci + plane form): the next
+  // accumulate with the same key — the next result shell — multiplies them again without gathering / decoding
+  std::string planes_key;
   // count-matrix cache (tpg_config.cache_counts): d_counts holds all four products of the job
   // described by counts_key (file identity + indices); empty = nothing cached
   std::string counts_key;
