@@ -397,6 +397,12 @@ enum { TPG_MAT_DD = 0, TPG_MAT_NN = 1, TPG_MAT_HH = 2, TPG_MAT_HN = 3 };
  * 240- / 480-column tiles of the 4-bit Gram kernels) assigned by weight, largest first to the least loaded
  * rank, while a rank gets at least 8 of them; else 1024 x 1024 (512, 256) dealt round-robin.  Host only. */
 int32_t tpg_tile_owner(int64_t n, int64_t bi, int64_t bj, int32_t shard_world);
+/* Result shells (tpg_config.result_shells): how a whole-file job on n individuals would cut its n x n result —
+ * shells = 0 asks for the automatic count (6, 4 or 3, as many as the 3840-wide regions allow).  Returns the number of
+ * shells K (0 = the result comes home in one piece) and writes K + 1 bounds: shell k holds the entries (i, j) with
+ * bounds[k] <= max(i, j) < bounds[k + 1] (a top-left square, then L-shaped rims).  Geometry only; whether a job
+ * uses them also depends on its source, flags and the free HBM.  Host only. */
+int32_t tpg_result_shell_bounds(int64_t n, int32_t shells, int64_t* bounds /* >= 9 entries */);
 int64_t tpg_counts_ld(int64_t n);       /* n rounded up to the tile multiple       */
 int64_t tpg_counts_elems(int64_t n);    /* TPG_NUM_COUNT_MATS * ld * ld            */
 

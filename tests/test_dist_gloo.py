@@ -168,3 +168,25 @@ def test_partitions_cover_exactly():
     assert tdist.shard_region_blocks(196, 8) == 15 and tdist.shard_region_blocks(79, 8) == 4
     assert tdist.shard_region_blocks(24, 8) == 2 and tdist.shard_region_blocks(4, 2) == 1
     assert tdist.choose_mode(929, 8) == "loci" and tdist.choose_mode(50000, 8) == "tiles"
+
+
+def test_result_shell_geometry():
+    """tpg_result_shell_bounds: nested shells on 3840-wide region boundaries — a first square of ~45 % of the area,
+    rims of equal area, as many shells (6, 4, 3) as the regions allow; small matrices come home in one piece."""
+    import ctypes as C
+    from tidypopgen_b200 import _lib as L
+    lib = L.lib()
+    b = (C.c_int64 * 9)()
+    for n in (100, 5000, 20000, 23000):
+        assert lib.tpg_result_shell_bounds(n, 0, b) == 0, n
+    assert lib.tpg_result_shell_bounds(27136 + 77, 0, b) == 4
+    assert lib.tpg_result_shell_bounds(27136 + 77, 6, b) == 0 and lib.tpg_result_shell_bounds(27136 + 77, 1, b) == 0
+    for n, asked, want in ((50000, 0, 6), (50000, 4, 4), (50000, 3, 3), (35000, 0, 6), (30000, 0, 4), (400000, 8, 8)):
+        K = lib.tpg_result_shell_bounds(n, asked, b)
+        assert K == want, (n, asked, K)
+        bounds = list(b)[: K + 1]
+        assert bounds[0] == 0 and bounds[-1] == n and all(x < y for x, y in zip(bounds, bounds[1:]))
+        assert all(x % 3840 == 0 for x in bounds[:-1])
+        area = [(y * y - x * x) / (n * n) for x, y in zip(bounds, bounds[1:])]
+        assert 0.3 < area[0] < 0.6, area
+        assert abs(sum(area) - 1) < 1e-12 and max(area[1:]) <= 0.4 and (K < 6 or max(area[1:]) < 0.25), area

@@ -179,6 +179,7 @@ SIGNATURES = {
     "tpg_release": (None, [C.c_int]),
     "tpg_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "tpg_tile_owner": (C.c_int32, [C.c_int64, C.c_int64, C.c_int64, C.c_int32]),
+    "tpg_result_shell_bounds": (C.c_int32, [C.c_int64, C.c_int32, C.c_void_p]),
     "tpg_counts_ld": (C.c_int64, [C.c_int64]),
     "tpg_counts_elems": (C.c_int64, [C.c_int64]),
     "tpg_accumulate": (C.c_int, [C.c_void_p, C.POINTER(Job), C.c_void_p, C.POINTER(Stats)] + _ERR),

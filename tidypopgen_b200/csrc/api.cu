@@ -179,6 +179,7 @@ void build_owner_table(int64_t nblocks, int world, std::vector<uint8_t>* out) {
 // Result shells (pairwise_shells): the regions are cut into `shells` nested groups — the first one a top-left square
 // holding `first_frac` of the area, the others L-shaped rims of equal area — and a block belongs to the shell of
 // max(region of its row, region of its column).  Same table layout as build_owner_table.
+constexpr double kShellFirstFrac = 0.45;   // shell 0's share of the area: about what the Gram kernels do while the host reads and packs the file
 static void build_shell_table(int64_t nblocks, int shells, double first_frac, std::vector<uint8_t>* out, std::vector<int64_t>* bounds) {
   out->clear();
   bounds->clear();
@@ -210,7 +211,7 @@ int owner_table(Ctx* ctx, int64_t n_pad, int world, const uint8_t** host, const 
   char key[64];
   snprintf(key, sizeof key, "%s%lld/%d", ctx->owner_shells > 0 ? "shells:" : "", (long long)nblocks, world);
   if (ctx->owner_key != key) {
-    if (ctx->owner_shells > 0) build_shell_table(nblocks, world, 0.45, &ctx->h_owner, &ctx->shell_bounds);
+    if (ctx->owner_shells > 0) build_shell_table(nblocks, world, kShellFirstFrac, &ctx->h_owner, &ctx->shell_bounds);
     else build_owner_table(nblocks, world, &ctx->h_owner);
     if (!ctx->h_owner.empty()) {
       int rc = ensure_slot(&ctx->d_owner, ctx->h_owner.size(), false, "owner table", E);
@@ -1634,6 +1635,16 @@ static int rect_to_host(Ctx* ctx, cudaStream_t stream, const double* const* dev,
   return TPG_OK;
 }
 
+// Shells need the 3840-wide ownership regions (shard_region_blocks): as many as they allow, or exactly `asked`.
+static int shell_count(int64_t nblocks, int asked) {
+  for (int cand : {6, 4, 3}) {
+    if (asked >= 2) cand = asked;
+    if (shard_region_blocks(nblocks, cand) == 15 && (nblocks + 14) / 15 >= cand) return cand;
+    if (asked >= 2) break;
+  }
+  return 0;
+}
+
 // How many shells this job's result comes home in (0 = the ordinary path).
 static int shells_for(Ctx* c, const tpg_job* job, int stat, const tpg_result* res) {
   const tpg_config C = cfg();
@@ -1644,12 +1655,7 @@ static int shells_for(Ctx* c, const tpg_job* job, int stat, const tpg_result* re
   if (job->flags & (TPG_FLAG_PLANES_K_MAJOR | TPG_FLAG_NO_PACK | TPG_FLAG_GRAM_1CTA | TPG_FLAG_NO_OVERLAP)) return 0;
   if (C.pack_mode == 1 || C.no_compact || C.cache_counts || C.gram_ctas == 1) return 0;
   const int64_t n = job->nrow_total, nblocks = round_up(n, kRowPad) / 256;
-  int K = 0;                                 // needs the 3840-wide ownership regions: as many shells as they allow
-  for (int cand : {6, 4, 3}) {
-    if (C.result_shells >= 2) cand = C.result_shells;
-    if (shard_region_blocks(nblocks, cand) == 15 && (nblocks + 14) / 15 >= cand) { K = cand; break; }
-    if (C.result_shells >= 2) break;
-  }
+  const int K = shell_count(nblocks, C.result_shells);
   if (!K) return 0;
   if (!gather_pack_fits((n + 3) / 4)) return 0;
   // room for the packed image beside everything a phase-B shell holds at once
@@ -1907,6 +1913,19 @@ int64_t tpg_split_len(int64_t m, int64_t block_size, int64_t* lower, int64_t* up
 }
 
 int64_t tpg_as_pad_count(int64_t m, int64_t block_size) { return as_pad_count(m, block_size); }
+
+int32_t tpg_result_shell_bounds(int64_t n, int32_t shells, int64_t* bounds) {
+  if (n <= 0 || !bounds || shells == 1 || shells < 0 || shells > 8) return 0;
+  const int64_t nblocks = tpg::round_up(n, tpg::kRowPad) / 256;
+  const int K = tpg::shell_count(nblocks, shells);
+  if (!K) return 0;
+  std::vector<uint8_t> table;
+  std::vector<int64_t> b;
+  tpg::build_shell_table(nblocks, K, tpg::kShellFirstFrac, &table, &b);
+  if (int(b.size()) != K + 1) return 0;
+  for (int k = 0; k <= K; ++k) bounds[k] = std::min<int64_t>(n, b[size_t(k)] * 15 * 256);
+  return K;
+}
 
 int32_t tpg_tile_owner(int64_t n, int64_t bi, int64_t bj, int32_t world) {
   if (n <= 0 || world <= 1) return 0;
