@@ -70,7 +70,9 @@ def test_config_roundtrip_and_validation(tpg_cfg):
     got = tpg_cfg(gram_route=1, io_mode=1, host_threads=3, link_gbps=12.5, device_chunk_loci=4096)
     assert (got["gram_route"], got["io_mode"], got["host_threads"], got["link_gbps"], got["device_chunk_loci"]) == (1, 1, 3, 12.5, 4096)
     assert tpg_cfg() == got
-    for bad in ({"gram_route": 7}, {"pack_mode": 3}, {"io_mode": -1}, {"host_threads": -2}, {"link_gbps": -1.0}):
+    assert base["cache_genotypes"] == 0 and base["result_shells"] == 0 and base["scan_table"] == 0
+    for bad in ({"gram_route": 7}, {"pack_mode": 3}, {"io_mode": -1}, {"host_threads": -2}, {"link_gbps": -1.0},
+                {"result_shells": 9}, {"result_shells": -1}, {"scan_table": 4}):
         with pytest.raises(L.TpgError) as ei:
             tpg_cfg(**bad)
         assert ei.value.code == L.ERR_ARG
