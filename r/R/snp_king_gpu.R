@@ -23,6 +23,13 @@ tpg_gpu_config <- function() {
   invisible(NULL)
 }
 
+# Drops the buffers and caches the backend keeps on the GPUs (after a FBM was rewritten in place, or to give the
+# memory back): tpg_gpu_release()
+tpg_gpu_release <- function(devices = tpg_gpu_devices()) {
+  gpu_release(as.integer(devices))
+  invisible(NULL)
+}
+
 snp_king <- function(
   X, # nolint start
   ind.row = bigstatsr::rows_along(X),

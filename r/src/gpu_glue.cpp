@@ -85,6 +85,13 @@ void gpu_set_config(List opts) {
   if (tpg_config_set(&c, err, sizeof err) != TPG_OK) stop("tidypopgen GPU backend: %s", err);
 }
 
+// Frees what the library keeps on the given devices between jobs — staging and plane buffers, the count-matrix
+// and genotype caches (tpg_config.cache_counts / cache_genotypes).  Call it after rewriting a FBM in place.
+// [[Rcpp::export]]
+void gpu_release(const IntegerVector& devices) {
+  for (long k = 0; k < devices.size(); ++k) tpg_release(devices.begin()[k]);
+}
+
 // snp_king(): returns the n x n KING-robust matrix (R/snp_king.R:32-103).
 // [[Rcpp::export]]
 NumericMatrix gpu_snp_king(Environment BM, const IntegerVector& rowInd, const IntegerVector& colInd,
