@@ -1757,7 +1757,7 @@ static int pairwise_shells(Ctx* c, const tpg_job* job, int stat, tpg_result* res
     if (r) return r;
     const int64_t ca = std::min(n, c->shell_bounds[size_t(k)] * 15 * 256), cb = std::min(n, c->shell_bounds[size_t(k) + 1] * 15 * 256);
     const cudaEvent_t ready = ev_fin[size_t(k)];
-    hb.th = std::thread([c, &hb, dev, host, n, ca, cb, ready]() {
+    auto body = [c, &hb, dev, host, n, ca, cb, ready]() {
       Err Et{hb.err, sizeof hb.err};
       const double t0 = now_ms();
       if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamWaitEvent(c->s_copy, ready, 0) != cudaSuccess) {
@@ -1768,7 +1768,12 @@ static int pairwise_shells(Ctx* c, const tpg_job* job, int stat, tpg_result* res
       if (r2 == TPG_OK) r2 = rect_to_host(c, c->s_copy, dev, host, 4, n, ca, cb, 0, ca, &hb.bytes, Et);
       hb.rc = r2;
       hb.ms += now_ms() - t0;
-    });
+    };
+    try {
+      hb.th = std::thread(body);
+    } catch (const std::exception&) {   // no thread to be had: hand back on this one
+      body();
+    }
     return TPG_OK;
   };
   for (int k = 0; k < K && rc == TPG_OK; ++k) {
